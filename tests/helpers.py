@@ -1,0 +1,66 @@
+"""Shared test helpers: seeded synthetic weights, twist sets, fixtures.  No reference access."""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+def synth_state_dict(seed, obs_size, emb, hidden, n_act):
+    """Seeded N(0, 0.05^2) weights, small uniform biases (same generator as gen_golden.py)."""
+    g = np.random.default_rng(seed)
+    f = lambda *s: (g.standard_normal(s) * 0.05).astype(np.float32)
+    b = lambda n: g.uniform(-0.05, 0.05, size=n).astype(np.float32)
+    return {"embeddings.weight": f(emb, obs_size), "embeddings.bias": b(emb),
+            "common.0.weight": f(hidden, emb), "common.0.bias": b(hidden),
+            "action.0.weight": f(n_act, hidden), "action.0.bias": b(n_act),
+            "value.0.weight": f(1, hidden), "value.0.bias": b(1)}
+
+
+def transpose_twists(w):
+    """{identity, main-diagonal transpose} twist set for a square w x w puzzle."""
+    N = w * w
+    T = [(i % w) * w + (i // w) for i in range(N)]
+    ident = list(range(N * N))
+    tw = [0] * (N * N)
+    for i in range(N):
+        for v in range(N):
+            tw[i * N + v] = T[i] * N + T[v]
+    return [ident, tw], [[0, 1, 2, 3], [1, 0, 3, 2]]
+
+
+def trained15():
+    z = np.load(GOLDEN / "policy15_trained.npz")
+    sd = {k[2:]: z[k] for k in z.files if k.startswith("w.")}
+    return z, sd
+
+
+def replays():
+    return json.loads((GOLDEN / "puzzle_replays.json").read_text())
+
+
+def obs_from_states(states):
+    """u8 board [n, N] -> sparse one-hot indices [n, N] (envs/puzzle.rs:183-185)."""
+    s = np.asarray(states).astype(np.int32)
+    N = s.shape[1]
+    return np.arange(N, dtype=np.int32)[None, :] * N + s
+
+
+def scramble_states(rng, n, w, h, max_moves):
+    N = w * h
+    states = np.zeros((n, N), dtype=np.uint8)
+    for k in range(n):
+        s = list(range(N)); z = 0
+        for a in rng.integers(0, 4, size=int(rng.integers(0, max_moves + 1))):
+            x, y = z % w, z // w
+            if a == 0 and x > 0: t = z - 1
+            elif a == 1 and y > 0: t = z - w
+            elif a == 2 and x < w - 1: t = z + 1
+            elif a == 3 and y < h - 1: t = z + w
+            else: continue
+            s[z] = s[t]; s[t] = 0; z = t
+        states[k] = s
+    return states

@@ -1,0 +1,236 @@
+/*
+ * twisterl_b200.h -- C ABI of the B200-native rollout engine for twisteRL.
+ *
+ * This is the drop-in boundary for the reference's Rust data-collection path.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference checkout).
+ * A Rust shim (`extern "C"` block + `impl Collector for B200Collector`) binds it 1:1 -- see
+ * INTEGRATION.md; in this repository the host side above it is Python (the twisterl_b200 package),
+ * mirroring the PyO3 module `twisterl.twisterl.{env,nn,collector}`.
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures; device pointers travel as `void*`/typed
+ *     pointers documented "device"; everything else is a HOST pointer.
+ *   - every function returns TWR_OK (0) or a negative twr_status; the message is in
+ *     twr_last_error() (thread-local), which the host maps to RuntimeError exactly like
+ *     rust/src/python_interface/error_mapping.rs:29-33.
+ *   - one engine per CUDA device; an engine is used from one host thread at a time.
+ *   - there is NO CPU fallback: without a CUDA device twr_engine_create fails.
+ *
+ * RNG contract (shared with oracle/twr_oracle.h): Philox4x32-10, key = 64-bit seed,
+ * counter = (global_env_id, index, kind, collect_id); kinds: 0 reset, 1 twist pick, 2 action
+ * sampling.  The reference itself is unseedable (rand::thread_rng, rl/evaluate.rs:29).
+ */
+#ifndef TWISTERL_B200_H
+#define TWISTERL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TWR_ABI_VERSION 1
+
+typedef enum {
+    TWR_OK = 0,
+    TWR_ERR_INVALID = -1,     /* bad argument */
+    TWR_ERR_UNSUPPORTED = -2, /* env / policy shape the device path does not implement */
+    TWR_ERR_CUDA = -3,        /* CUDA runtime failure (no device, launch error, OOM) */
+    TWR_ERR_STATE = -4        /* call order (e.g. to_host before collect) */
+} twr_status;
+
+typedef enum { TWR_ENV_PUZZLE = 0, TWR_ENV_GRIDWORLD = 1 } twr_env_kind;
+
+/* arithmetic of the policy forward (kernel K2) */
+typedef enum {
+    TWR_PREC_FP32 = 0,  /* SIMT fp32 FMA; parity bar 1e-5 */
+    TWR_PREC_F16X2 = 1  /* tcgen05, operands split into fp16 hi+lo, fp32 TMEM accumulate; bar 1e-3 */
+} twr_precision;
+
+typedef struct twr_engine twr_engine;
+typedef struct twr_policy twr_policy;
+typedef struct twr_envs twr_envs;
+
+int         twr_abi_version(void);
+const char* twr_last_error(void);
+/* number of CUDA devices visible (0 when none / no driver); never fails */
+int         twr_device_count(void);
+
+/* ------------------------------------------------------------------ engine --- */
+typedef struct {
+    int32_t  device;      /* CUDA ordinal */
+    int32_t  precision;   /* twr_precision */
+    uint64_t seed;        /* Philox key */
+    int32_t  rank, world; /* env shard of this engine: global env id = rank*num_episodes + e */
+    void*    stream;      /* cudaStream_t to launch on, NULL = engine-owned stream */
+} twr_engine_cfg;
+
+int  twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out);
+void twr_engine_destroy(twr_engine* e);
+int  twr_engine_synchronize(twr_engine* e);
+/* kernels launched by this engine since creation (bench.py reports the delta as gpu_launches) */
+int64_t twr_engine_launch_count(const twr_engine* e);
+
+/* --------------------------------------------------------------------- env --- */
+/* Device-side equivalent of a `Box<dyn Env>` (rust/src/rl/env.rs:18-66): the constructor
+ * arguments of envs::Puzzle (rust/src/envs/puzzle.rs:34-42, python_interface/env.rs:124-134)
+ * or of grid_world::GridWorld (examples/grid_world/src/lib.rs:23-41) plus its difficulty. */
+typedef struct {
+    int32_t kind;        /* twr_env_kind */
+    int32_t width, height;
+    int32_t difficulty;
+    int32_t depth_slope; /* puzzle */
+    int32_t max_depth;   /* puzzle: max_depth; grid_world: max_steps */
+} twr_env_spec;
+
+/* ------------------------------------------------------------------ policy --- */
+/* One Linear as nn.Linear(weights_vector, bias_vector, apply_relu) receives it
+ * (rust/src/python_interface/layers.rs:19-33): weights = W.T.flatten(), w[i*out + o] == W[o][i]. */
+typedef struct {
+    const float* weights; /* [in][out] */
+    const float* bias;    /* [out] */
+    int32_t in, out, apply_relu;
+} twr_linear_desc;
+
+/* nn.Policy(embeddings, common, action_net, value_net, obs_perms, act_perms)
+ * (rust/src/python_interface/policy.rs:27-31, rust/src/nn/policy.rs:20-32), in the layouts
+ * `BasicPolicy.to_rust()` produces (src/twisterl/nn/utils.py:17-59). */
+typedef struct {
+    const float* emb_vectors;  /* [obs_size][emb_size]  (EmbeddingBag vec_vectors) */
+    const float* emb_bias;     /* [emb_size] */
+    int32_t obs_size, emb_size, emb_apply_relu;
+    int32_t obs_shape[2], obs_shape_len, conv_dim; /* EmbeddingBag obs_shape / conv_dim */
+    const twr_linear_desc* common;     int32_t n_common;
+    const twr_linear_desc* action_net; int32_t n_action;
+    const twr_linear_desc* value_net;  int32_t n_value;
+    const int32_t* obs_perms;  /* [n_perms][obs_size] or NULL */
+    const int32_t* act_perms;  /* [n_perms][num_actions] or NULL */
+    int32_t n_perms;
+} twr_policy_desc;
+
+/* Uploads the weights (H2D) and builds the device-side operand layouts.  The device path
+ * implements the BasicPolicy family the three reference configs use: 1-D EmbeddingBag + ReLU,
+ * exactly one common Linear+ReLU (width 64..256, multiple of 64), single-Linear action and
+ * value heads, <= 4 actions.  Anything else returns TWR_ERR_UNSUPPORTED. */
+int  twr_policy_create(twr_engine* e, const twr_policy_desc* desc, twr_policy** out);
+/* In-place refresh with the same shapes (replaces rebuilding nn.Policy every iteration,
+ * src/twisterl/rl/algorithm.py:91-93). */
+int  twr_policy_update(twr_policy* p, const twr_policy_desc* desc);
+/* Flat fp32 parameter blob: [emb_vectors][emb_bias][common w][common b][action w][action b]
+ * [value w][value b], each in the layout above.  update_from_device takes a DEVICE pointer
+ * (e.g. the buffer an NCCL broadcast just filled). */
+int64_t twr_policy_blob_floats(const twr_policy* p);
+int  twr_policy_update_from_device(twr_policy* p, const float* d_blob);
+int  twr_policy_blob_device_ptr(twr_policy* p, float** d_blob);
+void twr_policy_destroy(twr_policy* p);
+
+/* ------------------------------------------------- batched env (parity API) --- */
+/* n independent envs in structure-of-arrays form on the device; the methods are the Env trait
+ * (rust/src/rl/env.rs:18-66) applied to all n at once. */
+int  twr_envs_create(twr_engine* e, const twr_env_spec* spec, int64_t n, twr_envs** out);
+void twr_envs_destroy(twr_envs* v);
+int  twr_envs_set_difficulty(twr_envs* v, int32_t difficulty);
+/* states: [n][width*height] boards (Env::set_state) */
+int  twr_envs_set_state(twr_envs* v, const int64_t* states);
+/* Env::reset for all n, env i drawing from Philox stream (env_id_base + i, *, reset, collect_id) */
+int  twr_envs_reset(twr_envs* v, uint32_t env_id_base, uint32_t collect_id);
+/* Env::step with forced actions[n] */
+int  twr_envs_step(twr_envs* v, const int32_t* actions);
+int  twr_envs_get_state(twr_envs* v, int64_t* states /* [n][cells] */);
+int  twr_envs_observe(twr_envs* v, int32_t* obs /* [n][cells] sparse one-hot indices */);
+int  twr_envs_masks(twr_envs* v, uint8_t* masks /* [n][num_actions] */);
+int  twr_envs_reward(twr_envs* v, float* rewards /* [n] */);
+int  twr_envs_is_final(twr_envs* v, uint8_t* finals /* [n] */);
+int  twr_envs_success(twr_envs* v, uint8_t* success /* [n] */);
+int  twr_envs_depth(twr_envs* v, int32_t* depth /* [n] puzzle depth / grid_world steps_left */);
+
+/* Policy::_raw_predict / forward_with_perm (rust/src/nn/policy.rs:56-100) for all n envs.
+ * perm_idx: [n] twist index per env (-1 = none) or NULL.  apply_masks != 0 writes -1e10 on
+ * masked actions like forward_with_perm.  logits [n][num_actions], values [n]. */
+int  twr_policy_forward(twr_engine* e, const twr_policy* p, twr_envs* v, const int32_t* perm_idx,
+                        int32_t apply_masks, float* logits, float* values);
+
+/* Policy::_raw_predict for n sparse observations given directly: obs [n][n_obs] one-hot indices
+ * (what Env::observe returns), as python_interface/policy.rs:33-44 receives them.  n_obs <= 32. */
+int  twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* obs, int64_t n, int32_t n_obs,
+                            const int32_t* perm_idx, float* logits, float* values);
+
+/* sample_from_logits (rust/src/nn/policy.rs:169-172) for n logit rows, row i using the uniforms
+ * of Philox stream (env_id_base + i, step, sample, collect_id).  uniforms_out may be NULL. */
+int  twr_sample(twr_engine* e, const float* logits, int64_t n, int32_t num_actions,
+                uint32_t env_id_base, uint32_t step, uint32_t collect_id,
+                int32_t* actions, float* uniforms_out /* [n][num_actions] */);
+
+/* per-episode GAE (rust/src/collector/ppo.rs:82-92) over `num_episodes` concatenated episodes;
+ * offsets has num_episodes+1 entries. */
+int  twr_gae(twr_engine* e, const float* rewards, const float* values, const int64_t* offsets,
+             int64_t num_episodes, float gamma, float lambda, float* advs, float* rets);
+
+/* ----------------------------------------------------------------- collect --- */
+typedef struct {
+    int64_t n_records;      /* R = sum of episode lengths */
+    int64_t num_episodes;
+    int32_t n_cells, num_actions;
+    int64_t successes;      /* episodes that ended with Env::success() */
+    double  reward_sum;     /* sum over episodes of the terminal-state reward */
+    /* DEVICE pointers, owned by the engine, valid until the next collect / destroy.
+     * Episodes are concatenated in the reference's merge order [last, 0, 1, ..., n-2]
+     * (rust/src/collector/collector.rs:40-46). */
+    const uint16_t* obs;      /* [R][n_cells]  CollectedData.obs (sparse one-hot indices) */
+    const float*    logits;   /* [R][num_actions]  masked logits, CollectedData.logits */
+    const float*    values;   /* [R] */
+    const float*    rewards;  /* [R] */
+    const float*    advs;     /* [R]  additional_data["advs"] */
+    const float*    rets;     /* [R]  additional_data["rets"] */
+    const uint8_t*  actions;  /* [R] */
+    const int8_t*   perms;    /* [R]  -1 == None */
+    const int32_t*  ep_len;   /* [num_episodes] by episode id */
+} twr_collected;
+
+/* PPOCollector::collect (rust/src/collector/ppo.rs:108-126; PyBaseCollector.collect,
+ * rust/src/python_interface/collector.rs:147-151).  Episode e of this call draws from Philox
+ * env id rank*num_episodes + e and collect_id = number of collects this engine has run
+ * (or the value set by twr_engine_set_collect_id). */
+int  twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p,
+                     int64_t num_episodes, float gamma, float lambda, twr_collected* out);
+int  twr_engine_set_collect_id(twr_engine* e, uint32_t collect_id);
+
+/* Host mirror of twr_collected; the caller owns every buffer (capacity in records). */
+typedef struct {
+    int64_t   capacity;     /* records each buffer can hold */
+    uint16_t* obs;          /* [capacity][n_cells] */
+    float*    logits;       /* [capacity][num_actions] */
+    float*    values;
+    float*    rewards;
+    float*    advs;
+    float*    rets;
+    uint8_t*  actions;
+    int8_t*   perms;
+    int32_t*  ep_len;       /* [num_episodes] or NULL */
+} twr_host_buffers;
+
+/* D2H of the last collect into caller buffers (any field may be NULL to skip it) */
+int  twr_collected_to_host(twr_engine* e, const twr_host_buffers* dst);
+/* upper bound of records a collect of num_episodes can produce (episodes * (horizon+1)) */
+int64_t twr_max_records(const twr_env_spec* spec, int64_t num_episodes);
+
+/* End-to-end call with HOST buffers on both sides: uploads the weights in `desc` into `p`
+ * (H2D), collects, and copies the result into `dst` (D2H).  This is what a Rust
+ * `impl Collector` would call; bench.py times it as `e2e`. */
+int  twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
+                          const twr_policy_desc* desc, int64_t num_episodes, float gamma, float lambda,
+                          const twr_host_buffers* dst, twr_collected* out);
+
+/* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for the e2e path */
+int  twr_host_alloc(void** ptr, int64_t bytes);
+void twr_host_free(void* ptr);
+
+/* device time in ms of the last collect's forward kernels / all its kernels (CUDA events on
+ * the engine stream); used by bench.py for the roofline line */
+int  twr_engine_set_timing(twr_engine* e, int32_t enabled);
+int  twr_engine_last_timing(const twr_engine* e, float* forward_ms, float* total_ms, int64_t* forward_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TWISTERL_B200_H */

@@ -1,0 +1,415 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs,
+against the committed golden fixtures, and -- at BASELINE.json's full size -- through size-independent
+properties.  Bars: bit-exact for env transitions / observations / masks / rewards / twists / episode
+layout; |d| <= 1e-5 * max(1,|ref|) for fp32 logits and values (1e-3 for the f16x2 tensor-core forward);
+1e-5 for GAE (the kernel is in fact bit-exact); chi-square p > 0.001 for sampled actions."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, obs_from_states, replays, scramble_states, synth_state_dict, trained15, transpose_twists
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+PRECISION = os.environ.get("TWISTERL_B200_PRECISION", "fp32")
+TOL = 1e-5 if PRECISION == "fp32" else 1e-3
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import twisterl_b200 as tw
+    e = tw.Engine(device=0, precision=PRECISION, seed=0xABCDEF12345)
+    yield e
+    e.close()
+
+
+def _spec(o):
+    from twisterl_b200 import _lib
+    return _lib.EnvSpec(o.kind, o.width, o.height, o.difficulty, o.depth_slope, o.max_depth)
+
+
+def _close(a, ref, tol):
+    return float((np.abs(a - ref) / np.maximum(1.0, np.abs(ref))).max(initial=0.0)) <= tol
+
+
+# ------------------------------------------------------------------------ K1 ---
+@pytest.mark.parametrize("key,w", [("puzzle8_35", 3), ("puzzle8_123", 3)])
+def test_env_notebook_replays(eng, key, w):
+    from twisterl_b200.env import EnvBatch
+    r = replays()[key]
+    b = EnvBatch(_spec(orc.puzzle_spec(w, w, 1, 2, 256)), 1, eng)
+    b.set_state([r["start"]])
+    assert b.depth()[0] == 256
+    for a, board in zip(r["actions"], r["boards"][1:]):
+        b.step([a])
+        assert b.get_state()[0].tolist() == board
+        assert b.observe()[0].tolist() == [i * 9 + v for i, v in enumerate(board)]
+    assert b.success()[0] and b.is_final()[0] and b.reward()[0] == 1.0
+
+
+def test_env_gridworld_notebook_replay(eng):
+    from twisterl_b200.env import EnvBatch
+    r = replays()["gridworld_4"]
+    b = EnvBatch(_spec(orc.gridworld_spec(5, 5, 64, 1)), 1, eng)
+    b.set_state([r["start"]])
+    for a, board in zip(r["actions"], r["boards"][1:]):
+        b.step([a])
+        assert b.get_state()[0].tolist() == board
+    assert b.success()[0] and b.reward()[0] == 1.0 and b.depth()[0] == 60
+
+
+SPECS = [orc.puzzle_spec(4, 4, 128, 2, 256), orc.puzzle_spec(3, 3, 32, 2, 256), orc.puzzle_spec(2, 2, 3, 1, 10),
+         orc.puzzle_spec(3, 2, 9, 3, 40), orc.puzzle_spec(4, 4, 0, 2, 256), orc.puzzle_spec(4, 4, 1, 2, 256),
+         orc.gridworld_spec(5, 5, 64, 10), orc.gridworld_spec(4, 3, 7, 2), orc.gridworld_spec(5, 5, 64, 1)]
+
+
+@pytest.mark.parametrize("ospec", SPECS, ids=lambda s: f"k{s.kind}_{s.width}x{s.height}_d{s.difficulty}")
+def test_env_reset_and_forced_steps_bit_exact(eng, ospec):
+    """reset from the shared Philox stream, then 40 forced (random, often illegal) actions: state,
+    observation, masks, reward, final flag, success and depth must equal the oracle's at every step."""
+    from twisterl_b200.env import EnvBatch
+    n, steps = 257, 40
+    rng = np.random.default_rng(ospec.width * 100 + ospec.difficulty)
+    b = EnvBatch(_spec(ospec), n, eng)
+    b.reset(env_id_base=1000, collect_id=3)
+    envs = [orc.Env(ospec) for _ in range(n)]
+    for i, e in enumerate(envs):
+        e.reset(seed=eng.seed, env_id=1000 + i, collect_id=3)
+
+    def compare(tag):
+        st, ob, mk = b.get_state(), b.observe(), b.masks()
+        rw, fi, su, dp = b.reward(), b.is_final(), b.success(), b.depth()
+        for i, e in enumerate(envs):
+            assert st[i].tolist() == e.get_state(), (tag, i)
+            assert ob[i].tolist() == e.observe(), (tag, i)
+            assert mk[i].tolist() == e.masks(), (tag, i)
+            assert rw[i] == np.float32(e.reward()), (tag, i)
+            assert bool(fi[i]) == e.is_final() and bool(su[i]) == e.success(), (tag, i)
+            assert dp[i] == e.depth, (tag, i)
+
+    compare("reset")
+    for t in range(steps):
+        acts = rng.integers(0, 4, size=n)
+        b.step(acts)
+        for e, a in zip(envs, acts):
+            e.step(int(a))
+        if t % 4 == 3 or t < 3:
+            compare(t)
+
+
+def test_env_set_state_edge_cases(eng):
+    from twisterl_b200.env import EnvBatch
+    b = EnvBatch(_spec(orc.puzzle_spec(4, 4, 5, 2, 256)), 3, eng)
+    states = [list(range(16)), [1, 0] + list(range(2, 16)), [5, 1, 2, 3, 4, 0] + list(range(6, 16))]
+    b.set_state(states)
+    assert b.get_state().tolist() == states and b.depth().tolist() == [256] * 3
+    assert b.success().tolist() == [True, False, False]
+    assert b.masks().tolist() == [[False, False, True, True], [True, False, True, True], [True, True, True, True]]
+    with pytest.raises(RuntimeError, match="blank"):
+        b.set_state([[1] * 16] * 3)
+    empty = EnvBatch(_spec(orc.puzzle_spec(4, 4, 5, 2, 256)), 0, eng)
+    assert empty.get_state().shape == (0, 16)
+    empty.reset(); empty.step([])
+    from twisterl_b200 import _lib
+    with pytest.raises(RuntimeError, match="16 cells"):
+        EnvBatch(_lib.EnvSpec(0, 5, 5, 1, 1, 1), 1, eng)
+    with pytest.raises(RuntimeError, match="unknown env kind"):
+        EnvBatch(_lib.EnvSpec(7, 2, 2, 1, 1, 1), 1, eng)
+
+
+# ------------------------------------------------------------------------ K2 ---
+def test_forward_matches_reference_torch_golden(eng):
+    """logits/values of the reference's own torch BasicPolicy on the shipped ppo_puzzle15_v1.pt weights."""
+    from parity import make_policies
+    from twisterl_b200.env import EnvBatch
+    from twisterl_b200.nn import forward_batch
+    z, sd = trained15()
+    pol, opol = make_policies(sd, 256)
+    st = z["states"]
+    b = EnvBatch(_spec(orc.puzzle_spec(4, 4, 1, 2, 256)), len(st), eng)
+    b.set_state(st)
+    logits, values = forward_batch(eng, pol, b)
+    assert _close(logits, z["logits"], TOL) and _close(values, z["values"], TOL)
+    assert _close(logits[0], np.array([-4.4116335, -5.16946, -2.0670972, 0.8337202], np.float32), TOL)
+    # and against the oracle, element by element
+    ref = np.array([np.append(*opol.raw_predict(o)) for o in obs_from_states(st[:128])])
+    assert _close(logits[:128], ref[:, :4], TOL) and _close(values[:128], ref[:, 4], TOL)
+    # masked variant = forward_with_perm
+    ml, _ = forward_batch(eng, pol, b, apply_masks=True)
+    mk = b.masks()
+    assert np.array_equal(ml == np.float32(-1e10), ~mk)
+    assert np.array_equal(ml[mk], logits[mk])
+
+
+def test_forward_twists_match_reference_torch_golden(eng):
+    from parity import make_policies
+    from twisterl_b200.env import EnvBatch
+    from twisterl_b200.nn import forward_batch, forward_obs
+    z, sd = trained15()
+    obs_perms, act_perms = transpose_twists(4)
+    pol, opol = make_policies(sd, 256, obs_perms, act_perms)
+    st = z["states"]
+    b = EnvBatch(_spec(orc.puzzle_spec(4, 4, 1, 2, 256)), len(st), eng)
+    b.set_state(st)
+    logits, values = forward_batch(eng, pol, b, perm_idx=z["twist_perm_idx"])
+    assert _close(logits, z["twist_logits"], TOL) and _close(values, z["twist_values"], TOL)
+    # the direct-observation entry point gives the same numbers
+    l2, v2 = forward_obs(eng, pol, obs_from_states(st), z["twist_perm_idx"])
+    assert np.array_equal(l2, logits) and np.array_equal(v2, values)
+    # twist consistency: value is invariant, logits permute (transpose symmetry of the puzzle)
+    with pytest.raises(RuntimeError, match="perm_idx"):
+        forward_batch(eng, pol, b, perm_idx=np.full(len(st), 2))
+
+
+@pytest.mark.parametrize("name,N,kind", [("puzzle8", 9, 0), ("gridworld", 25, 1)])
+def test_forward_other_config_shapes(eng, name, N, kind):
+    from parity import make_policies
+    from twisterl_b200.env import EnvBatch
+    from twisterl_b200.nn import forward_batch
+    z = np.load(GOLDEN / "policy_synth.npz")
+    sd = synth_state_dict(int(z[f"{name}.seed"]), N * N, 512, int(z[f"{name}.hidden"]), 4)
+    pol, _ = make_policies(sd, N * N)
+    st = z[f"{name}.states"]
+    spec = orc.puzzle_spec(3, 3, 1, 2, 256) if kind == 0 else orc.gridworld_spec(5, 5, 64, 3)
+    b = EnvBatch(_spec(spec), len(st), eng)
+    b.set_state(st)
+    logits, values = forward_batch(eng, pol, b)
+    assert _close(logits, z[f"{name}.logits"], TOL) and _close(values, z[f"{name}.values"], TOL)
+
+
+def test_forward_ragged_batch_sizes(eng):
+    """batch sizes around the 128-env tile: 1, 127, 128, 129, 1000."""
+    from parity import make_policies
+    from twisterl_b200.env import EnvBatch
+    from twisterl_b200.nn import forward_batch
+    z, sd = trained15()
+    pol, _ = make_policies(sd, 256)
+    for n in (1, 127, 128, 129, 1000):
+        st = np.tile(z["states"], (2, 1))[:n]
+        b = EnvBatch(_spec(orc.puzzle_spec(4, 4, 1, 2, 256)), n, eng)
+        b.set_state(st)
+        logits, values = forward_batch(eng, pol, b)
+        ref_l, ref_v = np.tile(z["logits"], (2, 1))[:n], np.tile(z["values"], 2)[:n]
+        assert _close(logits, ref_l, TOL) and _close(values, ref_v, TOL), n
+
+
+def test_policy_scalar_api_and_unsupported_shapes(eng):
+    import twisterl_b200 as tw
+    from parity import make_policies
+    z, sd = trained15()
+    obs_perms, act_perms = transpose_twists(4)
+    pol, opol = make_policies(sd, 256, obs_perms, act_perms)
+    tw.configure(device=0, precision=PRECISION)
+    o = obs_from_states(z["states"])[5].tolist()
+    masks = [True, False, True, True]
+    probs, value = pol.full_predict(o, masks)
+    rp, rv = opol.full_predict(o, masks)
+    assert np.allclose(probs, rp, atol=max(TOL, 1e-5)) and abs(value - rv) <= max(TOL, 1e-5) * max(1, abs(rv))
+    ml, v = pol.forward(o, masks)
+    assert ml[1] == -1e10 and len(ml) == 4
+    deep = tw.nn.Policy(pol.embeddings, tw.nn.Sequential(pol.common.layers * 2), pol.action_net, pol.value_net, [], [])
+    with pytest.raises(RuntimeError, match="one common"):
+        deep.device_handle(eng)
+    conv = tw.nn.Policy(tw.nn.EmbeddingBag(np.zeros((16, 32)), np.zeros(512), True, [16, 16], 0), pol.common,
+                        pol.action_net, pol.value_net, [], [])
+    with pytest.raises(RuntimeError, match="1-D EmbeddingBag"):
+        conv.device_handle(eng)
+
+
+# ------------------------------------------------------------------------ K3 ---
+def _sample(eng, logits, env_id_base, step, cid):
+    import ctypes as C
+    from twisterl_b200 import _lib
+    l = np.ascontiguousarray(logits, dtype=np.float32)
+    n, A = l.shape
+    acts = np.zeros(n, np.int32); u = np.zeros((n, A), np.float32)
+    _lib.check(_lib.load().twr_sample(eng._h, _lib.ptr(l), n, A, env_id_base, step, cid, _lib.ptr(acts), _lib.ptr(u)))
+    return acts, u
+
+
+def test_sample_uses_shared_philox_stream_and_matches_oracle(eng):
+    rng = np.random.default_rng(3)
+    n = 4096
+    logits = rng.normal(0, 2, size=(n, 4)).astype(np.float32)
+    logits[rng.random((n, 4)) < 0.2] = -1e10
+    logits[:, 0][np.all(logits == -1e10, axis=1)] = 0.0
+    acts, u = _sample(eng, logits, 77, 9, 4)
+    key = [eng.seed & 0xFFFFFFFF, eng.seed >> 32]
+    mism = 0
+    for i in range(n):
+        w = orc.philox([77 + i, 9, orc.RNG_SAMPLE, 4], key)
+        ref_u = [orc.u32_to_unit_f32(int(x)) for x in w]
+        assert u[i].tolist() == ref_u                                  # uniforms bit-exact
+        with np.errstate(divide="ignore"):
+            g = np.sort(logits[i].astype(np.float64) - np.log(np.abs(np.log(u[i].astype(np.float64)))))
+        if g[-1] - g[-2] > 1e-4:                                       # libm vs CUDA logf: <= 1 ulp apart
+            mism += orc.sample_from_logits(logits[i], ref_u) != acts[i]
+        assert logits[i, acts[i]] != np.float32(-1e10)                 # a masked action is never sampled
+    assert mism == 0
+
+
+def test_sample_distribution_chi_square(eng):
+    logits = np.tile(np.array([[0.3, -1e10, 1.2, -0.8]], np.float32), (1_000_000, 1))
+    acts, _ = _sample(eng, logits, 0, 0, 0)
+    cnt = np.bincount(acts, minlength=4).astype(np.float64)
+    p = np.exp(np.array([0.3, -np.inf, 1.2, -0.8])); p /= p.sum()
+    assert cnt[1] == 0
+    keep = [0, 2, 3]
+    chi2 = (((cnt[keep] - 1e6 * p[keep]) ** 2) / (1e6 * p[keep])).sum()
+    assert chi2 < 13.82, chi2                                           # p > 0.001 at 2 degrees of freedom
+
+
+# ------------------------------------------------------------------------ K4 ---
+def test_gae_matches_oracle(eng):
+    from twisterl_b200 import _lib
+    rng = np.random.default_rng(5)
+    lens = np.concatenate([[1, 2, 257, 1, 3], rng.integers(1, 258, size=300)])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    R = int(off[-1])
+    r = rng.normal(0, 1, R).astype(np.float32); v = rng.normal(0, 1, R).astype(np.float32)
+    adv = np.zeros(R, np.float32); ret = np.zeros(R, np.float32)
+    _lib.check(_lib.load().twr_gae(eng._h, _lib.ptr(r), _lib.ptr(v), _lib.ptr(off), len(lens), 0.995, 0.995,
+                                   _lib.ptr(adv), _lib.ptr(ret)))
+    for i in range(len(lens)):
+        a, g = orc.gae(r[off[i]:off[i + 1]], v[off[i]:off[i + 1]], 0.995, 0.995)
+        assert np.abs(a - adv[off[i]:off[i + 1]]).max() <= 1e-5 and np.abs(g - ret[off[i]:off[i + 1]]).max() <= 1e-5
+        assert np.array_equal(a, adv[off[i]:off[i + 1]]) and np.array_equal(g, ret[off[i]:off[i + 1]])
+    # known answer derived from collector/ppo.rs:82-92 with r=v=1, gamma=.9, lambda=.95
+    o2 = np.array([0, 2], np.int64); one = np.ones(2, np.float32); a2 = np.zeros(2, np.float32); g2 = np.zeros(2, np.float32)
+    _lib.check(_lib.load().twr_gae(eng._h, _lib.ptr(one), _lib.ptr(one), _lib.ptr(o2), 1, 0.9, 0.95, _lib.ptr(a2), _lib.ptr(g2)))
+    assert np.allclose(g2, [1.9, 1.0], atol=1e-7) and np.allclose(a2, [0.9, 0.0], atol=1e-7)
+
+
+# ------------------------------------------------------------------- collect ---
+CASES = [
+    ("puzzle8", orc.puzzle_spec(3, 3, 6, 2, 256), 81, 256, 700, False),
+    ("puzzle15_d1", orc.puzzle_spec(4, 4, 1, 2, 256), 256, 256, 300, False),
+    ("puzzle15_d32_twists", orc.puzzle_spec(4, 4, 32, 2, 256), 256, 256, 130, True),
+    ("gridworld", orc.gridworld_spec(5, 5, 64, 10), 625, 128, 400, False),
+    ("one_episode", orc.puzzle_spec(4, 4, 4, 2, 256), 256, 256, 1, False),
+]
+
+
+@pytest.mark.parametrize("name,ospec,obs_size,hidden,episodes,twists", CASES, ids=[c[0] for c in CASES])
+def test_collect_replays_through_oracle(eng, name, ospec, obs_size, hidden, episodes, twists):
+    import twisterl_b200 as tw
+    from parity import check_collect_against_oracle, make_policies
+    if obs_size == 256:
+        _, sd = trained15()
+    else:
+        sd = synth_state_dict(21, obs_size, 512, hidden, 4)
+    perms = transpose_twists(4) if twists else ((), ())
+    pol, opol = make_policies(sd, obs_size, *perms)
+    env = (tw.env.Puzzle(ospec.width, ospec.height, ospec.difficulty, ospec.depth_slope, ospec.max_depth)
+           if ospec.kind == 0 else tw.env.GridWorld(ospec.width, ospec.height, ospec.max_depth, ospec.difficulty))
+    col = tw.collector.PPOCollector(episodes, 0.995, 0.995, 32, engine=eng)
+    eng.set_collect_id(11)
+    data = col.collect(env, pol)
+    rep = check_collect_against_oracle(data, ospec, opol, seed=eng.seed, collect_id=11, gamma=0.995, lam=0.995, tol=TOL)
+    assert rep["records"] == len(data.values_array)
+    assert data.stats["episodes"] == episodes and data.stats["records"] == rep["records"]
+    if twists:
+        assert set(np.unique(data.perms_array)) == {0, 1}
+    else:
+        assert (data.perms_array == -1).all()
+    # same call again: collect_id advanced -> different rollouts; pinned id -> identical rollouts
+    eng.set_collect_id(11)
+    again = col.collect(env, pol)
+    assert np.array_equal(again.obs_array, data.obs_array) and np.array_equal(again.actions_array, data.actions_array)
+    assert np.array_equal(again.additional_array("rets"), data.additional_array("rets"))
+    # whole-collect comparison with the oracle collector on the same streams (actions can differ only
+    # where ulp-level logit differences flip a Gumbel near-tie)
+    oc = orc.ppo_collect(ospec, opol, episodes, 0.995, 0.995, seed=eng.seed, collect_id=11)
+    same = sum(int(a == b) for a, b in zip(oc["ep_len"], data.ep_len))
+    assert same >= 0.98 * episodes
+    if oc["n_records"] == rep["records"] and np.array_equal(oc["actions"], data.actions_array):
+        assert np.array_equal(oc["obs"], data.obs_array) and np.array_equal(oc["rewards"], data.rewards_array)
+        assert _close(data.logits_array, oc["logits"], TOL) and np.abs(oc["rets"] - data.additional_array("rets")).max() <= 1e-4
+
+
+def test_collect_reference_semantics(eng):
+    """terminal state recorded, merge order [last, 0..n-2], list-valued drop-in properties."""
+    import twisterl_b200 as tw
+    from parity import make_policies
+    sd = synth_state_dict(2, 4, 512, 64, 4)
+    pol, _ = make_policies(sd, 4)
+    env = tw.env.Puzzle(2, 1, 1, 1, 10)                                # 1 or 2 records per episode
+    col = tw.collector.PPOCollector(num_episodes=64, gamma=0.9, num_cores=1, **{"lambda": 0.95})
+    col._engine = eng
+    d = col.collect(env, pol)
+    assert set(d.ep_len.tolist()) == {1, 2}
+    assert isinstance(d.obs, list) and isinstance(d.obs[0], list) and len(d.obs) == int(d.ep_len.sum())
+    assert set(d.additional_data) == {"advs", "rets"} and len(d.additional_data["rets"]) == len(d.obs)
+    assert d.get_additional_data_item("advs") is not None
+    order = orc.merge_order(64)
+    off = 0
+    for ep in order:                                                   # first chunk is the LAST episode
+        n = int(d.ep_len[ep])
+        last = d.obs_array[off + n - 1].tolist()
+        if n == 2:
+            assert d.rewards_array[off] == np.float32(-0.5 / 10) and last in ([0, 3], [1, 2])
+            assert d.rewards_array[off + 1] in (np.float32(1.0), np.float32(-0.5))
+        else:
+            assert last == [0, 3] and d.rewards_array[off] == 1.0       # scramble no-op: solved at reset
+        off += n
+    with pytest.raises(RuntimeError, match="No data in collected data chunks to merge"):
+        tw.collector.PPOCollector(0, 0.9, 0.9, 1, engine=eng).collect(env, pol)
+    big, _ = make_policies(synth_state_dict(2, 256, 512, 256, 4), 256)
+    with pytest.raises(RuntimeError, match="obs_size"):
+        col.collect(env, big)
+
+
+def test_collect_full_size_properties(eng):
+    """BASELINE config 2 size (65 536 envs, puzzle15, difficulty 128): size-independent properties."""
+    import twisterl_b200 as tw
+    from parity import check_collect_against_oracle, make_policies
+    sd = synth_state_dict(0, 256, 512, 256, 4)
+    pol, opol = make_policies(sd, 256)
+    ospec = orc.puzzle_spec(4, 4, 128, 2, 256)
+    env = tw.env.Puzzle(4, 4, 128, 2, 256)
+    E = 65536
+    col = tw.collector.PPOCollector(E, 0.995, 0.995, 32, engine=eng)
+    eng.set_collect_id(5)
+    d = col.collect(env, pol)
+    L, R = d.ep_len.astype(np.int64), len(d.values_array)
+    assert L.min() >= 1 and L.max() <= 257 and L.sum() == R == d.stats["records"]
+    obs = d.obs_array.astype(np.int64)
+    tiles = obs - np.arange(16) * 16
+    assert tiles.min() >= 0 and tiles.max() <= 15
+    assert (np.sort(tiles, axis=1) == np.arange(16)).all()              # every record is a permutation board
+    order = orc.merge_order(E)
+    starts = np.concatenate([[0], np.cumsum(L[order])])[:-1]
+    ends = starts + L[order] - 1
+    solved = (tiles == np.arange(16)).all(axis=1)
+    rew = d.rewards_array
+    assert set(np.unique(rew)) <= {np.float32(1.0), np.float32(-0.5), np.float32(-0.5 / 256)}
+    inner = np.ones(R, bool); inner[ends] = False
+    assert not solved[inner].any() and (rew[inner] == np.float32(-0.5 / 256)).all()
+    assert (solved[ends] | (L[order] == 257)).all()                     # episodes end solved or out of budget
+    assert (rew[ends] == np.where(solved[ends], np.float32(1.0), np.float32(-0.5))).all()
+    assert int(solved[ends].sum()) == d.stats["successes"]
+    # consecutive records inside an episode differ by one legal blank move matching the recorded action
+    blank = np.argmax(tiles == 0, axis=1)
+    nxt = np.where(inner)[0]
+    delta = blank[nxt + 1] - blank[nxt]
+    act = d.actions_array.astype(np.int64)[nxt]
+    exp = np.array([-1, -4, 1, 4])[act]
+    legal = np.stack([blank[nxt] % 4 > 0, blank[nxt] // 4 > 0, blank[nxt] % 4 < 3, blank[nxt] // 4 < 3], 1)[np.arange(len(nxt)), act]
+    assert (legal).all(), "a masked (illegal) action was sampled"
+    assert (delta == exp).all()
+    changed = (tiles[nxt + 1] != tiles[nxt]).sum(axis=1)
+    assert (changed == 2).all()
+    # masked logits exactly where the move is illegal
+    bl = blank
+    masks = np.stack([bl % 4 > 0, bl // 4 > 0, bl % 4 < 3, bl // 4 < 3], 1)
+    assert np.array_equal(d.logits_array == np.float32(-1e10), ~masks)
+    # GAE identity on every record: rets - advs == values ; terminal rets == rewards
+    adv, ret = d.additional_array("advs"), d.additional_array("rets")
+    assert np.abs((ret - adv) - d.values_array).max() <= 1e-5
+    assert np.array_equal(ret[ends], rew[ends])
+    # and the full replay check on the first 24 episodes in merge order
+    rep = check_collect_against_oracle(d, ospec, opol, seed=eng.seed, collect_id=5, gamma=0.995, lam=0.995, tol=TOL,
+                                       max_episodes=24)
+    assert rep["records"] > 24

@@ -1,0 +1,164 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the host
+mirror keeps the reference's names / argument meaning / error behaviour, and the product fails loudly
+without a CUDA device.  No compute calls are made here."""
+import re
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from twisterl_b200 import _lib
+    L = _lib.load()
+    header = (ROOT / "include" / "twisterl_b200.h").read_text()
+    declared = set(re.findall(r"\b(twr_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/twisterl_b200.h but not exported"
+    assert declared == set(_lib.SYMBOLS)
+    assert L.twr_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    import twisterl_b200 as tw
+    assert tw._lib.load().twr_device_count() == 0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tw.Engine()
+    p = tw.env.Puzzle(3, 3, 2, 2, 256)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        p.reset()
+
+
+def test_product_never_imports_the_oracle():
+    for f in list((ROOT / "twisterl_b200").rglob("*.py")) + list((ROOT / "twisterl_b200" / "csrc").glob("*")):
+        txt = f.read_text()
+        assert "oracle" not in txt.replace("oracle/twr_oracle.h", "").replace("the oracle's libm", ""), f
+
+
+def test_env_description_without_device():
+    import twisterl_b200 as tw
+    p = tw.env.Puzzle(4, 4, 1, 2, 256)
+    assert p.obs_shape() == [16, 16] and p.num_actions() == 4 and p.twists() == ([], [])
+    p.difficulty = 7
+    assert p.difficulty == 7
+    g = tw.env.GridWorld(5, 5, 64, 99)
+    assert g.difficulty == 10 and g.obs_shape() == [25, 25]          # clamp to W+H (lib.rs:36)
+    g.difficulty = 3
+    assert g.difficulty == 3
+    with pytest.raises(OverflowError):
+        tw.env.Puzzle(-1, 3, 1, 1, 1)
+    s = tw.env.spec_from_env(p)
+    assert (s.kind, s.width, s.height, s.difficulty, s.depth_slope, s.max_depth) == (0, 4, 4, 7, 2, 256)
+    with pytest.raises(TypeError, match="__extract_env__"):
+        tw.env.spec_from_env(object())
+
+    class Fake:
+        def __extract_env__(self):
+            return 12345
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tw.env.spec_from_env(Fake())
+
+
+def test_pyenv_wrapper_is_rejected_by_collectors():
+    import twisterl_b200 as tw
+
+    class Dummy:                      # the reference's pure-Python DummyEnv (tests/test_all.py:14-29)
+        def num_actions(self): return 2
+        def obs_shape(self): return [2]
+        def reset(self, d): self.d = d
+        def observe(self): return [0]
+        def masks(self): return [True, True]
+        def is_final(self): return True
+        def value(self): return 1.0
+        def next(self, a): pass
+        def set_state(self, s): pass
+    e = tw.env.PyEnv(Dummy())
+    assert e.num_actions() == 2 and e.obs_shape() == [2] and e.twists() == ([], [])
+    e.reset()
+    assert e.observe() == [0] and e.is_final() and e.reward() == 1.0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        tw.env.spec_from_env(e)
+
+
+def test_ppo_collector_constructor_keywords():
+    import twisterl_b200 as tw
+    cfg = {"num_cores": 32, "num_episodes": 1024, "lambda": 0.995, "gamma": 0.99}   # examples/*.json "collecting"
+    c = tw.collector.PPOCollector(**cfg)
+    assert (c.num_episodes, c.gamma, c.lambda_, c.num_cores) == (1024, 0.99, 0.995, 32)
+    c2 = tw.collector.PPOCollector(8, 0.9, 0.95, 1)
+    assert (c2.num_episodes, c2.gamma, c2.lambda_, c2.num_cores) == (8, 0.9, 0.95, 1)
+    with pytest.raises(TypeError):
+        tw.collector.PPOCollector(8, 0.9, 0.95, 1, seed=3)
+    with pytest.raises(TypeError):
+        tw.collector.PPOCollector(8, 0.9)
+    az = tw.collector.AZCollector(num_episodes=4, num_mcts_searches=8, C=1.4, max_expand_depth=2, num_cores=1)
+    with pytest.raises(NotImplementedError):
+        az.collect(None, None)
+
+
+def test_collected_data_mirror():                     # python_interface/collector.rs:24-137
+    import twisterl_b200 as tw
+    CD = tw.collector.CollectedData
+    d1 = CD([[0]], [[0.1]], [0.2], [0.3], [1], [0])
+    d2 = CD([[1]], [[0.4]], [0.5], [0.6], [0])
+    assert d2.perms == [-1]
+    d1.set_additional_data_item("rets", [1.0]); d2.set_additional_data_item("rets", [2.0])
+    d2.merge(d1)                                       # collector.rs:101-126: d2 first, then d1
+    assert d2.actions == [0, 1] and d2.obs == [[1], [0]] and d2.perms == [-1, 0]
+    assert d2.additional_data == {"rets": [2.0, 1.0]} and d2.get_additional_data_item("nope") is None
+    d2.perms = [None, 3]
+    assert d2.perms == [-1, 3]
+    d2.values = [9.0, 8.0]
+    assert d2.values == [9.0, 8.0]
+    a = CD(np.zeros((2, 3), np.uint16), np.zeros((2, 4), np.float32), np.zeros(2, np.float32), np.zeros(2, np.float32),
+           np.zeros(2, np.uint8), np.full(2, -1, np.int8))
+    assert a.obs == [[0, 0, 0], [0, 0, 0]] and a.perms == [-1, -1] and isinstance(a.obs, list)
+
+
+def test_nn_mirror_layouts():                         # python_interface/layers.rs, nn/utils.py:17-59
+    import twisterl_b200 as tw
+    l = tw.nn.Linear([1, 2, 3, 4, 5, 6], [0, 0], True)
+    assert (l.in_, l.out, l.apply_relu) == (3, 2, True)
+    with pytest.raises(ValueError):
+        tw.nn.Linear([1, 2, 3], [0, 0], False)
+    e = tw.nn.EmbeddingBag([[1, 2], [3, 4], [5, 6]], [0, 0], True, [3], 0)
+    p = tw.nn.Policy(e, tw.nn.Sequential([tw.nn.Linear([1] * 8, [0] * 4, True)]),
+                     tw.nn.Sequential([tw.nn.Linear([1] * 16, [0] * 4, False)]),
+                     tw.nn.Sequential([tw.nn.Linear([1] * 4, [0], False)]), [], [])
+    d = p.desc()
+    assert (d.obs_size, d.emb_size, d.n_common, d.n_action, d.n_value, d.n_perms) == (3, 2, 1, 1, 1, 0)
+    assert d.common[0].in_ == 2 and d.common[0].out == 4 and d.action_net[0].out == 4
+    with pytest.raises(TypeError):
+        tw.nn.Sequential([1])
+
+
+def test_install_as_twisterl_registers_reference_names():
+    import twisterl_b200 as tw
+    mod = tw.install_as_twisterl()
+    import importlib
+    assert importlib.import_module("twisterl.twisterl") is mod
+    for sub, names in {"env": ["Puzzle", "PyBaseEnv", "PyEnv"], "nn": ["Linear", "EmbeddingBag", "Sequential", "Policy"],
+                       "collector": ["PPOCollector", "AZCollector", "CollectedData", "solve", "evaluate"]}.items():
+        for n in names:
+            assert hasattr(getattr(mod, sub), n), (sub, n)
+    assert importlib.import_module("grid_world").GridWorld is tw.env.GridWorld
+
+
+def test_max_records_and_spec_validation():
+    import ctypes as C
+    from twisterl_b200 import _lib
+    L = _lib.load()
+    s = _lib.EnvSpec(0, 4, 4, 128, 2, 256)
+    assert L.twr_max_records(C.byref(s), 65536) == 65536 * 257
+    g = _lib.EnvSpec(1, 5, 5, 10, 0, 64)
+    assert L.twr_max_records(C.byref(g), 10) == 650
+    big = _lib.EnvSpec(0, 5, 5, 1, 1, 1)
+    assert L.twr_max_records(C.byref(big), 1) == -1
+    assert b"16 cells" in L.twr_last_error()

@@ -1,0 +1,764 @@
+// twr_engine.cu -- host side of the C ABI declared in include/twisterl_b200.h: owns device memory,
+// validates env specs / policy shapes, drives the per-step kernel sequence of a collect on one CUDA
+// stream, and moves results to caller buffers.  No CPU compute path exists here: every Env / Policy /
+// collector operation is a kernel launch (twr_kernels.cu, twr_forward_*.cu).
+#include "../../include/twisterl_b200.h"
+#include "twr_kernels.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+extern std::atomic<long long> g_twr_launches;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(TWR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CU_TRY(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+    return TWR_OK;
+}
+template <typename T>
+void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+int check_spec(const twr_env_spec* s, EnvParams* out) {
+    if (!s) return fail(TWR_ERR_INVALID, "env spec is NULL");
+    if (s->width < 1 || s->height < 1) return fail(TWR_ERR_INVALID, "env width/height must be >= 1");
+    EnvParams p{};
+    p.kind = s->kind; p.W = s->width; p.H = s->height; p.N = s->width * s->height;
+    p.difficulty = s->difficulty; p.depth_slope = s->depth_slope; p.max_depth = s->max_depth;
+    if (s->difficulty < 0 || s->max_depth < 0) return fail(TWR_ERR_INVALID, "difficulty/max_depth must be >= 0");
+    if (s->kind == TWR_ENV_PUZZLE) {
+        if (p.N > TWR_MAX_CELLS_PUZZLE)
+            return fail(TWR_ERR_UNSUPPORTED, "Puzzle boards above 16 cells are not implemented on the device path");
+        if (s->depth_slope < 0) return fail(TWR_ERR_INVALID, "depth_slope must be >= 0");
+        if ((int64_t)s->depth_slope * s->difficulty >= (1 << 24)) return fail(TWR_ERR_INVALID, "depth budget too large");
+    } else if (s->kind == TWR_ENV_GRIDWORLD) {
+        if (p.N > TWR_MAX_CELLS || p.N < 3)
+            return fail(TWR_ERR_UNSUPPORTED, "GridWorld needs 3..32 cells on the device path");
+        const int cap = s->width + s->height;                      // lib.rs:36,92-94
+        p.difficulty = s->difficulty < cap ? s->difficulty : cap;
+        if (s->max_depth >= (1 << 24)) return fail(TWR_ERR_INVALID, "max_steps too large");
+    } else {
+        return fail(TWR_ERR_UNSUPPORTED, "unknown env kind: only Puzzle and GridWorld run on the device "
+                                         "(arbitrary Env implementations have no CPU fallback here)");
+    }
+    *out = p;
+    return TWR_OK;
+}
+
+int horizon_of(const EnvParams& p) {   // max env steps of one episode
+    return p.kind == TWR_ENV_PUZZLE ? p.depth_slope * p.difficulty : p.max_depth;
+}
+
+}  // namespace
+
+struct twr_engine {
+    int device = 0, precision = 0, rank = 0, world = 1;
+    uint64_t seed = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint32_t collect_id = 0;
+    long long launches0 = 0;
+    // collect buffers
+    CollectBuffers buf{};
+    int64_t cap_B = 0; int cap_T = 0; int64_t cap_R = 0; int cap_cells = 0;
+    bool has_last = false;
+    twr_collected last{};
+    // timing
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    float last_fwd_ms = 0.f, last_total_ms = 0.f; int64_t last_fwd_launches = 0;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+};
+
+struct twr_policy {
+    twr_engine* eng = nullptr;
+    PolicyDev dev{};
+    float* d_blob = nullptr;
+    int64_t blob_floats = 0;
+    int32_t* d_obs_perms = nullptr;
+    int32_t* d_act_perms = nullptr;
+    void* tc_pack = nullptr;
+    int64_t off_emb_b = 0, off_w1 = 0, off_b1 = 0, off_wa = 0, off_ba = 0, off_wv = 0, off_bv = 0;
+};
+
+struct twr_envs {
+    twr_engine* eng = nullptr;
+    EnvParams p{};
+    int64_t n = 0;
+    uint4* cells = nullptr;
+    uint32_t* meta = nullptr;
+};
+
+template <typename T>
+struct Staging {
+    T* d = nullptr;
+    ~Staging() { if (d) cudaFree(d); }
+    int alloc(size_t n) { return dev_alloc(&d, n); }
+};
+
+
+template <typename T>
+static int query_field(twr_envs* v, T* host, size_t per_env, int which) {
+    if (!v || !host) return fail(TWR_ERR_INVALID, "envs/out is NULL");
+    if (v->n == 0) return TWR_OK;
+    twr_engine* e = v->eng;
+    CU_TRY(cudaSetDevice(e->device));
+    Staging<T> st;
+    int rc = st.alloc((size_t)v->n * per_env);
+    if (rc) return rc;
+    launch_envs_query(e->stream, v->p, v->cells, v->meta, v->n,
+                      which == 0 ? reinterpret_cast<int64_t*>(st.d) : nullptr,
+                      which == 1 ? reinterpret_cast<int32_t*>(st.d) : nullptr,
+                      which == 2 ? reinterpret_cast<uint8_t*>(st.d) : nullptr,
+                      which == 3 ? reinterpret_cast<float*>(st.d) : nullptr,
+                      which == 4 ? reinterpret_cast<uint8_t*>(st.d) : nullptr,
+                      which == 5 ? reinterpret_cast<uint8_t*>(st.d) : nullptr,
+                      which == 6 ? reinterpret_cast<int32_t*>(st.d) : nullptr);
+    CU_TRY(cudaMemcpyAsync(host, st.d, sizeof(T) * (size_t)v->n * per_env, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return TWR_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int twr_abi_version(void) { return TWR_ABI_VERSION; }
+const char* twr_last_error(void) { return g_err.c_str(); }
+
+int twr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
+    if (!cfg || !out) return fail(TWR_ERR_INVALID, "cfg/out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n);
+    if (ce != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(TWR_ERR_CUDA, "no CUDA device: the twisterl_b200 engine has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= n) return fail(TWR_ERR_INVALID, "device ordinal out of range");
+    if (cfg->precision != TWR_PREC_FP32 && cfg->precision != TWR_PREC_F16X2)
+        return fail(TWR_ERR_INVALID, "unknown precision");
+    if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(TWR_ERR_INVALID, "bad rank/world");
+    CU_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10)
+        return fail(TWR_ERR_UNSUPPORTED, std::string("device '") + prop.name + "' is not Blackwell (sm_100a kernels only)");
+    twr_engine* e = new twr_engine();
+    e->device = cfg->device; e->precision = cfg->precision; e->seed = cfg->seed;
+    e->rank = cfg->rank; e->world = cfg->world;
+    if (cfg->stream) {
+        e->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
+    } else {
+        cudaError_t se = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { delete e; return fail(TWR_ERR_CUDA, cudaGetErrorString(se)); }
+        e->own_stream = true;
+    }
+    cudaEventCreate(&e->ev_t0); cudaEventCreate(&e->ev_t1);
+    e->launches0 = g_twr_launches.load();
+    *out = e;
+    return TWR_OK;
+}
+
+static void free_collect_buffers(twr_engine* e) {
+    CollectBuffers& b = e->buf;
+    dev_free(b.cells); dev_free(b.meta); dev_free(b.live_a); dev_free(b.live_b); dev_free(b.n_live);
+    dev_free(b.logits); dev_free(b.values);
+    dev_free(b.rec_state); dev_free(b.rec_logits); dev_free(b.rec_value); dev_free(b.rec_reward);
+    dev_free(b.rec_adv); dev_free(b.rec_ret); dev_free(b.rec_action); dev_free(b.rec_perm);
+    dev_free(b.ep_len); dev_free(b.ep_off); dev_free(b.stats);
+    dev_free(b.out_obs); dev_free(b.out_logits); dev_free(b.out_values); dev_free(b.out_rewards);
+    dev_free(b.out_advs); dev_free(b.out_rets); dev_free(b.out_actions); dev_free(b.out_perms);
+    e->cap_B = 0; e->cap_T = 0; e->cap_R = 0; e->cap_cells = 0;
+}
+
+void twr_engine_destroy(twr_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    free_collect_buffers(e);
+    for (auto ev : e->ev) cudaEventDestroy(ev);
+    if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+    if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int twr_engine_synchronize(twr_engine* e) {
+    if (!e) return fail(TWR_ERR_INVALID, "engine is NULL");
+    CU_TRY(cudaSetDevice(e->device));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return TWR_OK;
+}
+
+int64_t twr_engine_launch_count(const twr_engine* e) {
+    return e ? (int64_t)(g_twr_launches.load() - e->launches0) : 0;
+}
+
+int twr_engine_set_collect_id(twr_engine* e, uint32_t collect_id) {
+    if (!e) return fail(TWR_ERR_INVALID, "engine is NULL");
+    e->collect_id = collect_id;
+    return TWR_OK;
+}
+
+int twr_engine_set_timing(twr_engine* e, int32_t enabled) {
+    if (!e) return fail(TWR_ERR_INVALID, "engine is NULL");
+    e->timing = enabled != 0;
+    return TWR_OK;
+}
+
+int twr_engine_last_timing(const twr_engine* e, float* forward_ms, float* total_ms, int64_t* forward_launches) {
+    if (!e) return fail(TWR_ERR_INVALID, "engine is NULL");
+    if (forward_ms) *forward_ms = e->last_fwd_ms;
+    if (total_ms) *total_ms = e->last_total_ms;
+    if (forward_launches) *forward_launches = e->last_fwd_launches;
+    return TWR_OK;
+}
+
+// ----------------------------------------------------------------------- policy ---
+static int validate_desc(const twr_policy_desc* d) {
+    if (!d || !d->emb_vectors || !d->emb_bias) return fail(TWR_ERR_INVALID, "policy desc / embedding is NULL");
+    if (d->obs_shape_len != 1)
+        return fail(TWR_ERR_UNSUPPORTED, "only the 1-D EmbeddingBag path (BasicPolicy) runs on the device; "
+                                         "the conv1d 2-D path (Conv1dPolicy) is not implemented");
+    if (!d->emb_apply_relu) return fail(TWR_ERR_UNSUPPORTED, "EmbeddingBag without ReLU is not implemented");
+    if (d->n_common != 1 || !d->common) return fail(TWR_ERR_UNSUPPORTED, "exactly one common Linear layer is implemented");
+    if (d->n_action != 1 || !d->action_net || d->n_value != 1 || !d->value_net)
+        return fail(TWR_ERR_UNSUPPORTED, "single-Linear action and value heads are implemented");
+    const twr_linear_desc& c = d->common[0];
+    const twr_linear_desc& a = d->action_net[0];
+    const twr_linear_desc& v = d->value_net[0];
+    if (c.in != d->emb_size || !c.apply_relu) return fail(TWR_ERR_UNSUPPORTED, "common layer must be Linear(E,H)+ReLU");
+    if (a.in != c.out || a.apply_relu || a.out < 1 || a.out > TWR_MAX_ACTIONS)
+        return fail(TWR_ERR_UNSUPPORTED, "action head must be Linear(H,A) without ReLU, A <= 4");
+    if (v.in != c.out || v.apply_relu || v.out != 1) return fail(TWR_ERR_UNSUPPORTED, "value head must be Linear(H,1)");
+    if (d->n_perms < 0 || d->n_perms > 127) return fail(TWR_ERR_INVALID, "n_perms must be in 0..127");
+    if (d->n_perms > 0 && (!d->obs_perms || !d->act_perms)) return fail(TWR_ERR_INVALID, "perm arrays are NULL");
+    if (d->obs_size < 1 || d->obs_size >= 65536) return fail(TWR_ERR_UNSUPPORTED, "obs_size must be in 1..65535");
+    if (d->n_perms > 0) {
+        for (int64_t i = 0; i < (int64_t)d->n_perms * d->obs_size; ++i)
+            if (d->obs_perms[i] < 0 || d->obs_perms[i] >= d->obs_size) return fail(TWR_ERR_INVALID, "obs_perms entry out of range");
+        for (int64_t i = 0; i < (int64_t)d->n_perms * a.out; ++i)
+            if (d->act_perms[i] < 0 || d->act_perms[i] >= a.out) return fail(TWR_ERR_INVALID, "act_perms entry out of range");
+    }
+    return TWR_OK;
+}
+
+static int upload_policy(twr_policy* p, const twr_policy_desc* d) {
+    twr_engine* e = p->eng;
+    const int E = d->emb_size, H = d->common[0].out, A = d->action_net[0].out;
+    if (d->obs_size != p->dev.obs_size || E != p->dev.E || H != p->dev.H || A != p->dev.A || d->n_perms != p->dev.n_perms)
+        return fail(TWR_ERR_INVALID, "twr_policy_update: shapes differ from the ones the policy was created with");
+    cudaStream_t st = e->stream;
+    float* b = p->d_blob;
+    CU_TRY(cudaMemcpyAsync(b, d->emb_vectors, sizeof(float) * (size_t)d->obs_size * E, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b + p->off_emb_b, d->emb_bias, sizeof(float) * E, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b + p->off_w1, d->common[0].weights, sizeof(float) * (size_t)E * H, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b + p->off_b1, d->common[0].bias, sizeof(float) * H, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b + p->off_wa, d->action_net[0].weights, sizeof(float) * (size_t)H * A, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b + p->off_ba, d->action_net[0].bias, sizeof(float) * A, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b + p->off_wv, d->value_net[0].weights, sizeof(float) * H, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(b + p->off_bv, d->value_net[0].bias, sizeof(float), cudaMemcpyHostToDevice, st));
+    if (d->n_perms > 0) {
+        CU_TRY(cudaMemcpyAsync(p->d_obs_perms, d->obs_perms, sizeof(int32_t) * (size_t)d->n_perms * d->obs_size, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(p->d_act_perms, d->act_perms, sizeof(int32_t) * (size_t)d->n_perms * A, cudaMemcpyHostToDevice, st));
+    }
+    if (p->tc_pack) launch_forward_tc_pack(st, p->dev, p->tc_pack);
+    CU_TRY(cudaStreamSynchronize(st));   // host source buffers may be freed by the caller after return
+    return TWR_OK;
+}
+
+int twr_policy_create(twr_engine* e, const twr_policy_desc* d, twr_policy** out) {
+    if (!e || !out) return fail(TWR_ERR_INVALID, "engine/out is NULL");
+    *out = nullptr;
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(e->device));
+    const int E = d->emb_size, H = d->common[0].out, A = d->action_net[0].out;
+    twr_policy* p = new twr_policy();
+    p->eng = e;
+    p->dev.obs_size = d->obs_size; p->dev.E = E; p->dev.H = H; p->dev.A = A; p->dev.n_perms = d->n_perms;
+    p->dev.n_obs = 0;
+    int64_t off = (int64_t)d->obs_size * E;
+    p->off_emb_b = off; off += E;
+    p->off_w1 = off; off += (int64_t)E * H;
+    p->off_b1 = off; off += H;
+    p->off_wa = off; off += (int64_t)H * A;
+    p->off_ba = off; off += A;
+    p->off_wv = off; off += H;
+    p->off_bv = off; off += 1;
+    p->blob_floats = off;
+    {
+        PolicyDev probe = p->dev;
+        probe.n_obs = 1;
+        EnvParams dummy{};
+        const char* why = "";
+        const int ok = e->precision == TWR_PREC_F16X2 ? forward_tc_supported(probe, dummy, &why)
+                                                       : forward_fp32_supported(probe, dummy, &why);
+        if (!ok) { delete p; return fail(TWR_ERR_UNSUPPORTED, std::string("policy shape not supported on the device: ") + why); }
+    }
+    if ((rc = dev_alloc(&p->d_blob, (size_t)p->blob_floats))) { delete p; return rc; }
+    if (d->n_perms > 0) {
+        if ((rc = dev_alloc(&p->d_obs_perms, (size_t)d->n_perms * d->obs_size)) ||
+            (rc = dev_alloc(&p->d_act_perms, (size_t)d->n_perms * A))) { twr_policy_destroy(p); return rc; }
+    }
+    p->dev.emb = p->d_blob; p->dev.emb_b = p->d_blob + p->off_emb_b;
+    p->dev.w1 = p->d_blob + p->off_w1; p->dev.b1 = p->d_blob + p->off_b1;
+    p->dev.wa = p->d_blob + p->off_wa; p->dev.ba = p->d_blob + p->off_ba;
+    p->dev.wv = p->d_blob + p->off_wv; p->dev.bv = p->d_blob + p->off_bv;
+    p->dev.obs_perms = p->d_obs_perms; p->dev.act_perms = p->d_act_perms;
+    if (e->precision == TWR_PREC_F16X2) {
+        const size_t bytes = forward_tc_pack_bytes(p->dev);
+        cudaError_t ce = cudaMalloc(&p->tc_pack, bytes);
+        if (ce != cudaSuccess) { twr_policy_destroy(p); return fail(TWR_ERR_CUDA, cudaGetErrorString(ce)); }
+        p->dev.tc_pack = p->tc_pack;
+    }
+    if ((rc = upload_policy(p, d))) { twr_policy_destroy(p); return rc; }
+    *out = p;
+    return TWR_OK;
+}
+
+int twr_policy_update(twr_policy* p, const twr_policy_desc* d) {
+    if (!p) return fail(TWR_ERR_INVALID, "policy is NULL");
+    int rc = validate_desc(d);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(p->eng->device));
+    return upload_policy(p, d);
+}
+
+int64_t twr_policy_blob_floats(const twr_policy* p) { return p ? p->blob_floats : 0; }
+
+int twr_policy_blob_device_ptr(twr_policy* p, float** d_blob) {
+    if (!p || !d_blob) return fail(TWR_ERR_INVALID, "policy/out is NULL");
+    *d_blob = p->d_blob;
+    return TWR_OK;
+}
+
+int twr_policy_update_from_device(twr_policy* p, const float* d_src) {
+    if (!p || !d_src) return fail(TWR_ERR_INVALID, "policy/blob is NULL");
+    twr_engine* e = p->eng;
+    CU_TRY(cudaSetDevice(e->device));
+    if (d_src != p->d_blob)
+        CU_TRY(cudaMemcpyAsync(p->d_blob, d_src, sizeof(float) * (size_t)p->blob_floats, cudaMemcpyDeviceToDevice, e->stream));
+    if (p->tc_pack) launch_forward_tc_pack(e->stream, p->dev, p->tc_pack);
+    CU_TRY(cudaGetLastError());
+    return TWR_OK;
+}
+
+void twr_policy_destroy(twr_policy* p) {
+    if (!p) return;
+    cudaSetDevice(p->eng->device);
+    cudaStreamSynchronize(p->eng->stream);
+    dev_free(p->d_blob); dev_free(p->d_obs_perms); dev_free(p->d_act_perms);
+    if (p->tc_pack) cudaFree(p->tc_pack);
+    delete p;
+}
+
+// ------------------------------------------------------------------ batched env ---
+int twr_envs_create(twr_engine* e, const twr_env_spec* spec, int64_t n, twr_envs** out) {
+    if (!e || !out) return fail(TWR_ERR_INVALID, "engine/out is NULL");
+    *out = nullptr;
+    if (n < 0) return fail(TWR_ERR_INVALID, "n must be >= 0");
+    EnvParams p;
+    int rc = check_spec(spec, &p);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(e->device));
+    twr_envs* v = new twr_envs();
+    v->eng = e; v->p = p; v->n = n;
+    if ((rc = dev_alloc(&v->cells, (size_t)n)) || (rc = dev_alloc(&v->meta, (size_t)n))) { twr_envs_destroy(v); return rc; }
+    launch_envs_fresh(e->stream, p, v->cells, v->meta, n);
+    CU_TRY(cudaGetLastError());
+    *out = v;
+    return TWR_OK;
+}
+
+void twr_envs_destroy(twr_envs* v) {
+    if (!v) return;
+    cudaSetDevice(v->eng->device);
+    cudaStreamSynchronize(v->eng->stream);
+    dev_free(v->cells); dev_free(v->meta);
+    delete v;
+}
+
+int twr_envs_set_difficulty(twr_envs* v, int32_t difficulty) {
+    if (!v) return fail(TWR_ERR_INVALID, "envs is NULL");
+    if (difficulty < 0) return fail(TWR_ERR_INVALID, "difficulty must be >= 0");
+    if (v->p.kind == TWR_ENV_GRIDWORLD) {
+        const int cap = v->p.W + v->p.H;
+        v->p.difficulty = difficulty < cap ? difficulty : cap;
+    } else {
+        v->p.difficulty = difficulty;
+    }
+    return TWR_OK;
+}
+
+int twr_envs_set_state(twr_envs* v, const int64_t* states) {
+    if (!v || !states) return fail(TWR_ERR_INVALID, "envs/states is NULL");
+    if (v->n == 0) return TWR_OK;
+    const int N = v->p.N;
+    for (int64_t i = 0; i < v->n * N; ++i)
+        if (states[i] < 0 || states[i] > 255) return fail(TWR_ERR_INVALID, "set_state: cell values must be in 0..255");
+    if (v->p.kind == TWR_ENV_PUZZLE) {
+        for (int64_t e = 0; e < v->n; ++e) {
+            bool zero = false;
+            for (int i = 0; i < N; ++i) zero |= states[e * N + i] == 0;
+            if (!zero) return fail(TWR_ERR_INVALID, "set_state: a Puzzle board needs a blank (0) cell");
+        }
+    }
+    twr_engine* e = v->eng;
+    CU_TRY(cudaSetDevice(e->device));
+    Staging<int64_t> st;
+    int rc = st.alloc((size_t)v->n * N);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(st.d, states, sizeof(int64_t) * (size_t)v->n * N, cudaMemcpyHostToDevice, e->stream));
+    launch_envs_set_state(e->stream, v->p, v->cells, v->meta, v->n, st.d);
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return TWR_OK;
+}
+
+int twr_envs_reset(twr_envs* v, uint32_t env_id_base, uint32_t collect_id) {
+    if (!v) return fail(TWR_ERR_INVALID, "envs is NULL");
+    if (v->p.kind == TWR_ENV_GRIDWORLD && v->p.difficulty < 1)
+        return fail(TWR_ERR_INVALID, "GridWorld reset needs difficulty >= 1 (the reference loops forever at 0)");
+    twr_engine* e = v->eng;
+    CU_TRY(cudaSetDevice(e->device));
+    launch_envs_reset(e->stream, v->p, v->cells, v->meta, v->n, e->seed, env_id_base, collect_id, nullptr, nullptr);
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return TWR_OK;
+}
+
+int twr_envs_step(twr_envs* v, const int32_t* actions) {
+    if (!v || !actions) return fail(TWR_ERR_INVALID, "envs/actions is NULL");
+    if (v->n == 0) return TWR_OK;
+    twr_engine* e = v->eng;
+    CU_TRY(cudaSetDevice(e->device));
+    Staging<int32_t> st;
+    int rc = st.alloc((size_t)v->n);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(st.d, actions, sizeof(int32_t) * (size_t)v->n, cudaMemcpyHostToDevice, e->stream));
+    launch_envs_step(e->stream, v->p, v->cells, v->meta, v->n, st.d);
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return TWR_OK;
+}
+
+int twr_envs_get_state(twr_envs* v, int64_t* states) { return query_field<int64_t>(v, states, v ? v->p.N : 0, 0); }
+int twr_envs_observe(twr_envs* v, int32_t* obs) { return query_field<int32_t>(v, obs, v ? v->p.N : 0, 1); }
+int twr_envs_masks(twr_envs* v, uint8_t* masks) { return query_field<uint8_t>(v, masks, TWR_MAX_ACTIONS, 2); }
+int twr_envs_reward(twr_envs* v, float* r) { return query_field<float>(v, r, 1, 3); }
+int twr_envs_is_final(twr_envs* v, uint8_t* f) { return query_field<uint8_t>(v, f, 1, 4); }
+int twr_envs_success(twr_envs* v, uint8_t* s) { return query_field<uint8_t>(v, s, 1, 5); }
+int twr_envs_depth(twr_envs* v, int32_t* d) { return query_field<int32_t>(v, d, 1, 6); }
+
+// -------------------------------------------------------------------- forward ---
+static int check_policy_env(const twr_policy* p, const EnvParams& env, PolicyDev* dev) {
+    if (p->dev.obs_size != env.N * env.N)
+        return fail(TWR_ERR_INVALID, "policy obs_size does not match the env's obs_shape (cells*cells)");
+    if (p->dev.A != 4) return fail(TWR_ERR_INVALID, "policy has " + std::to_string(p->dev.A) + " actions, env has 4");
+    *dev = p->dev;
+    dev->n_obs = env.N;
+    return TWR_OK;
+}
+
+static void launch_forward(twr_engine* e, const PolicyDev& dev, const ForwardArgs& a) {
+    if (e->precision == TWR_PREC_F16X2) launch_forward_tc(e->stream, dev, a);
+    else launch_forward_fp32(e->stream, dev, a);
+}
+
+int twr_policy_forward(twr_engine* e, const twr_policy* p, twr_envs* v, const int32_t* perm_idx, int32_t apply_masks,
+                       float* logits, float* values) {
+    if (!e || !p || !v || !logits || !values) return fail(TWR_ERR_INVALID, "NULL argument");
+    if (p->eng != e || v->eng != e) return fail(TWR_ERR_INVALID, "policy/envs belong to another engine");
+    if (v->n == 0) return TWR_OK;
+    PolicyDev dev;
+    int rc = check_policy_env(p, v->p, &dev);
+    if (rc) return rc;
+    if (perm_idx) {
+        for (int64_t i = 0; i < v->n; ++i)
+            if (perm_idx[i] < -1 || perm_idx[i] >= p->dev.n_perms) return fail(TWR_ERR_INVALID, "perm_idx out of range");
+    }
+    CU_TRY(cudaSetDevice(e->device));
+    Staging<float4> d_logits; Staging<float> d_values; Staging<int32_t> d_perm;
+    if ((rc = d_logits.alloc((size_t)v->n)) || (rc = d_values.alloc((size_t)v->n))) return rc;
+    if (perm_idx) {
+        if ((rc = d_perm.alloc((size_t)v->n))) return rc;
+        CU_TRY(cudaMemcpyAsync(d_perm.d, perm_idx, sizeof(int32_t) * (size_t)v->n, cudaMemcpyHostToDevice, e->stream));
+    }
+    ForwardArgs a{};
+    a.env = v->p; a.seed = e->seed; a.cid = 0; a.env_id_base = 0; a.t = -1;
+    a.perm_idx = perm_idx ? d_perm.d : nullptr;
+    a.cells = v->cells; a.live = nullptr; a.n_live_ptr = nullptr; a.n = v->n;
+    a.logits = d_logits.d; a.values = d_values.d;
+    launch_forward(e, dev, a);
+    if (apply_masks) launch_mask_logits(e->stream, v->p, v->cells, v->meta, v->n, dev.A, d_logits.d);
+    CU_TRY(cudaGetLastError());
+    std::vector<float4> h((size_t)v->n);
+    CU_TRY(cudaMemcpyAsync(h.data(), d_logits.d, sizeof(float4) * (size_t)v->n, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(values, d_values.d, sizeof(float) * (size_t)v->n, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    for (int64_t i = 0; i < v->n; ++i) {
+        const float l[4] = {h[i].x, h[i].y, h[i].z, h[i].w};
+        for (int a2 = 0; a2 < dev.A; ++a2) logits[i * dev.A + a2] = l[a2];
+    }
+    return TWR_OK;
+}
+
+int twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* obs, int64_t n, int32_t n_obs,
+                           const int32_t* perm_idx, float* logits, float* values) {
+    if (!e || !p || !obs || !logits || !values) return fail(TWR_ERR_INVALID, "NULL argument");
+    if (p->eng != e) return fail(TWR_ERR_INVALID, "policy belongs to another engine");
+    if (n_obs < 1 || n_obs > TWR_MAX_CELLS) return fail(TWR_ERR_UNSUPPORTED, "n_obs must be in 1..32");
+    if (n <= 0) return TWR_OK;
+    for (int64_t i = 0; i < n * n_obs; ++i)
+        if (obs[i] < 0 || obs[i] >= p->dev.obs_size) return fail(TWR_ERR_INVALID, "observation index out of range");
+    if (perm_idx)
+        for (int64_t i = 0; i < n; ++i)
+            if (perm_idx[i] < -1 || perm_idx[i] >= p->dev.n_perms) return fail(TWR_ERR_INVALID, "perm_idx out of range");
+    CU_TRY(cudaSetDevice(e->device));
+    PolicyDev dev = p->dev;
+    dev.n_obs = n_obs;
+    Staging<float4> d_logits; Staging<float> d_values; Staging<int32_t> d_perm, d_obs;
+    int rc;
+    if ((rc = d_logits.alloc((size_t)n)) || (rc = d_values.alloc((size_t)n)) || (rc = d_obs.alloc((size_t)n * n_obs))) return rc;
+    CU_TRY(cudaMemcpyAsync(d_obs.d, obs, sizeof(int32_t) * (size_t)n * n_obs, cudaMemcpyHostToDevice, e->stream));
+    if (perm_idx) {
+        if ((rc = d_perm.alloc((size_t)n))) return rc;
+        CU_TRY(cudaMemcpyAsync(d_perm.d, perm_idx, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, e->stream));
+    }
+    ForwardArgs a{};
+    a.env.N = n_obs; a.seed = e->seed; a.t = -1;
+    a.perm_idx = perm_idx ? d_perm.d : nullptr;
+    a.obs_rows = d_obs.d; a.n = n;
+    a.logits = d_logits.d; a.values = d_values.d;
+    launch_forward(e, dev, a);
+    CU_TRY(cudaGetLastError());
+    std::vector<float4> h((size_t)n);
+    CU_TRY(cudaMemcpyAsync(h.data(), d_logits.d, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(values, d_values.d, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    for (int64_t i = 0; i < n; ++i) {
+        const float l[4] = {h[i].x, h[i].y, h[i].z, h[i].w};
+        for (int a2 = 0; a2 < dev.A; ++a2) logits[i * dev.A + a2] = l[a2];
+    }
+    return TWR_OK;
+}
+
+int twr_sample(twr_engine* e, const float* logits, int64_t n, int32_t A, uint32_t env_id_base, uint32_t step,
+               uint32_t collect_id, int32_t* actions, float* uniforms_out) {
+    if (!e || !logits || !actions) return fail(TWR_ERR_INVALID, "NULL argument");
+    if (A < 1 || A > TWR_MAX_ACTIONS) return fail(TWR_ERR_UNSUPPORTED, "num_actions must be 1..4");
+    if (n <= 0) return TWR_OK;
+    CU_TRY(cudaSetDevice(e->device));
+    Staging<float> d_l, d_u; Staging<int32_t> d_a;
+    int rc;
+    if ((rc = d_l.alloc((size_t)n * A)) || (rc = d_a.alloc((size_t)n)) || (rc = d_u.alloc((size_t)n * A))) return rc;
+    CU_TRY(cudaMemcpyAsync(d_l.d, logits, sizeof(float) * (size_t)n * A, cudaMemcpyHostToDevice, e->stream));
+    launch_sample(e->stream, d_l.d, n, A, e->seed, env_id_base, step, collect_id, d_a.d, d_u.d);
+    CU_TRY(cudaMemcpyAsync(actions, d_a.d, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+    if (uniforms_out)
+        CU_TRY(cudaMemcpyAsync(uniforms_out, d_u.d, sizeof(float) * (size_t)n * A, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return TWR_OK;
+}
+
+int twr_gae(twr_engine* e, const float* rewards, const float* values, const int64_t* offsets, int64_t n_ep, float gamma,
+            float lambda, float* advs, float* rets) {
+    if (!e || !rewards || !values || !offsets || !advs || !rets) return fail(TWR_ERR_INVALID, "NULL argument");
+    if (n_ep <= 0) return TWR_OK;
+    const int64_t R = offsets[n_ep];
+    for (int64_t i = 0; i < n_ep; ++i)
+        if (offsets[i] > offsets[i + 1] || offsets[i] < 0) return fail(TWR_ERR_INVALID, "offsets must be non-decreasing");
+    if (R == 0) return TWR_OK;
+    CU_TRY(cudaSetDevice(e->device));
+    Staging<float> d_r, d_v, d_a, d_t; Staging<int64_t> d_o;
+    int rc;
+    if ((rc = d_r.alloc((size_t)R)) || (rc = d_v.alloc((size_t)R)) || (rc = d_a.alloc((size_t)R)) ||
+        (rc = d_t.alloc((size_t)R)) || (rc = d_o.alloc((size_t)n_ep + 1))) return rc;
+    CU_TRY(cudaMemcpyAsync(d_r.d, rewards, sizeof(float) * (size_t)R, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(d_v.d, values, sizeof(float) * (size_t)R, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(d_o.d, offsets, sizeof(int64_t) * (size_t)(n_ep + 1), cudaMemcpyHostToDevice, e->stream));
+    launch_gae_concat(e->stream, d_r.d, d_v.d, d_o.d, n_ep, gamma, lambda, d_a.d, d_t.d);
+    CU_TRY(cudaMemcpyAsync(advs, d_a.d, sizeof(float) * (size_t)R, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(rets, d_t.d, sizeof(float) * (size_t)R, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return TWR_OK;
+}
+
+// -------------------------------------------------------------------- collect ---
+int64_t twr_max_records(const twr_env_spec* spec, int64_t num_episodes) {
+    EnvParams p;
+    if (check_spec(spec, &p)) return -1;
+    return num_episodes * (int64_t)(horizon_of(p) + 1);
+}
+
+static int ensure_collect_buffers(twr_engine* e, int64_t B, int T, int cells) {
+    if (B <= e->cap_B && T <= e->cap_T && cells <= e->cap_cells && B * T <= e->cap_R) {
+        e->buf.B = B; e->buf.Tmax = T;
+        return TWR_OK;
+    }
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    free_collect_buffers(e);
+    CollectBuffers& b = e->buf;
+    const size_t R = (size_t)B * T;
+    int rc;
+    if ((rc = dev_alloc(&b.cells, (size_t)B)) || (rc = dev_alloc(&b.meta, (size_t)B)) ||
+        (rc = dev_alloc(&b.live_a, (size_t)B)) || (rc = dev_alloc(&b.live_b, (size_t)B)) ||
+        (rc = dev_alloc(&b.n_live, (size_t)T + 1)) || (rc = dev_alloc(&b.logits, (size_t)B)) ||
+        (rc = dev_alloc(&b.values, (size_t)B)) || (rc = dev_alloc(&b.rec_state, R)) ||
+        (rc = dev_alloc(&b.rec_logits, R)) || (rc = dev_alloc(&b.rec_value, R)) ||
+        (rc = dev_alloc(&b.rec_reward, R)) || (rc = dev_alloc(&b.rec_adv, R)) || (rc = dev_alloc(&b.rec_ret, R)) ||
+        (rc = dev_alloc(&b.rec_action, R)) || (rc = dev_alloc(&b.rec_perm, R)) ||
+        (rc = dev_alloc(&b.ep_len, (size_t)B)) || (rc = dev_alloc(&b.ep_off, (size_t)B)) ||
+        (rc = dev_alloc(&b.stats, 4)) || (rc = dev_alloc(&b.out_obs, R * cells)) ||
+        (rc = dev_alloc(&b.out_logits, R * TWR_MAX_ACTIONS)) || (rc = dev_alloc(&b.out_values, R)) ||
+        (rc = dev_alloc(&b.out_rewards, R)) || (rc = dev_alloc(&b.out_advs, R)) || (rc = dev_alloc(&b.out_rets, R)) ||
+        (rc = dev_alloc(&b.out_actions, R)) || (rc = dev_alloc(&b.out_perms, R))) {
+        free_collect_buffers(e);
+        return rc;
+    }
+    e->cap_B = B; e->cap_T = T; e->cap_R = (int64_t)R; e->cap_cells = cells;
+    b.B = B; b.Tmax = T;
+    return TWR_OK;
+}
+
+int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, float gamma,
+                    float lambda, twr_collected* out) {
+    if (!e || !p || !out) return fail(TWR_ERR_INVALID, "NULL argument");
+    if (p->eng != e) return fail(TWR_ERR_INVALID, "policy belongs to another engine");
+    // merge() errors on zero chunks (collector/collector.rs:41)
+    if (num_episodes <= 0)
+        return fail(TWR_ERR_INVALID, "Something went wrong. No data in collected data chunks to merge. ");
+    if (num_episodes >= (1ll << 31)) return fail(TWR_ERR_INVALID, "num_episodes too large");
+    EnvParams env;
+    int rc = check_spec(spec, &env);
+    if (rc) return rc;
+    if (env.kind == TWR_ENV_GRIDWORLD && env.difficulty < 1)
+        return fail(TWR_ERR_INVALID, "GridWorld reset needs difficulty >= 1 (the reference loops forever at 0)");
+    PolicyDev dev;
+    if ((rc = check_policy_env(p, env, &dev))) return rc;
+    CU_TRY(cudaSetDevice(e->device));
+    const int T = horizon_of(env) + 1;
+    if ((rc = ensure_collect_buffers(e, num_episodes, T, env.N))) return rc;
+    CollectBuffers& b = e->buf;
+    cudaStream_t st = e->stream;
+    e->has_last = false;
+
+    const uint32_t cid = e->collect_id++;
+    const uint32_t env_id_base = (uint32_t)((int64_t)e->rank * num_episodes);
+    CU_TRY(cudaMemsetAsync(b.n_live, 0, sizeof(int32_t) * (size_t)(T + 1), st));
+    CU_TRY(cudaMemsetAsync(b.stats, 0, sizeof(unsigned long long) * 4, st));
+    if (e->timing) {
+        while ((int)e->ev.size() < 2 * T) { cudaEvent_t ev; cudaEventCreate(&ev); e->ev.push_back(ev); }
+        cudaEventRecord(e->ev_t0, st);
+    }
+    launch_envs_reset(st, env, b.cells, b.meta, num_episodes, e->seed, env_id_base, cid, b.live_a, b.n_live);
+
+    StepArgs sa{};
+    sa.env = env; sa.seed = e->seed; sa.cid = cid; sa.env_id_base = env_id_base; sa.n_perms = dev.n_perms; sa.A = dev.A;
+    ForwardArgs fa{};
+    fa.env = env; fa.seed = e->seed; fa.cid = cid; fa.env_id_base = env_id_base; fa.perm_idx = nullptr;
+    fa.cells = b.cells; fa.n = num_episodes; fa.logits = b.logits; fa.values = b.values;
+    for (int t = 0; t < T; ++t) {
+        int32_t* cur = (t & 1) ? b.live_b : b.live_a;
+        int32_t* nxt = (t & 1) ? b.live_a : b.live_b;
+        fa.t = t; fa.live = cur; fa.n_live_ptr = b.n_live + t;
+        if (e->timing) cudaEventRecord(e->ev[2 * t], st);
+        launch_forward(e, dev, fa);
+        if (e->timing) cudaEventRecord(e->ev[2 * t + 1], st);
+        sa.t = t;
+        launch_collect_step(st, sa, b, cur, nxt);
+    }
+    launch_gae_time_major(st, b, gamma, lambda);
+    launch_episode_offsets(st, b);
+    launch_compact(st, env, b, dev.A);
+    if (e->timing) cudaEventRecord(e->ev_t1, st);
+    CU_TRY(cudaGetLastError());
+
+    unsigned long long h_stats[4];
+    CU_TRY(cudaMemcpyAsync(h_stats, b.stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (e->timing) {
+        float tot = 0.f, ms = 0.f;
+        for (int t = 0; t < T; ++t) { cudaEventElapsedTime(&ms, e->ev[2 * t], e->ev[2 * t + 1]); tot += ms; }
+        e->last_fwd_ms = tot; e->last_fwd_launches = T;
+        cudaEventElapsedTime(&e->last_total_ms, e->ev_t0, e->ev_t1);
+    }
+    twr_collected& c = e->last;
+    c.n_records = (int64_t)h_stats[1];
+    c.num_episodes = num_episodes;
+    c.n_cells = env.N; c.num_actions = dev.A;
+    c.successes = (int64_t)h_stats[0];
+    double rs; memcpy(&rs, &h_stats[2], sizeof(double)); c.reward_sum = rs;
+    c.obs = b.out_obs; c.logits = b.out_logits; c.values = b.out_values; c.rewards = b.out_rewards;
+    c.advs = b.out_advs; c.rets = b.out_rets; c.actions = b.out_actions; c.perms = b.out_perms; c.ep_len = b.ep_len;
+    e->has_last = true;
+    *out = c;
+    return TWR_OK;
+}
+
+int twr_collected_to_host(twr_engine* e, const twr_host_buffers* dst) {
+    if (!e || !dst) return fail(TWR_ERR_INVALID, "NULL argument");
+    if (!e->has_last) return fail(TWR_ERR_STATE, "twr_collected_to_host: no collect has run on this engine");
+    const twr_collected& c = e->last;
+    const size_t R = (size_t)c.n_records;
+    if ((int64_t)R > dst->capacity) return fail(TWR_ERR_INVALID, "host buffers too small for the collected records");
+    CU_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    if (dst->obs) CU_TRY(cudaMemcpyAsync(dst->obs, c.obs, sizeof(uint16_t) * R * c.n_cells, cudaMemcpyDeviceToHost, st));
+    if (dst->logits) CU_TRY(cudaMemcpyAsync(dst->logits, c.logits, sizeof(float) * R * c.num_actions, cudaMemcpyDeviceToHost, st));
+    if (dst->values) CU_TRY(cudaMemcpyAsync(dst->values, c.values, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
+    if (dst->rewards) CU_TRY(cudaMemcpyAsync(dst->rewards, c.rewards, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
+    if (dst->advs) CU_TRY(cudaMemcpyAsync(dst->advs, c.advs, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
+    if (dst->rets) CU_TRY(cudaMemcpyAsync(dst->rets, c.rets, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
+    if (dst->actions) CU_TRY(cudaMemcpyAsync(dst->actions, c.actions, R, cudaMemcpyDeviceToHost, st));
+    if (dst->perms) CU_TRY(cudaMemcpyAsync(dst->perms, c.perms, R, cudaMemcpyDeviceToHost, st));
+    if (dst->ep_len) CU_TRY(cudaMemcpyAsync(dst->ep_len, c.ep_len, sizeof(int32_t) * (size_t)c.num_episodes, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return TWR_OK;
+}
+
+int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p, const twr_policy_desc* desc,
+                         int64_t num_episodes, float gamma, float lambda, const twr_host_buffers* dst, twr_collected* out) {
+    if (!e || !p || !dst || !out) return fail(TWR_ERR_INVALID, "NULL argument");
+    int rc;
+    if (desc && (rc = twr_policy_update(p, desc))) return rc;
+    if ((rc = twr_ppo_collect(e, spec, p, num_episodes, gamma, lambda, out))) return rc;
+    return twr_collected_to_host(e, dst);
+}
+
+int twr_host_alloc(void** ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail(TWR_ERR_INVALID, "bad argument");
+    CU_TRY(cudaHostAlloc(ptr, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault));
+    return TWR_OK;
+}
+void twr_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
+}  // extern "C"

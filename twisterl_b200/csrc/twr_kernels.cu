@@ -1,0 +1,424 @@
+// twr_kernels.cu -- the HBM-bound kernels of the rollout engine (sm_100a):
+//   K1  batched Env trait (reset / set_state / forced step / observe / masks / reward / is_final)
+//   K3  mask + Gumbel-max sampling (Philox), fused in collect_step with
+//   K4a trajectory write, env step and warp-ballot live-list compaction
+//   K4b GAE reverse scan
+//   K5  episode offsets (merge order) + transpose/compaction into concatenated episodes
+// All are one-thread-per-env, 16-byte vector state loads, time-major [t][env] record stores
+// (coalesced), grids sized from the env count.  Algorithmic bytes per record are listed in DESIGN.md.
+#include "twr_kernels.cuh"
+
+#include <atomic>
+
+std::atomic<long long> g_twr_launches{0};
+#define TWR_COUNT_LAUNCH() g_twr_launches.fetch_add(1, std::memory_order_relaxed)
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// ------------------------------------------------------------------------- K1 ---
+__global__ void __launch_bounds__(256) k_envs_reset(EnvParams p, uint4* __restrict__ cells, uint32_t* __restrict__ meta,
+                                                    int64_t n, uint64_t seed, uint32_t env_id_base, uint32_t cid,
+                                                    int32_t* __restrict__ live, int32_t* __restrict__ n_live0) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0 && n_live0) *n_live0 = (int32_t)n;
+    if (e >= n) return;
+    const EnvState s = env_reset(p, seed, env_id_base + (uint32_t)e, cid);
+    env_store(cells, meta, e, s);
+    if (live) live[e] = (int32_t)e;
+}
+
+__global__ void __launch_bounds__(256) k_envs_fresh(EnvParams p, uint4* __restrict__ cells, uint32_t* __restrict__ meta, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    env_store(cells, meta, e, env_fresh(p));
+}
+
+// Env::set_state.  puzzle.rs:107-117 (depth = max_depth, blank = first zero) ; lib.rs:100-112
+__global__ void __launch_bounds__(256) k_envs_set_state(EnvParams p, uint4* __restrict__ cells, uint32_t* __restrict__ meta,
+                                                        int64_t n, const int64_t* __restrict__ states) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    EnvState s = env_load(cells, meta, e);
+    const int64_t* st = states + e * p.N;
+    if (p.kind == 0) {
+        s.lo = TWR_IDENT_LO; s.hi = TWR_IDENT_HI;
+        bool found = false;
+        for (int i = 0; i < p.N; ++i) {
+            const int64_t v = st[i];
+            cell_set(s, i, (uint32_t)v);
+            if (v == 0 && !found) { s.blank = (uint32_t)i; found = true; }
+        }
+        s.depth = (uint32_t)p.max_depth;
+    } else {
+        for (int i = 0; i < p.N; ++i) {
+            const int64_t v = st[i];
+            if (v == 1) cell_set(s, 0, (uint32_t)i);
+            else if (v == 2) cell_set(s, 1, (uint32_t)i);
+            else if (v == 3) cell_set(s, 2, (uint32_t)i);
+        }
+        s.depth = (uint32_t)p.max_depth;
+    }
+    env_store(cells, meta, e, s);
+}
+
+__global__ void __launch_bounds__(256) k_envs_step(EnvParams p, uint4* __restrict__ cells, uint32_t* __restrict__ meta,
+                                                   int64_t n, const int32_t* __restrict__ actions) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    EnvState s = env_load(cells, meta, e);
+    env_step(p, s, actions[e]);
+    env_store(cells, meta, e, s);
+}
+
+__global__ void __launch_bounds__(256) k_envs_query(EnvParams p, const uint4* __restrict__ cells, const uint32_t* __restrict__ meta,
+                                                    int64_t n, int64_t* __restrict__ states, int32_t* __restrict__ obs,
+                                                    uint8_t* __restrict__ masks, float* __restrict__ reward,
+                                                    uint8_t* __restrict__ fin, uint8_t* __restrict__ succ, int32_t* __restrict__ depth) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const EnvState s = env_load(cells, meta, e);
+    if (states || obs) {
+        for (int i = 0; i < p.N; ++i) {
+            const uint32_t v = env_board(p, s, i);
+            if (states) states[e * p.N + i] = (int64_t)v;
+            if (obs) obs[e * p.N + i] = i * p.N + (int32_t)v;   // puzzle.rs:183-185
+        }
+    }
+    if (masks) {
+        const uint32_t m = env_masks(p, s);
+        for (int a = 0; a < TWR_MAX_ACTIONS; ++a) masks[e * TWR_MAX_ACTIONS + a] = (m >> a) & 1u;
+    }
+    if (reward) reward[e] = env_reward(p, s);
+    if (fin) fin[e] = env_is_final(p, s) ? 1 : 0;
+    if (succ) succ[e] = env_success(p, s) ? 1 : 0;
+    if (depth) depth[e] = (int32_t)s.depth;
+}
+
+// forward_with_perm's mask step (nn/policy.rs:62) for the parity API
+__global__ void __launch_bounds__(256) k_mask_logits(EnvParams p, const uint4* __restrict__ cells, const uint32_t* __restrict__ meta,
+                                                     int64_t n, int A, float4* __restrict__ logits) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const uint32_t m = env_masks(p, env_load(cells, meta, e));
+    float4 l = logits[e];
+    if (A > 0 && !(m & 1u)) l.x = -1e10f;
+    if (A > 1 && !(m & 2u)) l.y = -1e10f;
+    if (A > 2 && !(m & 4u)) l.z = -1e10f;
+    if (A > 3 && !(m & 8u)) l.w = -1e10f;
+    logits[e] = l;
+}
+
+void launch_envs_reset(cudaStream_t st, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n, uint64_t seed,
+                       uint32_t env_id_base, uint32_t cid, int32_t* live, int32_t* n_live0) {
+    if (n <= 0) return;
+    k_envs_reset<<<grid_for(n, 256), 256, 0, st>>>(p, cells, meta, n, seed, env_id_base, cid, live, n_live0);
+    TWR_COUNT_LAUNCH();
+}
+void launch_envs_fresh(cudaStream_t st, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n) {
+    if (n <= 0) return;
+    k_envs_fresh<<<grid_for(n, 256), 256, 0, st>>>(p, cells, meta, n);
+    TWR_COUNT_LAUNCH();
+}
+void launch_envs_set_state(cudaStream_t st, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n, const int64_t* d_states) {
+    if (n <= 0) return;
+    k_envs_set_state<<<grid_for(n, 256), 256, 0, st>>>(p, cells, meta, n, d_states);
+    TWR_COUNT_LAUNCH();
+}
+void launch_envs_step(cudaStream_t st, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n, const int32_t* d_actions) {
+    if (n <= 0) return;
+    k_envs_step<<<grid_for(n, 256), 256, 0, st>>>(p, cells, meta, n, d_actions);
+    TWR_COUNT_LAUNCH();
+}
+void launch_envs_query(cudaStream_t st, const EnvParams& p, const uint4* cells, const uint32_t* meta, int64_t n,
+                       int64_t* d_states, int32_t* d_obs, uint8_t* d_masks, float* d_reward, uint8_t* d_final,
+                       uint8_t* d_success, int32_t* d_depth) {
+    if (n <= 0) return;
+    k_envs_query<<<grid_for(n, 256), 256, 0, st>>>(p, cells, meta, n, d_states, d_obs, d_masks, d_reward, d_final, d_success, d_depth);
+    TWR_COUNT_LAUNCH();
+}
+void launch_mask_logits(cudaStream_t st, const EnvParams& p, const uint4* cells, const uint32_t* meta, int64_t n, int A, float4* logits) {
+    if (n <= 0) return;
+    k_mask_logits<<<grid_for(n, 256), 256, 0, st>>>(p, cells, meta, n, A, logits);
+    TWR_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------- K3 ---
+__global__ void __launch_bounds__(256) k_sample(const float* __restrict__ logits, int64_t n, int A, uint64_t seed,
+                                                uint32_t env_id_base, uint32_t step, uint32_t cid,
+                                                int32_t* __restrict__ actions, float* __restrict__ uniforms) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[4];
+    philox4x32_10(env_id_base + (uint32_t)i, step, TWR_RNG_SAMPLE, cid, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    float l[4] = {0.f, 0.f, 0.f, 0.f}, u[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        u[a] = u32_to_unit_f32(w[a]);
+        if (a < A) l[a] = logits[i * A + a];
+        if (uniforms && a < A) uniforms[i * A + a] = u[a];
+    }
+    actions[i] = sample_from_logits4(l, u, A);
+}
+
+void launch_sample(cudaStream_t st, const float* d_logits, int64_t n, int A, uint64_t seed, uint32_t env_id_base,
+                   uint32_t step, uint32_t cid, int32_t* d_actions, float* d_uniforms) {
+    if (n <= 0) return;
+    k_sample<<<grid_for(n, 256), 256, 0, st>>>(d_logits, n, A, seed, env_id_base, step, cid, d_actions, d_uniforms);
+    TWR_COUNT_LAUNCH();
+}
+
+// ---------------------------------------------------- K3 + K4a + K1: collect step ---
+// One record of PPOCollector::single_collect's loop (collector/ppo.rs:69-80) for every live env:
+// reward(s_t), masked logits, value, Gumbel-max action, twist index -> record [t][env];
+// terminal states are recorded and retire (their action is not applied), the rest step and are
+// appended to the next live list with one atomicAdd per warp (ballot + popc prefix).
+__global__ void __launch_bounds__(256) k_collect_step(StepArgs a, CollectBuffers b, const int32_t* __restrict__ live_cur,
+                                                      int32_t* __restrict__ live_next) {
+    const int nl = b.n_live[a.t];
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = pos < nl;
+    bool survives = false;
+    int e = 0;
+    if (active) {
+        e = live_cur[pos];
+        EnvState s = env_load(b.cells, b.meta, e);
+        const uint32_t gid = a.env_id_base + (uint32_t)e;
+        const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+
+        int perm = -1;
+        if (a.n_perms > 0) {                                  // get_perm_id, nn/policy.rs:67-77
+            uint32_t w[4];
+            philox4x32_10(gid, (uint32_t)a.t, TWR_RNG_PERM, a.cid, k0, k1, w);
+            perm = (int)mulhi_u32(w[0], (uint32_t)a.n_perms);
+        }
+        const uint32_t m = env_masks(a.env, s);
+        const float4 raw = b.logits[pos];
+        float l[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l[i] = (i < a.A) ? (((m >> i) & 1u) ? l[i] : -1e10f) : 0.0f;  // policy.rs:62
+
+        uint32_t w[4];
+        philox4x32_10(gid, (uint32_t)a.t, TWR_RNG_SAMPLE, a.cid, k0, k1, w);
+        const float u[4] = {u32_to_unit_f32(w[0]), u32_to_unit_f32(w[1]), u32_to_unit_f32(w[2]), u32_to_unit_f32(w[3])};
+        const int act = sample_from_logits4(l, u, a.A);
+        const float rew = env_reward(a.env, s);
+        const bool fin = env_is_final(a.env, s);
+
+        const int64_t r = (int64_t)a.t * b.B + e;
+        b.rec_state[r] = env_pack_cells(s);
+        b.rec_logits[r] = make_float4(l[0], l[1], l[2], l[3]);
+        b.rec_value[r] = b.values[pos];
+        b.rec_reward[r] = rew;
+        b.rec_action[r] = (uint8_t)act;
+        b.rec_perm[r] = (int8_t)perm;
+
+        if (fin) {
+            b.ep_len[e] = a.t + 1;
+            if (env_success(a.env, s)) atomicAdd(&b.stats[0], 1ull);
+            atomicAdd(reinterpret_cast<double*>(&b.stats[2]), (double)rew);
+        } else {
+            env_step(a.env, s, act);
+            env_store(b.cells, b.meta, e, s);
+            survives = true;
+        }
+    }
+    // warp-aggregated append to the next live list
+    const unsigned bal = __ballot_sync(0xffffffffu, survives);
+    if (bal) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&b.n_live[a.t + 1], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (survives) live_next[base + __popc(bal & ((1u << lane) - 1u))] = e;
+    }
+}
+
+void launch_collect_step(cudaStream_t st, const StepArgs& a, const CollectBuffers& b, const int32_t* live_cur, int32_t* live_next) {
+    k_collect_step<<<grid_for(b.B, 256), 256, 0, st>>>(a, b, live_cur, live_next);
+    TWR_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------ K4b ---
+// GAE, collector/ppo.rs:82-92, evaluation order as written: ret = r + gamma*(v' + lambda*adv').
+// __fmul_rn/__fadd_rn keep nvcc from contracting into FMAs so the result is bit-identical to the
+// reference's unfused f32 arithmetic.
+__device__ __forceinline__ void gae_step(float r, float v, float v_next, float adv_next, float gamma, float lambda,
+                                         float& adv, float& ret) {
+    ret = __fadd_rn(r, __fmul_rn(gamma, __fadd_rn(v_next, __fmul_rn(lambda, adv_next))));
+    adv = __fsub_rn(ret, v);
+}
+
+__global__ void __launch_bounds__(256) k_gae_time_major(CollectBuffers b, float gamma, float lambda) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= b.B) return;
+    const int n = b.ep_len[e];
+    if (n <= 0) return;
+    int64_t r = (int64_t)(n - 1) * b.B + e;
+    float rew = b.rec_reward[r], v = b.rec_value[r];
+    float adv = __fsub_rn(rew, v), ret = rew;
+    b.rec_adv[r] = adv; b.rec_ret[r] = ret;
+    float v_next = v;
+    for (int t = n - 2; t >= 0; --t) {
+        r -= b.B;
+        rew = b.rec_reward[r]; v = b.rec_value[r];
+        gae_step(rew, v, v_next, adv, gamma, lambda, adv, ret);
+        b.rec_adv[r] = adv; b.rec_ret[r] = ret;
+        v_next = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gae_concat(const float* __restrict__ rw, const float* __restrict__ vl,
+                                                    const int64_t* __restrict__ off, int64_t n_ep, float gamma, float lambda,
+                                                    float* __restrict__ advs, float* __restrict__ rets) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ep) return;
+    const int64_t lo = off[e], hi = off[e + 1];
+    if (hi <= lo) return;
+    float adv = __fsub_rn(rw[hi - 1], vl[hi - 1]), ret = rw[hi - 1], v_next = vl[hi - 1];
+    advs[hi - 1] = adv; rets[hi - 1] = ret;
+    for (int64_t i = hi - 2; i >= lo; --i) {
+        const float v = vl[i];
+        gae_step(rw[i], v, v_next, adv, gamma, lambda, adv, ret);
+        advs[i] = adv; rets[i] = ret;
+        v_next = v;
+    }
+}
+
+void launch_gae_time_major(cudaStream_t st, const CollectBuffers& b, float gamma, float lambda) {
+    k_gae_time_major<<<grid_for(b.B, 256), 256, 0, st>>>(b, gamma, lambda);
+    TWR_COUNT_LAUNCH();
+}
+void launch_gae_concat(cudaStream_t st, const float* r, const float* v, const int64_t* off, int64_t n_ep, float gamma,
+                       float lambda, float* adv, float* ret) {
+    if (n_ep <= 0) return;
+    k_gae_concat<<<grid_for(n_ep, 256), 256, 0, st>>>(r, v, off, n_ep, gamma, lambda, adv, ret);
+    TWR_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------- K5 ---
+// Exclusive scan of episode lengths in the reference's merge order (collector/collector.rs:40-46:
+// slot 0 = last episode, slots 1.. = episodes 0..n-2).  One CTA; thread i owns a contiguous run.
+__global__ void __launch_bounds__(1024) k_episode_offsets(CollectBuffers b) {
+    __shared__ long long part[1024];
+    const int64_t B = b.B;
+    const int64_t per = (B + 1023) / 1024;
+    const int64_t s0 = (int64_t)threadIdx.x * per, s1 = min(B, s0 + per);
+    long long sum = 0;
+    for (int64_t s = s0; s < s1; ++s) sum += b.ep_len[s == 0 ? B - 1 : s - 1];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {       // Hillis-Steele inclusive scan
+        long long v = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    long long run = part[threadIdx.x] - sum;
+    for (int64_t s = s0; s < s1; ++s) {
+        const int64_t e = (s == 0) ? B - 1 : s - 1;
+        b.ep_off[e] = run;
+        run += b.ep_len[e];
+    }
+    if (threadIdx.x == 1023) b.stats[1] = (unsigned long long)part[1023];
+}
+
+void launch_episode_offsets(cudaStream_t st, const CollectBuffers& b) {
+    k_episode_offsets<<<1, 1024, 0, st>>>(b);
+    TWR_COUNT_LAUNCH();
+}
+
+// Transpose/compaction: tile of 32 episodes x 32 timesteps.  Loads are coalesced along the env
+// axis of the time-major records, stores are coalesced along time inside each episode's
+// contiguous output range.  The 16-byte state is expanded to the sparse one-hot indices the
+// reference returns from Env::observe (obs[i] = i*N + board[i]).
+template <typename T>
+__device__ __forceinline__ void transpose_field(const T* __restrict__ src, T* __restrict__ dst, T (*tile)[33],
+                                                const CollectBuffers& b, int64_t e0, int t0, const int* lens,
+                                                const long long* offs) {
+    for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
+        const int t = t0 + ty;
+        const int64_t e = e0 + threadIdx.x;
+        if (t < b.Tmax && e < b.B && t < lens[threadIdx.x]) tile[ty][threadIdx.x] = src[(int64_t)t * b.B + e];
+    }
+    __syncthreads();
+    for (int ey = threadIdx.y; ey < 32; ey += blockDim.y) {
+        const int t = t0 + threadIdx.x;
+        if (e0 + ey < b.B && t < lens[ey]) dst[offs[ey] + t] = tile[threadIdx.x][ey];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, int A) {
+    __shared__ int lens[32];
+    __shared__ long long offs[32];
+    __shared__ float tile_f[32][33];
+    __shared__ uint8_t tile_b[32][33];
+    __shared__ uint4 tile_q[32][33];
+    const int64_t e0 = (int64_t)blockIdx.x * 32;
+    const int t0 = blockIdx.y * 32;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    if (tid < 32) {
+        const int64_t e = e0 + tid;
+        lens[tid] = e < b.B ? b.ep_len[e] : 0;
+        offs[tid] = e < b.B ? b.ep_off[e] : 0;
+    }
+    __syncthreads();
+    int maxlen = 0;
+    for (int i = 0; i < 32; ++i) maxlen = max(maxlen, lens[i]);
+    if (t0 >= maxlen) return;
+
+    transpose_field<float>(b.rec_value, b.out_values, tile_f, b, e0, t0, lens, offs);
+    transpose_field<float>(b.rec_reward, b.out_rewards, tile_f, b, e0, t0, lens, offs);
+    transpose_field<float>(b.rec_adv, b.out_advs, tile_f, b, e0, t0, lens, offs);
+    transpose_field<float>(b.rec_ret, b.out_rets, tile_f, b, e0, t0, lens, offs);
+    transpose_field<uint8_t>(b.rec_action, b.out_actions, tile_b, b, e0, t0, lens, offs);
+    transpose_field<uint8_t>(reinterpret_cast<const uint8_t*>(b.rec_perm), reinterpret_cast<uint8_t*>(b.out_perms), tile_b,
+                             b, e0, t0, lens, offs);
+
+    // logits: [t][env] float4 -> [record][A] floats
+    for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
+        const int t = t0 + ty;
+        const int64_t e = e0 + threadIdx.x;
+        if (e < b.B && t < lens[threadIdx.x]) tile_q[ty][threadIdx.x] = reinterpret_cast<const uint4*>(b.rec_logits)[(int64_t)t * b.B + e];
+    }
+    __syncthreads();
+    for (int ey = threadIdx.y; ey < 32; ey += blockDim.y) {
+        const int nt = min(32, lens[ey] - t0);                 // records of this episode in the tile
+        if (e0 + ey >= b.B || nt <= 0) continue;
+        float* dst = b.out_logits + (offs[ey] + t0) * A;
+        for (int j = threadIdx.x; j < nt * A; j += 32) {
+            const uint4 q = tile_q[j / A][ey];
+            const int c = j % A;
+            const uint32_t w = c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w;
+            dst[j] = __uint_as_float(w);
+        }
+    }
+    __syncthreads();
+    // obs: 16-byte state -> N u16 one-hot indices per record
+    for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
+        const int t = t0 + ty;
+        const int64_t e = e0 + threadIdx.x;
+        if (e < b.B && t < lens[threadIdx.x]) tile_q[ty][threadIdx.x] = b.rec_state[(int64_t)t * b.B + e];
+    }
+    __syncthreads();
+    for (int ey = threadIdx.y; ey < 32; ey += blockDim.y) {
+        const int nt = min(32, lens[ey] - t0);
+        if (e0 + ey >= b.B || nt <= 0) continue;
+        uint16_t* dst = b.out_obs + (offs[ey] + t0) * p.N;
+        for (int j = threadIdx.x; j < nt * p.N; j += 32) {
+            const uint4 q = tile_q[j / p.N][ey];
+            EnvState s;
+            s.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
+            s.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
+            s.blank = 0; s.depth = 0;
+            const int i = j % p.N;
+            dst[j] = (uint16_t)(i * p.N + (int)env_board(p, s, i));
+        }
+    }
+}
+
+void launch_compact(cudaStream_t st, const EnvParams& p, const CollectBuffers& b, int A) {
+    dim3 grid(grid_for(b.B, 32), (unsigned)((b.Tmax + 31) / 32));
+    k_compact<<<grid, dim3(32, 8), 0, st>>>(p, b, A);
+    TWR_COUNT_LAUNCH();
+}

@@ -1,0 +1,93 @@
+// twr_kernels.cuh -- launch wrappers of every kernel in the engine (defined in the .cu files).
+#pragma once
+#include "twr_common.cuh"
+
+// Device-resident policy: fp32 master copy in the blob layout of include/twisterl_b200.h plus
+// derived operand layouts for the tensor-core path.
+struct PolicyDev {
+    int obs_size, E, H, A, n_obs;  // n_obs = one-hot indices per observation (cells)
+    int n_perms;
+    const float* emb;     // [obs_size][E]
+    const float* emb_b;   // [E]
+    const float* w1;      // [E][H]   (k-major: W.T.flatten())
+    const float* b1;      // [H]
+    const float* wa;      // [H][A]
+    const float* ba;      // [A]
+    const float* wv;      // [H]
+    const float* bv;      // [1]
+    const int32_t* obs_perms;  // [n_perms][obs_size]
+    const int32_t* act_perms;  // [n_perms][A]
+    // tensor-core operands (fp16 hi/lo split, UMMA canonical K-major tiles), see twr_forward_tc.cu
+    const void* tc_pack;
+};
+
+struct CollectBuffers {
+    int64_t B;      // envs (episodes) in this collect
+    int Tmax;       // horizon + 1 records at most
+    // env state
+    uint4* cells; uint32_t* meta;
+    // live lists: position-indexed
+    int32_t* live_a; int32_t* live_b; int32_t* n_live;  // n_live[Tmax+1]
+    // forward outputs, position-indexed
+    float4* logits; float* values;
+    // time-major records [t][env]
+    uint4* rec_state; float4* rec_logits; float* rec_value; float* rec_reward;
+    float* rec_adv; float* rec_ret; uint8_t* rec_action; int8_t* rec_perm;
+    int32_t* ep_len;      // [B]
+    int64_t* ep_off;      // [B] record offset of episode e in merged order
+    unsigned long long* stats;  // [0] successes, [1] total records ; double at [2] = reward sum
+    // compacted outputs
+    uint16_t* out_obs; float* out_logits; float* out_values; float* out_rewards;
+    float* out_advs; float* out_rets; uint8_t* out_actions; int8_t* out_perms;
+};
+
+struct StepArgs {
+    EnvParams env;
+    uint64_t seed; uint32_t cid; uint32_t env_id_base;
+    int n_perms; int A;
+    int t;
+};
+
+// K1: batched Env-trait kernels (parity API + reset)
+void launch_envs_reset(cudaStream_t s, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n,
+                       uint64_t seed, uint32_t env_id_base, uint32_t cid, int32_t* live, int32_t* n_live0);
+void launch_envs_fresh(cudaStream_t s, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n);
+void launch_envs_set_state(cudaStream_t s, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n,
+                           const int64_t* d_states);
+void launch_envs_step(cudaStream_t s, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n,
+                      const int32_t* d_actions);
+void launch_envs_query(cudaStream_t s, const EnvParams& p, const uint4* cells, const uint32_t* meta, int64_t n,
+                       int64_t* d_states, int32_t* d_obs, uint8_t* d_masks, float* d_reward, uint8_t* d_final,
+                       uint8_t* d_success, int32_t* d_depth);
+void launch_mask_logits(cudaStream_t s, const EnvParams& p, const uint4* cells, const uint32_t* meta, int64_t n,
+                        int A, float4* logits);
+// K3 standalone
+void launch_sample(cudaStream_t s, const float* d_logits, int64_t n, int A, uint64_t seed, uint32_t env_id_base,
+                   uint32_t step, uint32_t cid, int32_t* d_actions, float* d_uniforms);
+// K3+K4a+K1 fused collect step: mask, Gumbel-max sample, trajectory write, env step, live compaction
+void launch_collect_step(cudaStream_t s, const StepArgs& a, const CollectBuffers& b, const int32_t* live_cur,
+                         int32_t* live_next);
+// K4b GAE reverse scan (time-major records) and standalone (concatenated episodes)
+void launch_gae_time_major(cudaStream_t s, const CollectBuffers& b, float gamma, float lambda);
+void launch_gae_concat(cudaStream_t s, const float* r, const float* v, const int64_t* off, int64_t n_ep,
+                       float gamma, float lambda, float* adv, float* ret);
+// K5 episode offsets in merged order + transpose/compaction into concatenated episodes
+void launch_episode_offsets(cudaStream_t s, const CollectBuffers& b);
+void launch_compact(cudaStream_t s, const EnvParams& p, const CollectBuffers& b, int A);
+
+// K2 policy forward.  `live` may be NULL (identity); n_live_ptr may be NULL (use n).
+struct ForwardArgs {
+    EnvParams env;
+    uint64_t seed; uint32_t cid; uint32_t env_id_base; int t;  // twist pick stream
+    const int32_t* perm_idx;  // explicit per-position twist (parity API) or NULL -> Philox pick
+    const uint4* cells; const int32_t* live; const int32_t* n_live_ptr; int64_t n;
+    const int32_t* obs_rows;  // optional [n][n_obs] sparse obs given directly (Policy.forward API); overrides cells
+    float4* logits; float* values;
+};
+int  forward_fp32_supported(const PolicyDev& p, const EnvParams& env, const char** why);
+void launch_forward_fp32(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a);
+int  forward_tc_supported(const PolicyDev& p, const EnvParams& env, const char** why);
+// builds / refreshes the packed fp16 hi/lo operand tiles from the fp32 blob
+size_t forward_tc_pack_bytes(const PolicyDev& p);
+void launch_forward_tc_pack(cudaStream_t s, const PolicyDev& p, void* pack);
+void launch_forward_tc(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a);

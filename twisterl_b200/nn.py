@@ -1,0 +1,194 @@
+"""Host mirror of `twisterl.twisterl.nn` (rust/src/python_interface/{layers,modules,policy}.rs).
+
+The classes keep the constructor signatures `BasicPolicy.to_rust()` calls
+(src/twisterl/nn/utils.py:17-79, src/twisterl/nn/policy.py:191-199); the arithmetic runs on the
+device (kernel K2).  Weights stay in the layouts the reference hands over: `Linear` gets
+`W.T.flatten()`, `EmbeddingBag` gets `vec_vectors[obs_idx][E]`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Linear:
+    """`nn.Linear(weights_vector, bias_vector, apply_relu)` (python_interface/layers.rs:19-33)."""
+
+    def __init__(self, weights_vector, bias_vector, apply_relu: bool):
+        self.bias = _f32(bias_vector).ravel()
+        self.weights = _f32(weights_vector).ravel()
+        self.out = int(self.bias.size)
+        if self.out == 0 or self.weights.size % self.out:
+            raise ValueError("weights_vector length must be a multiple of len(bias_vector)")
+        self.in_ = self.weights.size // self.out              # layers.rs:26
+        self.apply_relu = bool(apply_relu)
+
+
+class EmbeddingBag:
+    """`nn.EmbeddingBag(vec_vectors, bias_vector, apply_relu, obs_shape, conv_dim)` (layers.rs:36-49)."""
+
+    def __init__(self, vec_vectors, bias_vector, apply_relu: bool, obs_shape, conv_dim: int):
+        self.vectors = _f32(vec_vectors)
+        if self.vectors.ndim != 2:
+            raise ValueError("vec_vectors must be a list of equal-length vectors")
+        self.bias = _f32(bias_vector).ravel()
+        self.apply_relu = bool(apply_relu)
+        self.obs_shape = [int(x) for x in obs_shape]
+        self.conv_dim = int(conv_dim)
+
+
+class Sequential:
+    """`nn.Sequential(layers)` (python_interface/modules.rs:19-33)."""
+
+    def __init__(self, layers):
+        self.layers = list(layers)
+        for l in self.layers:
+            if not isinstance(l, Linear):
+                raise TypeError("Sequential takes a list of nn.Linear")
+
+
+class Policy:
+    """`nn.Policy(embeddings, common, action_net, value_net, obs_perms, act_perms)`
+    (python_interface/policy.rs:20-46, rust/src/nn/policy.rs:20-128)."""
+
+    def __init__(self, embeddings: EmbeddingBag, common: Sequential, action_net: Sequential, value_net: Sequential,
+                 obs_perms, act_perms):
+        self.embeddings, self.common, self.action_net, self.value_net = embeddings, common, action_net, value_net
+        as2d = lambda p: (np.ascontiguousarray(p, dtype=np.int32).reshape(len(p), -1) if len(p)
+                          else np.zeros((0, 0), dtype=np.int32))
+        self.obs_perms, self.act_perms = as2d(obs_perms), as2d(act_perms)
+        if len(self.obs_perms) != len(self.act_perms):
+            raise ValueError("obs_perms and act_perms must have the same length")
+        self._dev = None          # (engine, handle)
+        self._keep = None
+
+    # -- C ABI descriptor -----------------------------------------------------------
+    def desc(self) -> _lib.PolicyDesc:
+        keep = []
+
+        def lin_array(seq: Sequential):
+            arr = (_lib.LinearDesc * max(len(seq.layers), 1))()
+            for i, l in enumerate(seq.layers):
+                arr[i] = _lib.LinearDesc(l.weights.ctypes.data_as(_lib.f32p), l.bias.ctypes.data_as(_lib.f32p),
+                                         l.in_, l.out, int(l.apply_relu))
+            keep.append(arr)
+            return arr
+
+        e = self.embeddings
+        d = _lib.PolicyDesc()
+        d.emb_vectors = e.vectors.ctypes.data_as(_lib.f32p)
+        d.emb_bias = e.bias.ctypes.data_as(_lib.f32p)
+        d.obs_size, d.emb_size = int(e.vectors.shape[0]), int(e.bias.size)
+        d.emb_apply_relu = int(e.apply_relu)
+        d.obs_shape_len = len(e.obs_shape)
+        for i, v in enumerate(e.obs_shape[:2]):
+            d.obs_shape[i] = v
+        d.conv_dim = e.conv_dim
+        d.common, d.n_common = lin_array(self.common), len(self.common.layers)
+        d.action_net, d.n_action = lin_array(self.action_net), len(self.action_net.layers)
+        d.value_net, d.n_value = lin_array(self.value_net), len(self.value_net.layers)
+        d.n_perms = int(len(self.obs_perms))
+        if d.n_perms:
+            d.obs_perms = self.obs_perms.ctypes.data_as(_lib.i32p)
+            d.act_perms = self.act_perms.ctypes.data_as(_lib.i32p)
+        self._keep = keep
+        return d
+
+    @property
+    def num_actions(self) -> int:
+        return int(self.action_net.layers[-1].out)
+
+    def device_handle(self, engine: _lib.Engine | None = None):
+        engine = engine or _lib.default_engine()
+        if self._dev is None or self._dev[0] is not engine:
+            self.release()
+            h = C.c_void_p()
+            d = self.desc()
+            _lib.check(_lib.load().twr_policy_create(engine._h, C.byref(d), C.byref(h)))
+            self._dev = (engine, h)
+        return self._dev[1]
+
+    def release(self):
+        if self._dev is not None:
+            eng, h = self._dev
+            if getattr(eng, "_h", None):
+                _lib.load().twr_policy_destroy(h)
+            self._dev = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    # -- scalar API of the reference ---------------------------------------------------
+    def _raw(self, obs, perm_idx: int, engine=None):
+        """_raw_predict (nn/policy.rs:79-100) of one sparse observation, on the device."""
+        engine = engine or _lib.default_engine()
+        return forward_obs(engine, self, [list(obs)], None if perm_idx < 0 else [perm_idx])
+
+    def _pick_perm(self) -> int:
+        # get_perm_id (nn/policy.rs:67-77): uniform over the twists; the reference is unseeded here too
+        return int(np.random.randint(len(self.obs_perms))) if len(self.obs_perms) else -1
+
+    def forward(self, obs, masks):
+        logits, value = self._raw(obs, self._pick_perm())
+        l = np.where(np.asarray(masks, dtype=bool), logits[0], np.float32(-1e10)).astype(np.float32)   # policy.rs:62
+        return [float(x) for x in l], float(value[0])
+
+    def predict(self, obs, masks):
+        logits, value = self._raw(obs, self._pick_perm())
+        return _masked_exp_normalise(logits[0], masks), float(value[0])
+
+    def full_predict(self, obs, masks):
+        if len(self.obs_perms) == 0:
+            return self.predict(obs, masks)
+        n = np.float32(len(self.obs_perms))
+        acc = np.zeros(self.num_actions, dtype=np.float32)
+        val = np.float32(0)
+        for pi in range(len(self.obs_perms)):                  # policy.rs:109-115
+            l, v = self._raw(obs, pi)
+            val = np.float32(val + v[0] / n)
+            acc = (acc + l[0] / n).astype(np.float32)
+        return _masked_exp_normalise(acc, masks), float(val)
+
+
+def _masked_exp_normalise(logits, masks):
+    m = np.asarray(masks, dtype=bool)
+    e = np.where(m, np.exp(logits.astype(np.float32)), np.float32(0)).astype(np.float32)   # policy.rs:43-47
+    s = np.float32(e.sum(dtype=np.float32) + np.float32(1e-6))
+    return [float(x) for x in (e / s)]
+
+
+def forward_batch(engine: _lib.Engine, policy: Policy, batch, perm_idx=None, apply_masks: bool = False):
+    """Batched _raw_predict / forward_with_perm (twr_policy_forward): (logits [n][A], values [n])."""
+    n, A = batch.n, policy.num_actions
+    logits = np.zeros((n, A), dtype=np.float32)
+    values = np.zeros(n, dtype=np.float32)
+    pi = None
+    if perm_idx is not None:
+        pi = np.ascontiguousarray(perm_idx, dtype=np.int32).reshape(n)
+    _lib.check(_lib.load().twr_policy_forward(engine._h, policy.device_handle(engine), batch._h,
+                                              _lib.ptr(pi) if pi is not None else None, int(apply_masks),
+                                              _lib.ptr(logits), _lib.ptr(values)))
+    return logits, values
+
+
+def forward_obs(engine: _lib.Engine, policy: Policy, obs, perm_idx=None):
+    """Batched _raw_predict on sparse observations given directly (twr_policy_forward_obs)."""
+    o = np.ascontiguousarray(obs, dtype=np.int32)
+    n, n_obs = o.shape
+    logits = np.zeros((n, policy.num_actions), dtype=np.float32)
+    values = np.zeros(n, dtype=np.float32)
+    pi = None if perm_idx is None else np.ascontiguousarray(perm_idx, dtype=np.int32).reshape(n)
+    _lib.check(_lib.load().twr_policy_forward_obs(engine._h, policy.device_handle(engine), _lib.ptr(o), n, n_obs,
+                                                  _lib.ptr(pi) if pi is not None else None, _lib.ptr(logits),
+                                                  _lib.ptr(values)))
+    return logits, values

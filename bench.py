@@ -295,7 +295,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TWISTERL_B200_PRECISION", "fp32"), choices=["fp32", "f16x2"])
+    ap.add_argument("--precision", default=os.environ.get("TWISTERL_B200_PRECISION", "f16x2"), choices=["fp32", "f16x2"])
     ap.add_argument("--episodes", type=int, default=65536)
     ap.add_argument("--difficulty", type=int, default=128)
     ap.add_argument("--ref-episodes", type=int, default=2048)

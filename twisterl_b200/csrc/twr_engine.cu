@@ -542,6 +542,13 @@ int twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* ob
     if (perm_idx)
         for (int64_t i = 0; i < n; ++i)
             if (perm_idx[i] < -1 || perm_idx[i] >= p->dev.n_perms) return fail(TWR_ERR_INVALID, "perm_idx out of range");
+    if (e->precision == TWR_PREC_F16X2) {   // the one-hot GEMM operand cannot express a repeated index
+        for (int64_t i = 0; i < n; ++i)
+            for (int a2 = 0; a2 < n_obs; ++a2)
+                for (int b2 = a2 + 1; b2 < n_obs; ++b2)
+                    if (obs[i * n_obs + a2] == obs[i * n_obs + b2])
+                        return fail(TWR_ERR_UNSUPPORTED, "repeated observation index: use TWR_PREC_FP32 for multiset observations");
+    }
     CU_TRY(cudaSetDevice(e->device));
     PolicyDev dev = p->dev;
     dev.n_obs = n_obs;

@@ -155,6 +155,11 @@ int  twr_policy_forward(twr_engine* e, const twr_policy* p, twr_envs* v, const i
 int  twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* obs, int64_t n, int32_t n_obs,
                             const int32_t* perm_idx, float* logits, float* values);
 
+/* Debug: one forward over `v` with per-CTA cycle counters of the tensor-core kernel's pipeline waits
+ * (16 int64 per CTA, max_ctas >= number of SMs; layout documented in twr_forward_tc.cu). */
+int  twr_debug_forward_profile(twr_engine* e, const twr_policy* p, twr_envs* v, int64_t* counters, int32_t max_ctas,
+                               int32_t experiment_flags /* 0 = none; results are invalid when non-zero */);
+
 /* sample_from_logits (rust/src/nn/policy.rs:169-172) for n logit rows, row i using the uniforms
  * of Philox stream (env_id_base + i, step, sample, collect_id).  uniforms_out may be NULL. */
 int  twr_sample(twr_engine* e, const float* logits, int64_t n, int32_t num_actions,

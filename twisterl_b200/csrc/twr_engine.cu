@@ -531,6 +531,25 @@ int twr_policy_forward(twr_engine* e, const twr_policy* p, twr_envs* v, const in
     return TWR_OK;
 }
 
+int twr_debug_forward_profile(twr_engine* e, const twr_policy* p, twr_envs* v, int64_t* counters, int32_t max_ctas, int32_t flags) {
+    if (!e || !p || !v || !counters) return fail(TWR_ERR_INVALID, "NULL argument");
+    PolicyDev dev;
+    int rc = check_policy_env(p, v->p, &dev);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(e->device));
+    Staging<float4> d_logits; Staging<float> d_values; Staging<long long> d_dbg;
+    if ((rc = d_logits.alloc((size_t)v->n)) || (rc = d_values.alloc((size_t)v->n)) || (rc = d_dbg.alloc((size_t)max_ctas * 16))) return rc;
+    CU_TRY(cudaMemsetAsync(d_dbg.d, 0, sizeof(long long) * (size_t)max_ctas * 16, e->stream));
+    ForwardArgs a{};
+    a.env = v->p; a.seed = e->seed; a.t = -1; a.cells = v->cells; a.n = v->n;
+    a.logits = d_logits.d; a.values = d_values.d; a.dbg = d_dbg.d; a.dbg_flags = flags;
+    launch_forward(e, dev, a);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(counters, d_dbg.d, sizeof(long long) * (size_t)max_ctas * 16, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return TWR_OK;
+}
+
 int twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* obs, int64_t n, int32_t n_obs,
                            const int32_t* perm_idx, float* logits, float* values) {
     if (!e || !p || !obs || !logits || !values) return fail(TWR_ERR_INVALID, "NULL argument");

@@ -12,12 +12,13 @@
 //
 // Structure (persistent, one CTA per SM, 192 threads):
 //   warp 0      TMA producer: streams 16 KB operand tiles (pre-swizzled in HBM/L2 by k_tc_pack, so a
-//               tile is one contiguous cp.async.bulk) into a 5-slot shared-memory ring
+//               tile is one contiguous cp.async.bulk) into an 8-slot shared-memory ring
 //   warp 1      MMA issuer: one elected lane issues tcgen05.mma (M=128, N=128, K=16, kind::f16);
 //               accumulators live in TMEM: D2 in columns [0,H), D1 double-buffered in [256,512)
 //   warps 2..5  epilogue: thread == env row.  Build the one-hot A1 tile (K-major, 128B swizzle) from
-//               the 16-byte env state, tcgen05.ld D1 -> bias/ReLU/split -> st.shared A2 (swizzled),
-//               tcgen05.ld D2 -> heads on CUDA cores -> logits/values
+//               the 16-byte env state, tcgen05.ld D1 -> bias/ReLU/fp16 split -> tcgen05.st back into the
+//               same TMEM columns (GEMM2 reads its A operand from TMEM), tcgen05.ld D2 -> heads on CUDA
+//               cores -> logits/values
 //   All hand-offs are mbarriers; tcgen05.commit releases ring slots / publishes accumulators.
 //   E is processed in chunks of 128 columns: G1(c) fills D1[c&1], epilogue1(c) turns it into the
 //   A2 k-chunk, G2(c) accumulates it into D2, while G1(c+1) already runs -- and epilogue2 of tile i
@@ -26,8 +27,10 @@
 // Algorithmic flop per env-step: 2*E*H + n_obs*E + 2*H*5 (272 896 for puzzle15); executed tensor
 // flop: 2*K1*E*2 + 2*E*H*3.  Bound: tensor pipe / L2->SMEM operand streaming (1 MB per tile).
 #include "twr_kernels.cuh"
+#include "twr_tc_ptx.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 extern std::atomic<long long> g_twr_launches;
@@ -37,16 +40,14 @@ namespace {
 constexpr int TM = 128;               // envs per tile (UMMA M)
 constexpr int NTHREADS = 192;
 constexpr int TILE_BYTES = 16384;     // [128 rows x 64 k] fp16, K-major, 128B swizzle
-constexpr int NSLOTS = 5;
+constexpr int NSLOTS = 8;
 constexpr int MAX_KB1 = 4;            // obs_size <= 256
 constexpr int MAX_OBS = 32;
 
 // ---- shared memory map (dynamic, 1024-byte aligned base) ----
 constexpr int SM_A1 = 0;                                  // MAX_KB1 tiles
-constexpr int SM_A2H = SM_A1 + MAX_KB1 * TILE_BYTES;      // 2 tiles (128 k)
-constexpr int SM_A2L = SM_A2H + 2 * TILE_BYTES;           // 2 tiles
-constexpr int SM_RING = SM_A2L + 2 * TILE_BYTES;          // NSLOTS tiles
-constexpr int SM_MISC = SM_RING + NSLOTS * TILE_BYTES;    // 212992
+constexpr int SM_RING = SM_A1 + MAX_KB1 * TILE_BYTES;     // NSLOTS tiles
+constexpr int SM_MISC = SM_RING + NSLOTS * TILE_BYTES;    // 196608
 constexpr int SM_HEADW = SM_MISC;                         // [256][8] float = 8192
 constexpr int SM_B1 = SM_HEADW + 8192;                    // [256] float
 constexpr int SM_EMBB = SM_B1 + 1024;                     // [1024] float (E <= 1024)
@@ -55,80 +56,12 @@ constexpr int SM_BARS = SM_ROWS + TM * MAX_OBS;           // mbarriers
 constexpr int SM_TOTAL = SM_BARS + 256;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
-enum Bar { B_FULL0 = 0, B_EMPTY0 = NSLOTS, B_A1_FULL = 2 * NSLOTS, B_A1_EMPTY, B_D1_FULL0, B_D1_FULL1, B_D1_EMPTY0,
-           B_D1_EMPTY1, B_A2_FULL, B_A2_EMPTY, B_D2_FULL, B_D2_EMPTY, B_COUNT };
+enum Bar { B_FULL0 = 0, B_EMPTY0 = NSLOTS, B_A1_FULL = 2 * NSLOTS, B_A1_EMPTY, B_D1_FULL0, B_D1_FULL1, B_A2_FULL0,
+           B_A2_FULL1, B_D2_FULL, B_D2_EMPTY, B_COUNT };
 static_assert(B_COUNT * 8 + 8 <= 256, "barrier area");
 
-// ---- PTX wrappers ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// PTX wrappers, descriptors and tile_off(): twr_tc_ptx.cuh
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Spin with a watchdog: a protocol bug traps (launch error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spins = 0; !done; ++spins) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (!done && spins > (1u << 22)) __trap();
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_commit(uint32_t bar) {   // arrives on `bar` when all prior MMAs of this thread finish
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T ; M=128, N=128, K=16, fp16 in, fp32 accumulate
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i), columns [col, col+32)
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (=1024 B between
-// 8-row groups) | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=b=F16 (0), K-major both,
-// N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t IDESC_128x128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-
-// byte offset of element (row, k) inside one [128 x 64] fp16 tile, K-major with 128B swizzle
-__host__ __device__ __forceinline__ uint32_t tile_off(uint32_t row, uint32_t k) {
-    return (row >> 3) * 1024u + (row & 7u) * 128u + ((((k >> 3) ^ row) & 7u) << 4) + (k & 7u) * 2u;
-}
 
 struct TcParams {
     int NC;      // E / 128 chunks
@@ -176,14 +109,21 @@ __global__ void __launch_bounds__(256) k_tc_pack(PolicyDev p, TcParams t, __half
 }
 
 // -------------------------------------------------------------------- kernel ---
-template <int NH>   // H = 128 * NH
+// CSZ = thread-block cluster size: the CSZ CTAs of a cluster walk the same operand stream, each CTA
+// fetches every CSZ-th tile and TMA-multicasts it into the ring of all of them (L2 -> SM traffic / CSZ).
+template <int NH, int CSZ>   // H = 128 * NH
 __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, ForwardArgs a, TcParams t) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n = a.n_live_ptr ? (int64_t)*a.n_live_ptr : a.n;
     const int n_tiles = (int)((n + TM - 1) / TM);
-    if ((int)blockIdx.x >= n_tiles) return;
-    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int crank = CSZ > 1 ? (int)cluster_ctarank() : 0;
+    const int cluster_id = (int)blockIdx.x / CSZ, n_clusters = (int)gridDim.x / CSZ;
+    const int n_groups = (n_tiles + CSZ - 1) / CSZ;            // a group = CSZ consecutive tiles, one per CTA
+    if (cluster_id >= n_groups) return;                        // cluster-uniform
+    const int my_tiles = (n_groups - cluster_id + n_clusters - 1) / n_clusters;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CSZ) - 1u);
+    auto tile_of = [&](int it) -> int64_t { return ((int64_t)cluster_id + (int64_t)it * n_clusters) * CSZ + crank; };
 
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + SM_BARS;
@@ -197,11 +137,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
 
     // ---- one-time setup
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NSLOTS; ++i) { mbar_init(bar(B_FULL0 + i), 1); mbar_init(bar(B_EMPTY0 + i), 1); }
+        for (int i = 0; i < NSLOTS; ++i) { mbar_init(bar(B_FULL0 + i), 1); mbar_init(bar(B_EMPTY0 + i), CSZ); }
         mbar_init(bar(B_A1_FULL), 128); mbar_init(bar(B_A1_EMPTY), 1);
         mbar_init(bar(B_D1_FULL0), 1); mbar_init(bar(B_D1_FULL1), 1);
-        mbar_init(bar(B_D1_EMPTY0), 128); mbar_init(bar(B_D1_EMPTY1), 128);
-        mbar_init(bar(B_A2_FULL), 128); mbar_init(bar(B_A2_EMPTY), 1);
+        mbar_init(bar(B_A2_FULL0), 128); mbar_init(bar(B_A2_FULL1), 128);
         mbar_init(bar(B_D2_FULL), 1); mbar_init(bar(B_D2_EMPTY), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -223,9 +162,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
+    if (CSZ > 1) cluster_sync_all();       // peers' barriers are initialised before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t D2_COL = 0, D1_COL = 256;
+    const bool timed = a.dbg != nullptr;
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
@@ -233,11 +174,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
             const unsigned char* g1 = reinterpret_cast<const unsigned char*>(p.tc_pack);
             const unsigned char* g2 = g1 + g1_tiles(t) * TILE_BYTES;
             uint32_t use = 0;
+            long long w_empty = 0;
             auto push = [&](const unsigned char* src) {
                 const uint32_t slot = use % NSLOTS, round = use / NSLOTS;
-                mbar_wait(bar(B_EMPTY0 + slot), (round & 1u) ^ 1u);
+                mbar_wait_t(bar(B_EMPTY0 + slot), (round & 1u) ^ 1u, w_empty, timed);
                 mbar_expect_tx(bar(B_FULL0 + slot), TILE_BYTES);
-                bulk_g2s(sbase + SM_RING + slot * TILE_BYTES, src, TILE_BYTES, bar(B_FULL0 + slot));
+                if (CSZ == 1) bulk_g2s(sbase + SM_RING + slot * TILE_BYTES, src, TILE_BYTES, bar(B_FULL0 + slot));
+                else if ((int)(use % CSZ) == crank)
+                    bulk_g2s_mc(sbase + SM_RING + slot * TILE_BYTES, src, TILE_BYTES, bar(B_FULL0 + slot), CMASK);
                 ++use;
             };
             auto push_g1 = [&](int c) { for (int i = 0; i < 2 * NKB1; ++i) push(g1 + ((size_t)c * 2 * NKB1 + i) * TILE_BYTES); };
@@ -247,26 +191,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
                 for (int c = 1; c < NC; ++c) { push_g1(c); push_g2(c - 1); }
                 push_g2(NC - 1);
             }
+            if (a.dbg) a.dbg[blockIdx.x * 16 + 8] = w_empty;
         }
         __syncwarp();
     } else if (warp == 1) {
         // =============================== MMA issuer =================================
         if (lane == 0) {
             uint32_t use = 0, d1use = 0, a2use = 0;
+            long long w_slot = 0, w_a1 = 0, w_a2 = 0, w_d2 = 0;
+            const long long t_begin = clock64();
             auto wait_slot = [&]() -> uint32_t {
                 const uint32_t slot = use % NSLOTS, round = use / NSLOTS;
-                mbar_wait(bar(B_FULL0 + slot), round & 1u);
+                mbar_wait_t(bar(B_FULL0 + slot), round & 1u, w_slot, timed);
                 tc_fence_after();
                 ++use;
                 return slot;
             };
             for (int it = 0; it < my_tiles; ++it) {
-                mbar_wait(bar(B_A1_FULL), it & 1);
+                mbar_wait_t(bar(B_A1_FULL), it & 1, w_a1, timed);
                 tc_fence_after();
                 auto g1 = [&](int c) {
+                    // D1 buffer (c & 1) is free: its previous contents (chunk c-2, rewritten in place as the
+                    // fp16 A operand) were consumed by G2(c-2), issued earlier on this same in-order pipe
                     const uint32_t buf = d1use & 1u;
-                    mbar_wait(bar(B_D1_EMPTY0 + buf), ((d1use >> 1) & 1u) ^ 1u);
-                    tc_fence_after();
                     const uint32_t d = tmem + D1_COL + buf * 128u;
                     for (int kb = 0; kb < NKB1; ++kb) {
                         for (int part = 0; part < 2; ++part) {
@@ -276,7 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
                                 tc_mma(d, ad + 2u * ks, bd + 2u * ks, IDESC_128x128, (kb | part | ks) != 0);
-                            tc_commit(bar(B_EMPTY0 + slot));
+                            if (CSZ == 1) tc_commit(bar(B_EMPTY0 + slot)); else tc_commit_mc(bar(B_EMPTY0 + slot), CMASK);
                         }
                     }
                     tc_commit(bar(B_D1_FULL0 + buf));
@@ -284,12 +231,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
                     ++d1use;
                 };
                 auto g2 = [&](int j) {
-                    mbar_wait(bar(B_A2_FULL), a2use & 1u);
+                    const uint32_t buf = a2use & 1u;
+                    mbar_wait_t(bar(B_A2_FULL0 + buf), (a2use >> 1) & 1u, w_a2, timed);
                     tc_fence_after();
-                    if (j == 0) { mbar_wait(bar(B_D2_EMPTY), (it & 1) ^ 1); tc_fence_after(); }
+                    if (j == 0) { mbar_wait_t(bar(B_D2_EMPTY), (it & 1) ^ 1, w_d2, timed); tc_fence_after(); }
+                    const uint32_t a_base = tmem + D1_COL + buf * 128u;   // hi at +32q+8r, lo 16 columns further
                     for (int kb = 0; kb < 2; ++kb) {
-                        const uint64_t ah = make_desc(sbase + SM_A2H + kb * TILE_BYTES);
-                        const uint64_t al = make_desc(sbase + SM_A2L + kb * TILE_BYTES);
                         for (int part = 0; part < 2; ++part) {          // 0: W hi tiles, 1: W lo tiles
                             for (int half = 0; half < NH; ++half) {
                                 const uint32_t slot = wait_slot();
@@ -297,23 +244,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
                                 const uint32_t d = tmem + D2_COL + half * 128u;
                                 const bool first = (j == 0 && kb == 0 && part == 0);
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    tc_mma(d, ah + 2u * ks, bd + 2u * ks, IDESC_128x128, !(first && ks == 0));
-                                if (part == 0) {
-#pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks) tc_mma(d, al + 2u * ks, bd + 2u * ks, IDESC_128x128, 1u);
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint32_t sidx = kb * 4 + ks;   // K=16 step inside the 128-wide chunk
+                                    const uint32_t ah = a_base + 32u * (sidx >> 1) + 8u * (sidx & 1u);
+                                    tc_mma_ts(d, ah, bd + 2u * ks, IDESC_128x128, !(first && ks == 0));
+                                    if (part == 0) tc_mma_ts(d, ah + 16u, bd + 2u * ks, IDESC_128x128, 1u);
                                 }
-                                tc_commit(bar(B_EMPTY0 + slot));
+                                if (CSZ == 1) tc_commit(bar(B_EMPTY0 + slot)); else tc_commit_mc(bar(B_EMPTY0 + slot), CMASK);
                             }
                         }
                     }
-                    tc_commit(bar(B_A2_EMPTY));
                     ++a2use;
                     if (j == NC - 1) tc_commit(bar(B_D2_FULL));
                 };
                 g1(0);
                 for (int c = 1; c < NC; ++c) { g1(c); g2(c - 1); }
                 g2(NC - 1);
+            }
+            if (a.dbg) {
+                long long* d = a.dbg + blockIdx.x * 16;
+                d[0] = clock64() - t_begin; d[1] = w_slot; d[2] = w_a1; d[3] = w_a2; d[4] = w_d2; d[5] = my_tiles;
             }
         }
         __syncwarp();
@@ -323,13 +273,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
         const int row = quarter * 32 + lane;          // env row inside the tile
         const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
         const int n_obs = p.n_obs;
-        uint32_t d1use = 0, a2use = 0;
+        uint32_t d1use = 0;
         int perm_cur = -1;
+        long long w_d1 = 0, w_d2f = 0, w_a1e = 0;
+        const long long t_begin = clock64();
 
         // one-hot A1 tile for tile `it`: clear the previous ones of this row, set the new ones
         auto build_a1 = [&](int it) -> int {
-            mbar_wait(bar(B_A1_EMPTY), (it & 1) ^ 1);
-            const int64_t pos = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TM + row;
+            mbar_wait_t(bar(B_A1_EMPTY), (it & 1) ^ 1, w_a1e, timed);
+            const int64_t pos = tile_of(it) * TM + row;
             int perm = -1;
             EnvState s; s.lo = 0; s.hi = 0; s.blank = 0; s.depth = 0;
             int64_t e = 0;
@@ -371,47 +323,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
         int perm_next = build_a1(0);
         for (int it = 0; it < my_tiles; ++it) {
             perm_cur = perm_next;
-            // ---- epilogue 1: D1 chunk -> relu(x + bias) -> fp16 hi/lo -> A2 (swizzled K-major)
+            // ---- epilogue 1: D1 chunk -> relu(x + bias) -> fp16 hi/lo, written back IN PLACE into the same
+            //      TMEM columns as the A operand of GEMM2: batch q (32 fp32 columns) becomes 16 columns of
+            //      packed hi pairs followed by 16 columns of packed lo pairs
             for (int c = 0; c < NC; ++c) {
                 const uint32_t buf = d1use & 1u;
-                mbar_wait(bar(B_D1_FULL0 + buf), (d1use >> 1) & 1u);
+                mbar_wait_t(bar(B_D1_FULL0 + buf), (d1use >> 1) & 1u, w_d1, timed);
                 tc_fence_after();
-                for (int q = 0; q < 4; ++q) {                       // 4 x 32 columns = 2 k-blocks of 64
-                    uint32_t v[32];
-                    tc_ld32(tmem + lane_addr + D1_COL + buf * 128u + q * 32u, v);
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t v[32], w[32];
+                    const uint32_t taddr = tmem + lane_addr + D1_COL + buf * 128u + q * 32u;
+                    tc_ld32(taddr, v);
                     tc_wait_ld();
-                    if (q == 0) mbar_wait(bar(B_A2_EMPTY), (a2use & 1u) ^ 1u);   // GEMM2 of the previous chunk done with A2
                     const float* bias = embb + c * 128 + q * 32;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {                   // 8 columns -> one 16-byte chunk per hi / lo
-                        uint32_t hp[4], lp[4];
-#pragma unroll
-                        for (int e2 = 0; e2 < 4; ++e2) {
-                            float x0 = __uint_as_float(v[g * 8 + e2 * 2]) + bias[g * 8 + e2 * 2];
-                            float x1 = __uint_as_float(v[g * 8 + e2 * 2 + 1]) + bias[g * 8 + e2 * 2 + 1];
-                            x0 = x0 > 0.f ? x0 : 0.f; x1 = x1 > 0.f ? x1 : 0.f;
-                            const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-                            const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-                            hp[e2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                            lp[e2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                        }
-                        const uint32_t kcol = q * 32 + g * 8;       // k inside the 128-wide chunk
-                        const uint32_t off = (kcol >> 6) * TILE_BYTES + tile_off(row, kcol & 63u);
-                        *reinterpret_cast<uint4*>(smem + SM_A2H + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                        *reinterpret_cast<uint4*>(smem + SM_A2L + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+                    for (int e2 = 0; e2 < 16; ++e2) {
+                        float x0 = __uint_as_float(v[2 * e2]) + bias[2 * e2];
+                        float x1 = __uint_as_float(v[2 * e2 + 1]) + bias[2 * e2 + 1];
+                        x0 = x0 > 0.f ? x0 : 0.f; x1 = x1 > 0.f ? x1 : 0.f;
+                        const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                        const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+                        w[e2] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                        w[16 + e2] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
                     }
+                    tc_st32(taddr, w);
                 }
+                tc_wait_st();
                 tc_fence_before();
-                mbar_arrive(bar(B_D1_EMPTY0 + buf));
-                fence_async_smem();
-                mbar_arrive(bar(B_A2_FULL));
-                ++d1use; ++a2use;
+                mbar_arrive(bar(B_A2_FULL0 + buf));
+                ++d1use;
             }
             // ---- next tile's one-hot operand, so its GEMM1 overlaps this tile's heads
             if (it + 1 < my_tiles) perm_next = build_a1(it + 1);
 
             // ---- epilogue 2: heads on CUDA cores from the fp32 accumulator row
-            mbar_wait(bar(B_D2_FULL), it & 1);
+            mbar_wait_t(bar(B_D2_FULL), it & 1, w_d2f, timed);
             tc_fence_after();
             float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
             for (int q = 0; q < H / 32; ++q) {
@@ -432,7 +378,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
             }
             tc_fence_before();
             mbar_arrive(bar(B_D2_EMPTY));
-            const int64_t pos = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * TM + row;
+            const int64_t pos = tile_of(it) * TM + row;
             if (pos < n) {
                 float l[4];
 #pragma unroll
@@ -451,11 +397,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
                 a.values[pos] = acc[4] + p.bv[0];
             }
         }
+        if (a.dbg && threadIdx.x == 64) {
+            long long* d = a.dbg + blockIdx.x * 16;
+            d[9] = clock64() - t_begin; d[10] = w_d1; d[11] = w_d2f; d[12] = w_a1e;
+        }
     }
 
     // ---- teardown: everyone done with TMEM, then the allocating warp frees it
     tc_fence_before();
     __syncthreads();
+    if (CSZ > 1) cluster_sync_all();       // no peer may still multicast into / arrive on this CTA's shared memory
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
@@ -475,6 +426,7 @@ int g_num_sms = 0;
 
 }  // namespace
 
+
 int forward_tc_supported(const PolicyDev& p, const EnvParams&, const char** why) {
     static const char* m1 = "tensor-core forward needs obs_size <= 256 (one-hot operand must fit 64 KB of shared memory)";
     static const char* m2 = "tensor-core forward needs embedding size a multiple of 128, <= 1024";
@@ -487,16 +439,35 @@ int forward_tc_supported(const PolicyDev& p, const EnvParams&, const char** why)
     return 1;
 }
 
-size_t forward_tc_pack_bytes(const PolicyDev& p) {
+static size_t single_pack_bytes(const PolicyDev& p) {
     const TcParams t = make_params(p);
     return (g1_tiles(t) + g2_tiles(t)) * TILE_BYTES;
 }
+
+// [single-CTA operand image][CTA-pair operand image]
+size_t forward_tc_pack_bytes(const PolicyDev& p) { return single_pack_bytes(p) + forward_tc2_pack_bytes(p); }
 
 void launch_forward_tc_pack(cudaStream_t st, const PolicyDev& p, void* pack) {
     const TcParams t = make_params(p);
     k_tc_pack<<<1024, 256, 0, st>>>(p, t, reinterpret_cast<__half*>(pack));
     g_twr_launches.fetch_add(1, std::memory_order_relaxed);
+    if (forward_tc2_supported(p)) launch_forward_tc2_pack(st, p, reinterpret_cast<unsigned char*>(pack) + single_pack_bytes(p));
 }
+
+template <int NH, int CSZ>
+void launch_cfg(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a, const TcParams& t, int grid) {
+    auto kern = k_forward_tc<NH, CSZ>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SM_TOTAL; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CSZ; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, p, a, t);
+}
+
+int g_cluster = -1, g_pair = -1;
 
 void launch_forward_tc(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a) {
     if (a.n <= 0) return;
@@ -505,15 +476,29 @@ void launch_forward_tc(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
+    if (g_pair < 0) {
+        const char* m = getenv("TWISTERL_B200_TC_MODE");      // "pair" (default) | "single"
+        g_pair = (m && m[0] == 's') ? 0 : 1;
+    }
+    if (g_pair && forward_tc2_supported(p)) {
+        if (launch_forward_tc2(st, p, a, reinterpret_cast<const unsigned char*>(p.tc_pack) + single_pack_bytes(p))) return;
+        g_pair = 0;   // tensor map could not be created: use the single-CTA kernel from now on
+    }
+    if (g_cluster < 0) {
+        const char* e = getenv("TWISTERL_B200_CLUSTER");
+        g_cluster = e ? atoi(e) : 1;
+        if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 1;
+    }
     const TcParams t = make_params(p);
+    const int csz = g_cluster;
     const int n_tiles = (int)((a.n + TM - 1) / TM);
-    const int grid = n_tiles < g_num_sms ? n_tiles : g_num_sms;
+    const int n_groups = (n_tiles + csz - 1) / csz;
+    const int max_clusters = g_num_sms / csz;
+    const int grid = (n_groups < max_clusters ? n_groups : max_clusters) * csz;
     if (t.NH == 2) {
-        cudaFuncSetAttribute(k_forward_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-        k_forward_tc<2><<<grid, NTHREADS, SM_TOTAL, st>>>(p, a, t);
+        if (csz == 1) launch_cfg<2, 1>(st, p, a, t, grid); else if (csz == 2) launch_cfg<2, 2>(st, p, a, t, grid); else launch_cfg<2, 4>(st, p, a, t, grid);
     } else {
-        cudaFuncSetAttribute(k_forward_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-        k_forward_tc<1><<<grid, NTHREADS, SM_TOTAL, st>>>(p, a, t);
+        if (csz == 1) launch_cfg<1, 1>(st, p, a, t, grid); else if (csz == 2) launch_cfg<1, 2>(st, p, a, t, grid); else launch_cfg<1, 4>(st, p, a, t, grid);
     }
     g_twr_launches.fetch_add(1, std::memory_order_relaxed);
 }

@@ -1,0 +1,552 @@
+// twr_forward_tc2.cu -- K2, tensor-core variant with CTA pairs (tcgen05 cta_group::2).
+//
+// Same math and pipeline as twr_forward_tc.cu (one-hot GEMM1 -> TMEM -> bias/ReLU/fp16 split in place
+// -> GEMM2 with A from TMEM -> heads), but two CTAs of a cluster cooperate on a 256-env tile:
+// every tcgen05.mma is M=256 (rows 0..127 live in CTA 0's TMEM, 128..255 in CTA 1's) and the B operand
+// (weights) is split along N between the two CTAs' shared memory -- each SM therefore ingests only
+// HALF of the operand stream per env (the single-CTA kernel is bound by the ~25 B/clk/SM L2->SM
+// ingest rate, measured with the pipeline wait counters).
+//
+//   CTA 0 (leader): warp 1 issues all MMAs; its mbarriers collect the arrivals of both CTAs
+//   CTA 1 (peer)  : warp 1 relays "my half of ring slot s has landed" to the leader; epilogue warps
+//                   arrive remotely (mapa + mbarrier.arrive.release.cluster) on the leader's barriers
+//   both          : warp 0 streams this CTA's half tiles with cp.async.bulk into its own ring;
+//                   warps 2..5 are the epilogue of this CTA's 128 envs; tcgen05.commit.cta_group::2
+//                   (multicast) publishes accumulators / frees ring slots in both CTAs.
+#include "twr_kernels.cuh"
+#include "twr_tc_ptx.cuh"
+
+#include <atomic>
+#include <cstdlib>
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <map>
+#include <mutex>
+
+extern std::atomic<long long> g_twr_launches;
+
+namespace {
+
+constexpr int TM = 128;               // envs per CTA (the pair covers 256)
+constexpr int NTHREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int NEPI = 256;
+constexpr int TILE_BYTES = 16384;
+constexpr int HALF_BYTES = 8192;
+constexpr int NSLOTS = 8;
+constexpr int MAX_KB1 = 4;
+constexpr int MAX_OBS = 32;
+
+constexpr int SM_A1 = 0;
+constexpr int SM_RING = SM_A1 + MAX_KB1 * TILE_BYTES;
+constexpr int SM_MISC = SM_RING + NSLOTS * TILE_BYTES;
+constexpr int SM_HEADW = SM_MISC;
+constexpr int SM_B1 = SM_HEADW + 8192;
+constexpr int SM_EMBB = SM_B1 + 1024;
+constexpr int SM_ROWS = SM_EMBB + 4096;
+constexpr int SM_PART = SM_ROWS + TM * MAX_OBS;           // [2][128][8] float: head partial sums of the upper column half
+constexpr int SM_BARS = SM_PART + 2 * TM * 8 * 4;
+constexpr int SM_TOTAL = SM_BARS + 512;
+static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
+
+enum Bar { B_FULL0 = 0, B_EMPTY0 = NSLOTS, B_A1_FULL = 2 * NSLOTS, B_A1_EMPTY, B_D1_FULL0, B_D1_FULL1,
+           B_A2_FULL0, B_A2_FULL1, B_D2_FULL, B_D2_EMPTY, B_COUNT };
+static_assert(B_COUNT * 8 + 8 <= 512, "barrier area");
+
+// ---- cluster / cta_group::2 PTX ----
+// TMA tile load (tensor map over the packed operand image, one box = one 16 KB ring slot) whose completion
+// bytes are credited to the LEADER CTA's mbarrier (peer bit of the barrier address cleared), the
+// cta_group::2 form CUTLASS uses for 2-SM MMA (cute/arch/copy_sm100_tma.hpp, SM100_TMA_2SM_LOAD_2D).
+__device__ __forceinline__ void tma_load_2sm(uint32_t dst, const CUtensorMap* tmap, int32_t c0, int32_t c1, uint32_t mbar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && spins > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_cluster_t(uint32_t bar, uint32_t parity, long long& acc, bool timed) {
+    if (!timed) { mbar_wait_cluster(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait_cluster(bar, parity);
+    acc += clock64() - t0;
+}
+// peer -> leader progress word (monotonic count of ring-slot uses whose peer half has landed)
+__device__ __forceinline__ void st_release_cluster(uint32_t cluster_addr, uint32_t v) {
+    asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cluster(uint32_t cta_addr) {
+    uint32_t v;
+    asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(cta_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc2_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+constexpr uint32_t IDESC_256x128 = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+constexpr uint32_t IDESC_256x256 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+
+struct Tc2Params { int NC, NKB1, E, H; };
+__host__ __device__ inline size_t slots_g1(const Tc2Params& t) { return (size_t)t.NC * t.NKB1; }
+__host__ __device__ inline size_t slots_g2(const Tc2Params& t) { return (size_t)t.NC * 4; }
+__host__ __device__ inline size_t slots_per_rank(const Tc2Params& t) { return slots_g1(t) + slots_g2(t); }
+
+// Operand image per CTA rank r (rank 0 image, then rank 1 image), in streaming order, 16 KB per ring slot:
+//   G1 slot (c,kb)      : [hi half-tile 8 KB][lo half-tile 8 KB], rows n = feature c*128 + r*64 + (0..63), k = obs row
+//   G2 slot (j,kb,part) : [128 rows x 64 k], rows n = output r*128 + (0..127), k = feature j*128 + kb*64 + kk
+__global__ void __launch_bounds__(256) k_tc2_pack(PolicyDev p, Tc2Params t, __half* __restrict__ pack) {
+    const size_t spr = slots_per_rank(t), n1 = slots_g1(t);
+    const size_t total = 2 * spr * (TILE_BYTES / 2);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t gslot = idx / (TILE_BYTES / 2);
+        const uint32_t within = (uint32_t)(idx % (TILE_BYTES / 2));
+        const int r = (int)(gslot / spr);
+        const size_t slot = gslot % spr;
+        float x = 0.0f;
+        int lo_part;
+        uint32_t off;
+        if (slot < n1) {
+            const int c = (int)(slot / t.NKB1), kb = (int)(slot % t.NKB1);
+            lo_part = within >= (HALF_BYTES / 2);
+            const uint32_t w2 = within % (HALF_BYTES / 2);
+            const uint32_t row = w2 >> 6, kk = w2 & 63u;
+            const int f = c * 128 + r * 64 + (int)row, k = kb * 64 + (int)kk;
+            if (k < p.obs_size) x = p.emb[(size_t)k * p.E + f];
+            off = (lo_part ? HALF_BYTES : 0) + tile_off(row, kk);
+        } else {
+            const size_t q = slot - n1;
+            const int j = (int)(q / 4), kb = (int)((q % 4) / 2);
+            lo_part = (int)(q % 2);
+            const uint32_t row = within >> 6, kk = within & 63u;
+            const int o = r * 128 + (int)row, f = j * 128 + kb * 64 + (int)kk;
+            x = p.w1[(size_t)f * p.H + o];
+            off = tile_off(row, kk);
+        }
+        const __half hi = __float2half_rn(x);
+        const __half v = lo_part ? __float2half_rn(x - __half2float(hi)) : hi;
+        *reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(pack) + gslot * TILE_BYTES + off) = v;
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n = a.n_live_ptr ? (int64_t)*a.n_live_ptr : a.n;
+    const int n_tiles = (int)((n + TM - 1) / TM);
+    const int crank = (int)ctarank();
+    const int pair_id = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
+    const int n_groups = (n_tiles + 1) / 2;
+    if (pair_id >= n_groups) return;                           // pair-uniform
+    const int my_tiles = (n_groups - pair_id + n_pairs - 1) / n_pairs;
+    auto tile_of = [&](int it) -> int64_t { return ((int64_t)pair_id + (int64_t)it * n_pairs) * 2 + crank; };
+
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bars = sbase + SM_BARS;
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+    auto lbar = [&](int i) { return mapa(bars + 8u * (uint32_t)i, 0); };     // same barrier in the leader CTA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BARS + 8 * B_COUNT);
+    float* headw = reinterpret_cast<float*>(smem + SM_HEADW);
+    float* b1s = reinterpret_cast<float*>(smem + SM_B1);
+    float* embb = reinterpret_cast<float*>(smem + SM_EMBB);
+    float* part_s = reinterpret_cast<float*>(smem + SM_PART);
+    uint8_t* rows_s = smem + SM_ROWS;
+    const int NC = t.NC, NKB1 = t.NKB1, H = t.H;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSLOTS; ++i) { mbar_init(bar(B_FULL0 + i), 1); mbar_init(bar(B_EMPTY0 + i), 1); }
+        mbar_init(bar(B_A1_FULL), 2 * TM); mbar_init(bar(B_A1_EMPTY), 1);
+        mbar_init(bar(B_D1_FULL0), 1); mbar_init(bar(B_D1_FULL1), 1);
+        mbar_init(bar(B_A2_FULL0), 2 * NEPI); mbar_init(bar(B_A2_FULL1), 2 * NEPI);
+        mbar_init(bar(B_D2_FULL), 1); mbar_init(bar(B_D2_EMPTY), 2 * NEPI);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < MAX_KB1 * TILE_BYTES / 16; i += NTHREADS)
+        reinterpret_cast<uint4*>(smem + SM_A1)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < H; i += NTHREADS) {
+        float* w = headw + i * 8;
+        for (int o = 0; o < 4; ++o) w[o] = o < p.A ? p.wa[(size_t)i * p.A + o] : 0.0f;
+        w[4] = p.wv[i]; w[5] = 0.f; w[6] = 0.f; w[7] = 0.f;
+        b1s[i] = p.b1[i];
+    }
+    for (int i = threadIdx.x; i < t.E; i += NTHREADS) embb[i] = p.emb_b[i];
+    for (int i = threadIdx.x; i < TM * MAX_OBS; i += NTHREADS) rows_s[i] = 0xFF;
+    if (warp == 1) {   // both CTAs, same warp id: allocates the same 512 columns in both SMs
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t D2_COL = 0, D1_COL = 256;
+    const bool timed = a.dbg != nullptr;
+
+    if (warp == 0) {
+        // =============================== TMA producer (both CTAs) ===================
+        // Each CTA fetches ITS half of every operand tile into its own ring; both halves credit the
+        // leader's `full` barrier, so the MMA issuer waits on one local barrier per ring slot.
+        if (lane == 0) {
+            const int img_row0 = crank * (int)slots_per_rank(t) * (TILE_BYTES / 128);   // tensor-map row of this rank's image
+            const int g1_row0 = img_row0, g2_row0 = img_row0 + (int)slots_g1(t) * (TILE_BYTES / 128);
+            uint32_t use = 0;
+            long long w_empty = 0;
+            auto push = [&](int row) {
+                const uint32_t slot = use % NSLOTS, round = use / NSLOTS;
+                mbar_wait_t(bar(B_EMPTY0 + slot), (round & 1u) ^ 1u, w_empty, timed);
+                if (crank == 0) mbar_expect_tx(bar(B_FULL0 + slot), 2 * TILE_BYTES);
+                tma_load_2sm(sbase + SM_RING + slot * TILE_BYTES, &tmap, 0, row, bar(B_FULL0 + slot));
+                ++use;
+            };
+            auto push_g1 = [&](int c) { for (int i = 0; i < NKB1; ++i) push(g1_row0 + (c * NKB1 + i) * (TILE_BYTES / 128)); };
+            auto push_g2 = [&](int j) { for (int i = 0; i < 4; ++i) push(g2_row0 + (j * 4 + i) * (TILE_BYTES / 128)); };
+            for (int it = 0; it < my_tiles; ++it) {
+                push_g1(0);
+                for (int c = 1; c < NC; ++c) { push_g1(c); push_g2(c - 1); }
+                push_g2(NC - 1);
+            }
+            if (a.dbg) a.dbg[blockIdx.x * 16 + 8] = w_empty;
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) {
+            // =========================== MMA issuer (leader CTA) ======================
+            uint32_t use = 0, d1use = 0, a2use = 0;
+            long long w_slot = 0, w_a1 = 0, w_a2 = 0, w_d2 = 0;
+            const long long t_begin = clock64();
+            auto wait_slot = [&]() -> uint32_t {
+                const uint32_t slot = use % NSLOTS, round = use / NSLOTS;
+                mbar_wait_cluster_t(bar(B_FULL0 + slot), round & 1u, w_slot, timed);
+                tc_fence_after();
+                ++use;
+                return slot;
+            };
+            for (int it = 0; it < my_tiles; ++it) {
+                mbar_wait_cluster_t(bar(B_A1_FULL), it & 1, w_a1, timed);
+                tc_fence_after();
+                auto g1 = [&](int c) {
+                    const uint32_t buf = d1use & 1u;
+                    const uint32_t d = tmem + D1_COL + buf * 128u;
+                    for (int kb = 0; kb < NKB1; ++kb) {
+                        const uint32_t slot = wait_slot();
+                        const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
+                        const uint64_t bh = make_desc(sbase + SM_RING + slot * TILE_BYTES);
+                        const uint64_t bl = make_desc(sbase + SM_RING + slot * TILE_BYTES + HALF_BYTES);
+                        if (!(a.dbg_flags & 8)) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                tc2_mma(d, ad + 2u * ks, bh + 2u * ks, IDESC_256x128, (kb | ks) != 0);
+                                tc2_mma(d, ad + 2u * ks, bl + 2u * ks, IDESC_256x128, 1u);
+                            }
+                        }
+                        tc2_commit(bar(B_EMPTY0 + slot));
+                    }
+                    tc2_commit(bar(B_D1_FULL0 + buf));
+                    if (c == NC - 1) tc2_commit(bar(B_A1_EMPTY));
+                    ++d1use;
+                };
+                auto g2 = [&](int j) {
+                    const uint32_t buf = a2use & 1u;
+                    mbar_wait_cluster_t(bar(B_A2_FULL0 + buf), (a2use >> 1) & 1u, w_a2, timed);
+                    tc_fence_after();
+                    if (j == 0) { mbar_wait_cluster_t(bar(B_D2_EMPTY), (it & 1) ^ 1, w_d2, timed); tc_fence_after(); }
+                    const uint32_t a_base = tmem + D1_COL + buf * 128u;
+                    const uint32_t d = tmem + D2_COL;
+                    for (int kb = 0; kb < 2; ++kb) {
+                        for (int part = 0; part < 2; ++part) {
+                            const uint32_t slot = wait_slot();
+                            const uint64_t bd = make_desc(sbase + SM_RING + slot * TILE_BYTES);
+                            const bool first = (j == 0 && kb == 0 && part == 0);
+                            if (!(a.dbg_flags & 4)) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint32_t sidx = kb * 4 + ks;
+                                    const uint32_t ah = a_base + 32u * (sidx >> 1) + 8u * (sidx & 1u);
+                                    tc2_mma_ts(d, ah, bd + 2u * ks, IDESC_256x256, !(first && ks == 0));
+                                    if (part == 0) tc2_mma_ts(d, ah + 16u, bd + 2u * ks, IDESC_256x256, 1u);
+                                }
+                            }
+                            tc2_commit(bar(B_EMPTY0 + slot));
+                        }
+                    }
+                    ++a2use;
+                    if (j == NC - 1) tc2_commit(bar(B_D2_FULL));
+                };
+                g1(0);
+                for (int c = 1; c < NC; ++c) { g1(c); g2(c - 1); }
+                g2(NC - 1);
+            }
+            if (a.dbg) {
+                long long* d = a.dbg + blockIdx.x * 16;
+                d[0] = clock64() - t_begin; d[1] = w_slot; d[2] = w_a1; d[3] = w_a2; d[4] = w_d2; d[5] = my_tiles;
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue warps (both CTAs) =================
+        // Two warps per TMEM lane quarter: `chalf` picks which half of the columns a thread handles.
+        const int quarter = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_addr = ((uint32_t)(quarter * 32)) << 16;
+        const int n_obs = p.n_obs;
+        uint32_t d1use = 0;
+        int perm_cur = -1, perm_next = -1;
+        long long w_d1 = 0, w_d2f = 0, w_a1e = 0;
+        const long long t_begin = clock64();
+        const uint32_t l_a1_full = lbar(B_A1_FULL), l_d2_empty = lbar(B_D2_EMPTY);
+        const uint32_t l_a2_full0 = lbar(B_A2_FULL0), l_a2_full1 = lbar(B_A2_FULL1);
+
+        auto build_a1 = [&](int it) -> int {
+            mbar_wait_t(bar(B_A1_EMPTY), (it & 1) ^ 1, w_a1e, timed);
+            const int64_t pos = tile_of(it) * TM + row;
+            int perm = -1;
+            EnvState s; s.lo = 0; s.hi = 0; s.blank = 0; s.depth = 0;
+            int64_t e = 0;
+            if (pos < n) {
+                e = a.live ? a.live[pos] : pos;
+                if (!a.obs_rows) {
+                    const uint4 c = a.cells[e];
+                    s.lo = (uint64_t)c.x | ((uint64_t)c.y << 32);
+                    s.hi = (uint64_t)c.z | ((uint64_t)c.w << 32);
+                }
+                if (a.perm_idx) {
+                    perm = a.perm_idx[pos];
+                } else if (p.n_perms > 0 && a.t >= 0) {
+                    uint32_t w[4];
+                    philox4x32_10(a.env_id_base + (uint32_t)e, (uint32_t)a.t, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
+                                  (uint32_t)(a.seed >> 32), w);
+                    perm = (int)mulhi_u32(w[0], (uint32_t)p.n_perms);
+                }
+            }
+            for (int i = 0; i < n_obs; ++i) {
+                const uint32_t old = rows_s[row * MAX_OBS + i];
+                if (old != 0xFF || it > 0)
+                    *reinterpret_cast<__half*>(smem + SM_A1 + (old >> 6) * TILE_BYTES + tile_off(row, old & 63u)) = __ushort_as_half(0);
+            }
+            for (int i = 0; i < n_obs; ++i) {
+                int r = 0;
+                if (pos < n) {
+                    r = a.obs_rows ? a.obs_rows[pos * n_obs + i] : i * a.env.N + (int)env_board(a.env, s, i);
+                    if (perm >= 0) r = p.obs_perms[(size_t)perm * p.obs_size + r];
+                }
+                rows_s[row * MAX_OBS + i] = (uint8_t)r;
+                *reinterpret_cast<__half*>(smem + SM_A1 + (r >> 6) * TILE_BYTES + tile_off(row, (uint32_t)r & 63u)) = __ushort_as_half(0x3C00);
+            }
+            fence_async_smem();
+            mbar_arrive_cluster(l_a1_full);
+            return perm;
+        };
+        // relu(x + bias) -> packed fp16 hi pair / lo pair (x = hi + lo to ~22 bits)
+        auto split2 = [](float x0, float x1, uint32_t& hi, uint32_t& lo) {
+            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f);
+            const __half2 h = __floats2half2_rn(x0, x1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+            hi = *reinterpret_cast<const uint32_t*>(&h);
+            lo = *reinterpret_cast<const uint32_t*>(&l);
+        };
+
+        if (chalf == 0) perm_next = build_a1(0);
+        for (int it = 0; it < my_tiles; ++it) {
+            perm_cur = perm_next;
+            // ---- epilogue 1: this thread's 64 columns of the D1 chunk, rewritten in place as the fp16 A operand
+            for (int c = 0; c < NC; ++c) {
+                const uint32_t buf = d1use & 1u;
+                mbar_wait_t(bar(B_D1_FULL0 + buf), (d1use >> 1) & 1u, w_d1, timed);
+                tc_fence_after();
+                if (!(a.dbg_flags & 1)) {
+                    uint32_t v0[32], v1[32];
+                    const uint32_t taddr = tmem + lane_addr + D1_COL + buf * 128u + (uint32_t)chalf * 64u;
+                    tc_ld32(taddr, v0);
+                    tc_ld32(taddr + 32u, v1);
+                    tc_wait_ld();
+                    const float* bias = embb + c * 128 + chalf * 64;
+                    uint32_t w[32];
+#pragma unroll
+                    for (int e2 = 0; e2 < 16; ++e2)
+                        split2(__uint_as_float(v0[2 * e2]) + bias[2 * e2], __uint_as_float(v0[2 * e2 + 1]) + bias[2 * e2 + 1], w[e2], w[16 + e2]);
+                    tc_st32(taddr, w);
+#pragma unroll
+                    for (int e2 = 0; e2 < 16; ++e2)
+                        split2(__uint_as_float(v1[2 * e2]) + bias[32 + 2 * e2], __uint_as_float(v1[2 * e2 + 1]) + bias[32 + 2 * e2 + 1], w[e2], w[16 + e2]);
+                    tc_st32(taddr + 32u, w);
+                    tc_wait_st();
+                }
+                tc_fence_before();
+                mbar_arrive_cluster(buf ? l_a2_full1 : l_a2_full0);
+                ++d1use;
+            }
+            // ---- next tile's one-hot operand, so its GEMM1 overlaps this tile's heads
+            if (chalf == 0 && it + 1 < my_tiles) perm_next = build_a1(it + 1);
+
+            // ---- epilogue 2: heads on CUDA cores; each thread reduces its 128 columns of the accumulator row
+            mbar_wait_t(bar(B_D2_FULL), it & 1, w_d2f, timed);
+            tc_fence_after();
+            float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {
+                uint32_t v0[32], v1[32];
+                const uint32_t col0 = (uint32_t)chalf * 128u + (uint32_t)q * 64u;
+                tc_ld32(tmem + lane_addr + D2_COL + col0, v0);
+                tc_ld32(tmem + lane_addr + D2_COL + col0 + 32u, v1);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    const int col = (int)col0 + j;
+                    float h = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]) + b1s[col];
+                    h = fmaxf(h, 0.f);
+                    const float4 w0 = *reinterpret_cast<const float4*>(headw + col * 8);
+                    const float w4 = headw[col * 8 + 4];
+                    acc[0] = fmaf(h, w0.x, acc[0]); acc[1] = fmaf(h, w0.y, acc[1]);
+                    acc[2] = fmaf(h, w0.z, acc[2]); acc[3] = fmaf(h, w0.w, acc[3]);
+                    acc[4] = fmaf(h, w4, acc[4]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(l_d2_empty);
+            float* ps = part_s + ((it & 1) * TM + row) * 8;
+            if (chalf == 1) {
+                *reinterpret_cast<float4*>(ps) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                ps[4] = acc[4];
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");     // the 8 epilogue warps only
+            const int64_t pos = tile_of(it) * TM + row;
+            if (chalf == 0 && pos < n) {
+                const float4 o4 = *reinterpret_cast<const float4*>(ps);
+                acc[0] += o4.x; acc[1] += o4.y; acc[2] += o4.z; acc[3] += o4.w; acc[4] += ps[4];
+                float l[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) l[o] = o < p.A ? acc[o] + p.ba[o] : 0.0f;
+                float out[4] = {l[0], l[1], l[2], l[3]};
+                if (perm_cur >= 0) {
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        if (o < p.A) {
+                            const int src = p.act_perms[perm_cur * p.A + o];
+                            out[o] = src == 0 ? l[0] : src == 1 ? l[1] : src == 2 ? l[2] : l[3];
+                        }
+                    }
+                }
+                a.logits[pos] = make_float4(out[0], out[1], out[2], out[3]);
+                a.values[pos] = acc[4] + p.bv[0];
+            }
+        }
+        if (a.dbg && threadIdx.x == 64) {
+            long long* d = a.dbg + blockIdx.x * 16;
+            d[9] = clock64() - t_begin; d[10] = w_d1; d[11] = w_d2f; d[12] = w_a1e;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+    }
+}
+
+Tc2Params make_params2(const PolicyDev& p) {
+    Tc2Params t;
+    t.E = p.E; t.H = p.H; t.NC = p.E / 128; t.NKB1 = (p.obs_size + 63) / 64;
+    return t;
+}
+
+int g_sms = 0;
+std::mutex g_tmap_mu;
+std::map<const void*, CUtensorMap> g_tmaps;
+
+// Tensor map over the packed operand image viewed as [rows][128 bytes]; one 128 x 128 box = one ring slot.
+bool get_tmap(const void* pack, size_t bytes, CUtensorMap* out) {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmaps.find(pack);
+    if (it != g_tmaps.end()) { *out = it->second; return true; }
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+    const cuuint64_t gdim[2] = {128, (cuuint64_t)(bytes / 128)};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {128, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap m;
+    const CUresult r = reinterpret_cast<encode_fn>(fn)(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(pack), gdim, gstride, box,
+                                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    g_tmaps[pack] = m;
+    *out = m;
+    return true;
+}
+
+}  // namespace
+
+int forward_tc2_supported(const PolicyDev& p) { return p.H == 256; }
+
+size_t forward_tc2_pack_bytes(const PolicyDev& p) {
+    if (!forward_tc2_supported(p)) return 0;
+    return 2 * slots_per_rank(make_params2(p)) * TILE_BYTES;
+}
+
+void launch_forward_tc2_pack(cudaStream_t st, const PolicyDev& p, void* pack) {
+    k_tc2_pack<<<1024, 256, 0, st>>>(p, make_params2(p), reinterpret_cast<__half*>(pack));
+    g_twr_launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+bool launch_forward_tc2(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a, const void* pack) {
+    if (a.n <= 0) return true;
+    CUtensorMap tmap;
+    if (!get_tmap(pack, forward_tc2_pack_bytes(p), &tmap)) return false;
+    if (g_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int n_tiles = (int)((a.n + TM - 1) / TM);
+    const int n_groups = (n_tiles + 1) / 2, max_pairs = g_sms / 2;
+    const int grid = (n_groups < max_pairs ? n_groups : max_pairs) * 2;
+    cudaFuncSetAttribute(k_forward_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    k_forward_tc2<<<grid, NTHREADS, SM_TOTAL, st>>>(p, a, make_params2(p), tmap);
+    g_twr_launches.fetch_add(1, std::memory_order_relaxed);
+    return true;
+}

@@ -83,6 +83,8 @@ struct ForwardArgs {
     const uint4* cells; const int32_t* live; const int32_t* n_live_ptr; int64_t n;
     const int32_t* obs_rows;  // optional [n][n_obs] sparse obs given directly (Policy.forward API); overrides cells
     float4* logits; float* values;
+    int dbg_flags;    // debug experiments (k_forward_tc2): 1 skip epilogue-1 TMEM traffic, 2 skip TMA copies, 4 skip GEMM2 MMAs, 8 skip GEMM1 MMAs
+    long long* dbg;   // optional [gridDim][16] cycle counters written by k_forward_tc (debug/profiling)
 };
 int  forward_fp32_supported(const PolicyDev& p, const EnvParams& env, const char** why);
 void launch_forward_fp32(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a);
@@ -91,3 +93,8 @@ int  forward_tc_supported(const PolicyDev& p, const EnvParams& env, const char**
 size_t forward_tc_pack_bytes(const PolicyDev& p);
 void launch_forward_tc_pack(cudaStream_t s, const PolicyDev& p, void* pack);
 void launch_forward_tc(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a);
+// CTA-pair (cta_group::2) variant, twr_forward_tc2.cu; `pack` is its own operand image
+int    forward_tc2_supported(const PolicyDev& p);
+size_t forward_tc2_pack_bytes(const PolicyDev& p);
+void   launch_forward_tc2_pack(cudaStream_t s, const PolicyDev& p, void* pack);
+bool   launch_forward_tc2(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a, const void* pack);  // false: tensor map unavailable

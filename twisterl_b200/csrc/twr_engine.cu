@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -712,15 +713,41 @@ int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p
     ForwardArgs fa{};
     fa.env = env; fa.seed = e->seed; fa.cid = cid; fa.env_id_base = env_id_base; fa.perm_idx = nullptr;
     fa.cells = b.cells; fa.n = num_episodes; fa.logits = b.logits; fa.values = b.values;
-    for (int t = 0; t < T; ++t) {
-        int32_t* cur = (t & 1) ? b.live_b : b.live_a;
-        int32_t* nxt = (t & 1) ? b.live_a : b.live_b;
-        fa.t = t; fa.live = cur; fa.n_live_ptr = b.n_live + t;
-        if (e->timing) cudaEventRecord(e->ev[2 * t], st);
-        launch_forward(e, dev, fa);
-        if (e->timing) cudaEventRecord(e->ev[2 * t + 1], st);
-        sa.t = t;
-        launch_collect_step(st, sa, b, cur, nxt);
+    const bool fused = e->precision == TWR_PREC_F16X2 && forward_tc_can_fuse(dev);
+    int n_fwd = 0;
+    if (fused) {
+        // Persistent chunks: one launch covers `chunk` consecutive steps of every tile (envs stay with their
+        // CTA pair, finished envs idle), then the live list is re-compacted.  Short episodes use chunk 1.
+        int chunk = T / 8 < 1 ? 1 : (T / 8 > 32 ? 32 : T / 8);
+        if (const char* c = getenv("TWISTERL_B200_CHUNK")) { const int v = atoi(c); if (v >= 1) chunk = v; }
+        CU_TRY(cudaMemsetAsync(b.ep_len, 0, sizeof(int32_t) * (size_t)num_episodes, st));
+        int32_t* cur = b.live_a;
+        int32_t* nxt = b.live_b;
+        for (int t0 = 0, ci = 0; t0 < T; t0 += chunk, ++ci) {
+            const int cnt = T - t0 < chunk ? T - t0 : chunk;
+            fa.t = t0; fa.t_count = cnt; fa.live = cur; fa.n_live_ptr = b.n_live + ci;
+            sa.t = t0;
+            fa.fused = 1; fa.step = sa; fa.cb = b; fa.live_next = cnt == 1 ? nxt : nullptr;
+            if (cnt == 1) { fa.cb.n_live = b.n_live + ci - t0; }   // collect_step_body appends at n_live[t+1]
+            if (e->timing) cudaEventRecord(e->ev[2 * n_fwd], st);
+            launch_forward(e, dev, fa);
+            if (e->timing) cudaEventRecord(e->ev[2 * n_fwd + 1], st);
+            ++n_fwd;
+            if (cnt > 1) launch_compact_live(st, cur, b.n_live + ci, b.ep_len, num_episodes, nxt, b.n_live + ci + 1);
+            int32_t* tmp = cur; cur = nxt; nxt = tmp;
+        }
+    } else {
+        for (int t = 0; t < T; ++t) {
+            int32_t* cur = (t & 1) ? b.live_b : b.live_a;
+            int32_t* nxt = (t & 1) ? b.live_a : b.live_b;
+            fa.t = t; fa.live = cur; fa.n_live_ptr = b.n_live + t;
+            sa.t = t;
+            if (e->timing) cudaEventRecord(e->ev[2 * t], st);
+            launch_forward(e, dev, fa);
+            if (e->timing) cudaEventRecord(e->ev[2 * t + 1], st);
+            launch_collect_step(st, sa, b, cur, nxt);
+        }
+        n_fwd = T;
     }
     launch_gae_time_major(st, b, gamma, lambda);
     launch_episode_offsets(st, b);
@@ -733,8 +760,8 @@ int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p
     CU_TRY(cudaStreamSynchronize(st));
     if (e->timing) {
         float tot = 0.f, ms = 0.f;
-        for (int t = 0; t < T; ++t) { cudaEventElapsedTime(&ms, e->ev[2 * t], e->ev[2 * t + 1]); tot += ms; }
-        e->last_fwd_ms = tot; e->last_fwd_launches = T;
+        for (int t = 0; t < n_fwd; ++t) { cudaEventElapsedTime(&ms, e->ev[2 * t], e->ev[2 * t + 1]); tot += ms; }
+        e->last_fwd_ms = tot; e->last_fwd_launches = n_fwd;
         cudaEventElapsedTime(&e->last_total_ms, e->ev_t0, e->ev_t1);
     }
     twr_collected& c = e->last;

@@ -469,6 +469,20 @@ void launch_cfg(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a, const
 
 int g_cluster = -1, g_pair = -1;
 
+static void resolve_mode() {
+    if (g_pair < 0) {
+        const char* m = getenv("TWISTERL_B200_TC_MODE");      // "pair" (default) | "single"
+        g_pair = (m && m[0] == 's') ? 0 : 1;
+    }
+}
+
+int forward_tc_can_fuse(const PolicyDev& p) {
+    resolve_mode();
+    const char* f = getenv("TWISTERL_B200_FUSE_STEP");         // "0" keeps the separate k_collect_step launch
+    if (f && f[0] == '0') return 0;
+    return g_pair && forward_tc2_supported(p);
+}
+
 void launch_forward_tc(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a) {
     if (a.n <= 0) return;
     if (g_num_sms == 0) {
@@ -476,10 +490,7 @@ void launch_forward_tc(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    if (g_pair < 0) {
-        const char* m = getenv("TWISTERL_B200_TC_MODE");      // "pair" (default) | "single"
-        g_pair = (m && m[0] == 's') ? 0 : 1;
-    }
+    resolve_mode();
     if (g_pair && forward_tc2_supported(p)) {
         if (launch_forward_tc2(st, p, a, reinterpret_cast<const unsigned char*>(p.tc_pack) + single_pack_bytes(p))) return;
         g_pair = 0;   // tensor map could not be created: use the single-CTA kernel from now on

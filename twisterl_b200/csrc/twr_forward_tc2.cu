@@ -15,6 +15,7 @@
 //                   (multicast) publishes accumulators / frees ring slots in both CTAs.
 #include "twr_kernels.cuh"
 #include "twr_tc_ptx.cuh"
+#include "twr_step.cuh"
 
 #include <atomic>
 #include <cstdlib>
@@ -174,6 +175,11 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     const int n_groups = (n_tiles + 1) / 2;
     if (pair_id >= n_groups) return;                           // pair-uniform
     const int my_tiles = (n_groups - pair_id + n_pairs - 1) / n_pairs;
+    // Work items: (step, tile) pairs, all steps of this launch for all tiles owned by this pair, step-major.
+    // With t_count > 1 the kernel is persistent over time: a tile's envs stay with this pair for the whole
+    // chunk, finished envs idle, and the live list is re-compacted between launches.
+    const int t_count = a.t_count > 0 ? a.t_count : 1;
+    const int n_items = my_tiles * t_count;
     auto tile_of = [&](int it) -> int64_t { return ((int64_t)pair_id + (int64_t)it * n_pairs) * 2 + crank; };
 
     const uint32_t sbase = smem_u32(smem);
@@ -237,7 +243,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             };
             auto push_g1 = [&](int c) { for (int i = 0; i < NKB1; ++i) push(g1_row0 + (c * NKB1 + i) * (TILE_BYTES / 128)); };
             auto push_g2 = [&](int j) { for (int i = 0; i < 4; ++i) push(g2_row0 + (j * 4 + i) * (TILE_BYTES / 128)); };
-            for (int it = 0; it < my_tiles; ++it) {
+            for (int it = 0; it < n_items; ++it) {
                 push_g1(0);
                 for (int c = 1; c < NC; ++c) { push_g1(c); push_g2(c - 1); }
                 push_g2(NC - 1);
@@ -258,7 +264,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 ++use;
                 return slot;
             };
-            for (int it = 0; it < my_tiles; ++it) {
+            for (int it = 0; it < n_items; ++it) {
                 mbar_wait_cluster_t(bar(B_A1_FULL), it & 1, w_a1, timed);
                 tc_fence_after();
                 auto g1 = [&](int c) {
@@ -336,14 +342,15 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
 
         auto build_a1 = [&](int it) -> int {
             mbar_wait_t(bar(B_A1_EMPTY), (it & 1) ^ 1, w_a1e, timed);
-            const int64_t pos = tile_of(it) * TM + row;
+            const int64_t pos = tile_of(it % my_tiles) * TM + row;
+            const int t_cur = a.t + it / my_tiles;
             int perm = -1;
             EnvState s; s.lo = 0; s.hi = 0; s.blank = 0; s.depth = 0;
             int64_t e = 0;
             if (pos < n) {
                 e = a.live ? a.live[pos] : pos;
                 if (!a.obs_rows) {
-                    const uint4 c = a.cells[e];
+                    const uint4 c = __ldcg(a.cells + e);     // written by this thread's own fused step one item earlier
                     s.lo = (uint64_t)c.x | ((uint64_t)c.y << 32);
                     s.hi = (uint64_t)c.z | ((uint64_t)c.w << 32);
                 }
@@ -351,7 +358,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     perm = a.perm_idx[pos];
                 } else if (p.n_perms > 0 && a.t >= 0) {
                     uint32_t w[4];
-                    philox4x32_10(a.env_id_base + (uint32_t)e, (uint32_t)a.t, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
+                    philox4x32_10(a.env_id_base + (uint32_t)e, (uint32_t)t_cur, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
                                   (uint32_t)(a.seed >> 32), w);
                     perm = (int)mulhi_u32(w[0], (uint32_t)p.n_perms);
                 }
@@ -384,8 +391,12 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             lo = *reinterpret_cast<const uint32_t*>(&l);
         };
 
+        // the next item's one-hot operand is normally built BEFORE this item's heads (so its GEMM1 overlaps
+        // them); with a single tile per pair the next item is the same envs one step later, whose state
+        // only exists after this item's fused env step
+        const bool build_early = my_tiles > 1 || t_count == 1;
         if (chalf == 0) perm_next = build_a1(0);
-        for (int it = 0; it < my_tiles; ++it) {
+        for (int it = 0; it < n_items; ++it) {
             perm_cur = perm_next;
             // ---- epilogue 1: this thread's 64 columns of the D1 chunk, rewritten in place as the fp16 A operand
             for (int c = 0; c < NC; ++c) {
@@ -415,7 +426,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 ++d1use;
             }
             // ---- next tile's one-hot operand, so its GEMM1 overlaps this tile's heads
-            if (chalf == 0 && it + 1 < my_tiles) perm_next = build_a1(it + 1);
+            if (build_early && chalf == 0 && it + 1 < n_items) perm_next = build_a1(it + 1);
 
             // ---- epilogue 2: heads on CUDA cores; each thread reduces its 128 columns of the accumulator row
             mbar_wait_t(bar(B_D2_FULL), it & 1, w_d2f, timed);
@@ -448,25 +459,43 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 ps[4] = acc[4];
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");     // the 8 epilogue warps only
-            const int64_t pos = tile_of(it) * TM + row;
-            if (chalf == 0 && pos < n) {
-                const float4 o4 = *reinterpret_cast<const float4*>(ps);
-                acc[0] += o4.x; acc[1] += o4.y; acc[2] += o4.z; acc[3] += o4.w; acc[4] += ps[4];
-                float l[4];
+            const int64_t pos = tile_of(it % my_tiles) * TM + row;
+            if (chalf == 0) {                                          // warp-uniform: whole warps take this branch
+                const bool active = pos < n;
+                float out[4] = {0.f, 0.f, 0.f, 0.f};
+                float value = 0.f;
+                if (active) {
+                    const float4 o4 = *reinterpret_cast<const float4*>(ps);
+                    acc[0] += o4.x; acc[1] += o4.y; acc[2] += o4.z; acc[3] += o4.w; acc[4] += ps[4];
+                    float l[4];
 #pragma unroll
-                for (int o = 0; o < 4; ++o) l[o] = o < p.A ? acc[o] + p.ba[o] : 0.0f;
-                float out[4] = {l[0], l[1], l[2], l[3]};
-                if (perm_cur >= 0) {
+                    for (int o = 0; o < 4; ++o) l[o] = o < p.A ? acc[o] + p.ba[o] : 0.0f;
 #pragma unroll
-                    for (int o = 0; o < 4; ++o) {
-                        if (o < p.A) {
-                            const int src = p.act_perms[perm_cur * p.A + o];
-                            out[o] = src == 0 ? l[0] : src == 1 ? l[1] : src == 2 ? l[2] : l[3];
+                    for (int o = 0; o < 4; ++o) out[o] = l[o];
+                    if (perm_cur >= 0) {                               // twist-out, nn/policy.rs:95-97
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            if (o < p.A) {
+                                const int src = p.act_perms[perm_cur * p.A + o];
+                                out[o] = src == 0 ? l[0] : src == 1 ? l[1] : src == 2 ? l[2] : l[3];
+                            }
                         }
                     }
+                    value = acc[4] + p.bv[0];
                 }
-                a.logits[pos] = make_float4(out[0], out[1], out[2], out[3]);
-                a.values[pos] = acc[4] + p.bv[0];
+                if (a.fused) {
+                    const int e = active ? (a.live ? a.live[pos] : (int)pos) : 0;
+                    StepArgs sa = a.step;
+                    sa.t = a.t + it / my_tiles;
+                    // inside a multi-step chunk an env that already recorded its terminal state idles
+                    const bool alive = active && (t_count == 1 || a.cb.ep_len[e] == 0);
+                    collect_step_body(sa, a.cb, alive, e, make_float4(out[0], out[1], out[2], out[3]), value, perm_cur,
+                                      a.live_next);
+                } else if (active) {
+                    a.logits[pos] = make_float4(out[0], out[1], out[2], out[3]);
+                    a.values[pos] = value;
+                }
+                if (!build_early && it + 1 < n_items) perm_next = build_a1(it + 1);
             }
         }
         if (a.dbg && threadIdx.x == 64) {

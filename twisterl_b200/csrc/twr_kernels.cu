@@ -7,6 +7,7 @@
 // All are one-thread-per-env, 16-byte vector state loads, time-major [t][env] record stores
 // (coalesced), grids sized from the env count.  Algorithmic bytes per record are listed in DESIGN.md.
 #include "twr_kernels.cuh"
+#include "twr_step.cuh"
 
 #include <atomic>
 
@@ -177,60 +178,44 @@ __global__ void __launch_bounds__(256) k_collect_step(StepArgs a, CollectBuffers
     const int nl = b.n_live[a.t];
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = pos < nl;
-    bool survives = false;
-    int e = 0;
+    int e = 0, perm = -1;
+    float4 raw = make_float4(0.f, 0.f, 0.f, 0.f);
+    float value = 0.f;
     if (active) {
         e = live_cur[pos];
-        EnvState s = env_load(b.cells, b.meta, e);
-        const uint32_t gid = a.env_id_base + (uint32_t)e;
-        const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-
-        int perm = -1;
+        raw = b.logits[pos];
+        value = b.values[pos];
         if (a.n_perms > 0) {                                  // get_perm_id, nn/policy.rs:67-77
             uint32_t w[4];
-            philox4x32_10(gid, (uint32_t)a.t, TWR_RNG_PERM, a.cid, k0, k1, w);
+            philox4x32_10(a.env_id_base + (uint32_t)e, (uint32_t)a.t, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
+                          (uint32_t)(a.seed >> 32), w);
             perm = (int)mulhi_u32(w[0], (uint32_t)a.n_perms);
         }
-        const uint32_t m = env_masks(a.env, s);
-        const float4 raw = b.logits[pos];
-        float l[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) l[i] = (i < a.A) ? (((m >> i) & 1u) ? l[i] : -1e10f) : 0.0f;  // policy.rs:62
-
-        uint32_t w[4];
-        philox4x32_10(gid, (uint32_t)a.t, TWR_RNG_SAMPLE, a.cid, k0, k1, w);
-        const float u[4] = {u32_to_unit_f32(w[0]), u32_to_unit_f32(w[1]), u32_to_unit_f32(w[2]), u32_to_unit_f32(w[3])};
-        const int act = sample_from_logits4(l, u, a.A);
-        const float rew = env_reward(a.env, s);
-        const bool fin = env_is_final(a.env, s);
-
-        const int64_t r = (int64_t)a.t * b.B + e;
-        b.rec_state[r] = env_pack_cells(s);
-        b.rec_logits[r] = make_float4(l[0], l[1], l[2], l[3]);
-        b.rec_value[r] = b.values[pos];
-        b.rec_reward[r] = rew;
-        b.rec_action[r] = (uint8_t)act;
-        b.rec_perm[r] = (int8_t)perm;
-
-        if (fin) {
-            b.ep_len[e] = a.t + 1;
-            if (env_success(a.env, s)) atomicAdd(&b.stats[0], 1ull);
-            atomicAdd(reinterpret_cast<double*>(&b.stats[2]), (double)rew);
-        } else {
-            env_step(a.env, s, act);
-            env_store(b.cells, b.meta, e, s);
-            survives = true;
-        }
     }
-    // warp-aggregated append to the next live list
+    collect_step_body(a, b, active, e, raw, value, perm, live_next);
+}
+
+__global__ void __launch_bounds__(256) k_compact_live(const int32_t* __restrict__ live_cur, const int32_t* __restrict__ n_cur,
+                                                      const int32_t* __restrict__ ep_len, int32_t* __restrict__ live_next,
+                                                      int32_t* __restrict__ n_next) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    int e = 0;
+    bool survives = false;
+    if (pos < *n_cur) { e = live_cur[pos]; survives = ep_len[e] == 0; }
     const unsigned bal = __ballot_sync(0xffffffffu, survives);
     if (bal) {
         const int lane = threadIdx.x & 31;
         int base = 0;
-        if (lane == 0) base = atomicAdd(&b.n_live[a.t + 1], __popc(bal));
+        if (lane == 0) base = atomicAdd(n_next, __popc(bal));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (survives) live_next[base + __popc(bal & ((1u << lane) - 1u))] = e;
     }
+}
+
+void launch_compact_live(cudaStream_t st, const int32_t* live_cur, const int32_t* n_cur, const int32_t* ep_len, int64_t max_n,
+                         int32_t* live_next, int32_t* n_next) {
+    k_compact_live<<<grid_for(max_n, 256), 256, 0, st>>>(live_cur, n_cur, ep_len, live_next, n_next);
+    TWR_COUNT_LAUNCH();
 }
 
 void launch_collect_step(cudaStream_t st, const StepArgs& a, const CollectBuffers& b, const int32_t* live_cur, int32_t* live_next) {

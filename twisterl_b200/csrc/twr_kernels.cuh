@@ -68,6 +68,9 @@ void launch_sample(cudaStream_t s, const float* d_logits, int64_t n, int A, uint
 void launch_collect_step(cudaStream_t s, const StepArgs& a, const CollectBuffers& b, const int32_t* live_cur,
                          int32_t* live_next);
 // K4b GAE reverse scan (time-major records) and standalone (concatenated episodes)
+// survivors (ep_len == 0) of live_cur[0..*n_cur) -> live_next, count -> *n_next (must be zeroed)
+void launch_compact_live(cudaStream_t s, const int32_t* live_cur, const int32_t* n_cur, const int32_t* ep_len, int64_t max_n,
+                         int32_t* live_next, int32_t* n_next);
 void launch_gae_time_major(cudaStream_t s, const CollectBuffers& b, float gamma, float lambda);
 void launch_gae_concat(cudaStream_t s, const float* r, const float* v, const int64_t* off, int64_t n_ep,
                        float gamma, float lambda, float* adv, float* ret);
@@ -83,6 +86,9 @@ struct ForwardArgs {
     const uint4* cells; const int32_t* live; const int32_t* n_live_ptr; int64_t n;
     const int32_t* obs_rows;  // optional [n][n_obs] sparse obs given directly (Policy.forward API); overrides cells
     float4* logits; float* values;
+    // fused collect step (k_forward_tc2 only): when `fused` != 0 the epilogue does k_collect_step's work
+    int fused; StepArgs step; CollectBuffers cb; int32_t* live_next;
+    int t_count;      // steps t .. t+t_count-1 in this launch (fused pair kernel only; 0/1 = one step)
     int dbg_flags;    // debug experiments (k_forward_tc2): 1 skip epilogue-1 TMEM traffic, 2 skip TMA copies, 4 skip GEMM2 MMAs, 8 skip GEMM1 MMAs
     long long* dbg;   // optional [gridDim][16] cycle counters written by k_forward_tc (debug/profiling)
 };
@@ -97,4 +103,5 @@ void launch_forward_tc(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a)
 int    forward_tc2_supported(const PolicyDev& p);
 size_t forward_tc2_pack_bytes(const PolicyDev& p);
 void   launch_forward_tc2_pack(cudaStream_t s, const PolicyDev& p, void* pack);
+int    forward_tc_can_fuse(const PolicyDev& p);   // 1 when launch_forward_tc will run the fusable pair kernel
 bool   launch_forward_tc2(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a, const void* pack);  // false: tensor map unavailable

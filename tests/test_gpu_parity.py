@@ -417,3 +417,38 @@ def test_collect_full_size_properties(eng):
     rep = check_collect_against_oracle(d, ospec, opol, seed=eng.seed, collect_id=5, gamma=0.995, lam=0.995, tol=TOL,
                                        max_episodes=24)
     assert rep["records"] > 24
+
+
+def test_collect_host_pipelined_matches_plain(eng, monkeypatch):
+    """twr_ppo_collect_host splits large collects into sub-batches whose D2H overlaps the next rollout; the
+    host buffers must hold exactly what the plain collect + to_host path produces."""
+    import ctypes as C
+    import twisterl_b200 as tw
+    from parity import make_policies
+    from twisterl_b200 import _lib, collector as twc
+    _, sd = trained15()
+    pol, _ = make_policies(sd, 256)
+    env = tw.env.Puzzle(4, 4, 12, 2, 256)
+    E = 1000
+    col = tw.collector.PPOCollector(E, 0.995, 0.995, 32, engine=eng)
+    eng.set_collect_id(21)
+    ref = col.collect(env, pol)
+    L = _lib.load()
+    spec = tw.env.spec_from_env(env)
+    cap = int(L.twr_max_records(C.byref(spec), E))
+    for split in ("3", "7"):
+        monkeypatch.setenv("TWISTERL_B200_E2E_SPLIT", split)
+        hb, arr, _ = twc._host_buffers(cap, 16, 4, E, pinned=True)
+        out = _lib.Collected()
+        eng.set_collect_id(21)
+        _lib.check(L.twr_ppo_collect_host(eng._h, C.byref(spec), pol.device_handle(eng), None, E, 0.995, 0.995,
+                                          C.byref(hb), C.byref(out)))
+        R = int(out.n_records)
+        assert R == len(ref.values_array) and int(out.successes) == ref.stats["successes"]
+        assert abs(out.reward_sum - ref.stats["reward_sum"]) < 1e-6
+        assert np.array_equal(arr["ep_len"], ref.ep_len)
+        assert np.array_equal(arr["obs"][:R], ref.obs_array) and np.array_equal(arr["actions"][:R], ref.actions_array)
+        assert np.array_equal(arr["logits"][:R], ref.logits_array) and np.array_equal(arr["values"][:R], ref.values_array)
+        assert np.array_equal(arr["rewards"][:R], ref.rewards_array) and np.array_equal(arr["perms"][:R], ref.perms_array)
+        assert np.array_equal(arr["advs"][:R], ref.additional_array("advs"))
+        assert np.array_equal(arr["rets"][:R], ref.additional_array("rets"))

@@ -22,6 +22,14 @@ struct EnvParams {
     int difficulty, depth_slope, max_depth;
 };
 
+// Global (Philox) env id of local env e: base + (e + off) mod `mod` (mod == 0: base + e).  The rotation lets
+// a collect lay episodes out directly in the reference's merge order [last, 0, 1, ..., n-2]
+// (collector/collector.rs:40-46): local 0 is the LAST episode id, local i is episode i-1.
+struct EnvIds {
+    uint32_t base, off, mod;
+    __host__ __device__ __forceinline__ uint32_t gid(uint32_t e) const { return base + (mod ? (e + off) % mod : e); }
+};
+
 // ------------------------------------------------------------------ Philox ---
 __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                        uint32_t k0, uint32_t k1, uint32_t out[4]) {

@@ -82,9 +82,16 @@ struct twr_engine {
     bool own_stream = false;
     uint32_t collect_id = 0;
     long long launches0 = 0;
-    // collect buffers
+    // collect buffers: working set + two compacted-output sets (double buffered for the pipelined host collect)
     CollectBuffers buf{};
+    struct OutSet { uint16_t* obs = nullptr; float* logits = nullptr; float* values = nullptr; float* rewards = nullptr;
+                    float* advs = nullptr; float* rets = nullptr; uint8_t* actions = nullptr; int8_t* perms = nullptr; };
+    OutSet outs[2];
+    int32_t* ep_len_id = nullptr; int64_t cap_E = 0;
     int64_t cap_B = 0; int cap_T = 0; int64_t cap_R = 0; int cap_cells = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    unsigned long long* h_stats = nullptr;   // pinned
     bool has_last = false;
     twr_collected last{};
     // timing
@@ -185,6 +192,12 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
         e->own_stream = true;
     }
     cudaEventCreate(&e->ev_t0); cudaEventCreate(&e->ev_t1);
+    cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming);
+    }
+    cudaHostAlloc(reinterpret_cast<void**>(&e->h_stats), 8 * sizeof(unsigned long long), cudaHostAllocDefault);
     e->launches0 = g_twr_launches.load();
     *out = e;
     return TWR_OK;
@@ -197,8 +210,10 @@ static void free_collect_buffers(twr_engine* e) {
     dev_free(b.rec_state); dev_free(b.rec_logits); dev_free(b.rec_value); dev_free(b.rec_reward);
     dev_free(b.rec_adv); dev_free(b.rec_ret); dev_free(b.rec_action); dev_free(b.rec_perm);
     dev_free(b.ep_len); dev_free(b.ep_off); dev_free(b.stats);
-    dev_free(b.out_obs); dev_free(b.out_logits); dev_free(b.out_values); dev_free(b.out_rewards);
-    dev_free(b.out_advs); dev_free(b.out_rets); dev_free(b.out_actions); dev_free(b.out_perms);
+    for (auto& o : e->outs) {
+        dev_free(o.obs); dev_free(o.logits); dev_free(o.values); dev_free(o.rewards);
+        dev_free(o.advs); dev_free(o.rets); dev_free(o.actions); dev_free(o.perms);
+    }
     e->cap_B = 0; e->cap_T = 0; e->cap_R = 0; e->cap_cells = 0;
 }
 
@@ -208,6 +223,10 @@ void twr_engine_destroy(twr_engine* e) {
     cudaStreamSynchronize(e->stream);
     free_collect_buffers(e);
     for (auto ev : e->ev) cudaEventDestroy(ev);
+    dev_free(e->ep_len_id);
+    for (int i = 0; i < 2; ++i) { if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]); }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->h_stats) cudaFreeHost(e->h_stats);
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
     if (e->ev_t1) cudaEventDestroy(e->ev_t1);
     if (e->own_stream) cudaStreamDestroy(e->stream);
@@ -452,7 +471,7 @@ int twr_envs_reset(twr_envs* v, uint32_t env_id_base, uint32_t collect_id) {
         return fail(TWR_ERR_INVALID, "GridWorld reset needs difficulty >= 1 (the reference loops forever at 0)");
     twr_engine* e = v->eng;
     CU_TRY(cudaSetDevice(e->device));
-    launch_envs_reset(e->stream, v->p, v->cells, v->meta, v->n, e->seed, env_id_base, collect_id, nullptr, nullptr);
+    launch_envs_reset(e->stream, v->p, v->cells, v->meta, v->n, e->seed, EnvIds{env_id_base, 0u, 0u}, collect_id, nullptr, nullptr);
     CU_TRY(cudaStreamSynchronize(e->stream));
     return TWR_OK;
 }
@@ -514,7 +533,7 @@ int twr_policy_forward(twr_engine* e, const twr_policy* p, twr_envs* v, const in
         CU_TRY(cudaMemcpyAsync(d_perm.d, perm_idx, sizeof(int32_t) * (size_t)v->n, cudaMemcpyHostToDevice, e->stream));
     }
     ForwardArgs a{};
-    a.env = v->p; a.seed = e->seed; a.cid = 0; a.env_id_base = 0; a.t = -1;
+    a.env = v->p; a.seed = e->seed; a.cid = 0; a.ids = EnvIds{0u, 0u, 0u}; a.t = -1;
     a.perm_idx = perm_idx ? d_perm.d : nullptr;
     a.cells = v->cells; a.live = nullptr; a.n_live_ptr = nullptr; a.n = v->n;
     a.logits = d_logits.d; a.values = d_values.d;
@@ -646,12 +665,28 @@ int64_t twr_max_records(const twr_env_spec* spec, int64_t num_episodes) {
     return num_episodes * (int64_t)(horizon_of(p) + 1);
 }
 
-static int ensure_collect_buffers(twr_engine* e, int64_t B, int T, int cells) {
+static void select_outset(twr_engine* e, int which) {
+    CollectBuffers& b = e->buf;
+    const twr_engine::OutSet& o = e->outs[which];
+    b.out_obs = o.obs; b.out_logits = o.logits; b.out_values = o.values; b.out_rewards = o.rewards;
+    b.out_advs = o.advs; b.out_rets = o.rets; b.out_actions = o.actions; b.out_perms = o.perms;
+}
+
+static int ensure_collect_buffers(twr_engine* e, int64_t B, int T, int cells, int64_t total_episodes) {
+    if (total_episodes > e->cap_E) {
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        dev_free(e->ep_len_id);
+        int rc = dev_alloc(&e->ep_len_id, (size_t)total_episodes);
+        if (rc) return rc;
+        e->cap_E = total_episodes;
+    }
+    e->buf.ep_len_id = e->ep_len_id;
     if (B <= e->cap_B && T <= e->cap_T && cells <= e->cap_cells && B * T <= e->cap_R) {
         e->buf.B = B; e->buf.Tmax = T;
         return TWR_OK;
     }
     CU_TRY(cudaStreamSynchronize(e->stream));
+    CU_TRY(cudaStreamSynchronize(e->copy_stream));
     free_collect_buffers(e);
     CollectBuffers& b = e->buf;
     const size_t R = (size_t)B * T;
@@ -664,63 +699,49 @@ static int ensure_collect_buffers(twr_engine* e, int64_t B, int T, int cells) {
         (rc = dev_alloc(&b.rec_reward, R)) || (rc = dev_alloc(&b.rec_adv, R)) || (rc = dev_alloc(&b.rec_ret, R)) ||
         (rc = dev_alloc(&b.rec_action, R)) || (rc = dev_alloc(&b.rec_perm, R)) ||
         (rc = dev_alloc(&b.ep_len, (size_t)B)) || (rc = dev_alloc(&b.ep_off, (size_t)B)) ||
-        (rc = dev_alloc(&b.stats, 4)) || (rc = dev_alloc(&b.out_obs, R * cells)) ||
-        (rc = dev_alloc(&b.out_logits, R * TWR_MAX_ACTIONS)) || (rc = dev_alloc(&b.out_values, R)) ||
-        (rc = dev_alloc(&b.out_rewards, R)) || (rc = dev_alloc(&b.out_advs, R)) || (rc = dev_alloc(&b.out_rets, R)) ||
-        (rc = dev_alloc(&b.out_actions, R)) || (rc = dev_alloc(&b.out_perms, R))) {
+        (rc = dev_alloc(&b.stats, 4))) {
         free_collect_buffers(e);
         return rc;
+    }
+    for (auto& o : e->outs) {
+        if ((rc = dev_alloc(&o.obs, R * cells)) || (rc = dev_alloc(&o.logits, R * TWR_MAX_ACTIONS)) ||
+            (rc = dev_alloc(&o.values, R)) || (rc = dev_alloc(&o.rewards, R)) || (rc = dev_alloc(&o.advs, R)) ||
+            (rc = dev_alloc(&o.rets, R)) || (rc = dev_alloc(&o.actions, R)) || (rc = dev_alloc(&o.perms, R))) {
+            free_collect_buffers(e);
+            return rc;
+        }
     }
     e->cap_B = B; e->cap_T = T; e->cap_R = (int64_t)R; e->cap_cells = cells;
     b.B = B; b.Tmax = T;
     return TWR_OK;
 }
 
-int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, float gamma,
-                    float lambda, twr_collected* out) {
-    if (!e || !p || !out) return fail(TWR_ERR_INVALID, "NULL argument");
-    if (p->eng != e) return fail(TWR_ERR_INVALID, "policy belongs to another engine");
-    // merge() errors on zero chunks (collector/collector.rs:41)
-    if (num_episodes <= 0)
-        return fail(TWR_ERR_INVALID, "Something went wrong. No data in collected data chunks to merge. ");
-    if (num_episodes >= (1ll << 31)) return fail(TWR_ERR_INVALID, "num_episodes too large");
-    EnvParams env;
-    int rc = check_spec(spec, &env);
-    if (rc) return rc;
-    if (env.kind == TWR_ENV_GRIDWORLD && env.difficulty < 1)
-        return fail(TWR_ERR_INVALID, "GridWorld reset needs difficulty >= 1 (the reference loops forever at 0)");
-    PolicyDev dev;
-    if ((rc = check_policy_env(p, env, &dev))) return rc;
-    CU_TRY(cudaSetDevice(e->device));
-    const int T = horizon_of(env) + 1;
-    if ((rc = ensure_collect_buffers(e, num_episodes, T, env.N))) return rc;
+// Enqueue one (sub-)collect of B local episodes on the engine stream: reset -> T x (forward [+ step]) -> GAE ->
+// offsets -> compaction into output set `which`.  No host synchronisation.
+static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev& dev, int64_t B, EnvIds ids, uint32_t cid,
+                           float gamma, float lambda, int which, int* n_fwd_out) {
     CollectBuffers& b = e->buf;
     cudaStream_t st = e->stream;
-    e->has_last = false;
-
-    const uint32_t cid = e->collect_id++;
-    const uint32_t env_id_base = (uint32_t)((int64_t)e->rank * num_episodes);
+    const int T = b.Tmax;
+    b.B = B;
+    select_outset(e, which);
     CU_TRY(cudaMemsetAsync(b.n_live, 0, sizeof(int32_t) * (size_t)(T + 1), st));
     CU_TRY(cudaMemsetAsync(b.stats, 0, sizeof(unsigned long long) * 4, st));
-    if (e->timing) {
-        while ((int)e->ev.size() < 2 * T) { cudaEvent_t ev; cudaEventCreate(&ev); e->ev.push_back(ev); }
-        cudaEventRecord(e->ev_t0, st);
-    }
-    launch_envs_reset(st, env, b.cells, b.meta, num_episodes, e->seed, env_id_base, cid, b.live_a, b.n_live);
+    launch_envs_reset(st, env, b.cells, b.meta, B, e->seed, ids, cid, b.live_a, b.n_live);
 
     StepArgs sa{};
-    sa.env = env; sa.seed = e->seed; sa.cid = cid; sa.env_id_base = env_id_base; sa.n_perms = dev.n_perms; sa.A = dev.A;
+    sa.env = env; sa.seed = e->seed; sa.cid = cid; sa.ids = ids; sa.n_perms = dev.n_perms; sa.A = dev.A;
     ForwardArgs fa{};
-    fa.env = env; fa.seed = e->seed; fa.cid = cid; fa.env_id_base = env_id_base; fa.perm_idx = nullptr;
-    fa.cells = b.cells; fa.n = num_episodes; fa.logits = b.logits; fa.values = b.values;
+    fa.env = env; fa.seed = e->seed; fa.cid = cid; fa.ids = ids; fa.perm_idx = nullptr;
+    fa.cells = b.cells; fa.n = B; fa.logits = b.logits; fa.values = b.values;
     const bool fused = e->precision == TWR_PREC_F16X2 && forward_tc_can_fuse(dev);
-    int n_fwd = 0;
+    int n_fwd = *n_fwd_out;
     if (fused) {
         // Persistent chunks: one launch covers `chunk` consecutive steps of every tile (envs stay with their
         // CTA pair, finished envs idle), then the live list is re-compacted.  Short episodes use chunk 1.
         int chunk = T / 8 < 1 ? 1 : (T / 8 > 32 ? 32 : T / 8);
         if (const char* c = getenv("TWISTERL_B200_CHUNK")) { const int v = atoi(c); if (v >= 1) chunk = v; }
-        CU_TRY(cudaMemsetAsync(b.ep_len, 0, sizeof(int32_t) * (size_t)num_episodes, st));
+        CU_TRY(cudaMemsetAsync(b.ep_len, 0, sizeof(int32_t) * (size_t)B, st));
         int32_t* cur = b.live_a;
         int32_t* nxt = b.live_b;
         for (int t0 = 0, ci = 0; t0 < T; t0 += chunk, ++ci) {
@@ -729,11 +750,11 @@ int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p
             sa.t = t0;
             fa.fused = 1; fa.step = sa; fa.cb = b; fa.live_next = cnt == 1 ? nxt : nullptr;
             if (cnt == 1) { fa.cb.n_live = b.n_live + ci - t0; }   // collect_step_body appends at n_live[t+1]
-            if (e->timing) cudaEventRecord(e->ev[2 * n_fwd], st);
+            if (e->timing && 2 * n_fwd + 1 < (int)e->ev.size()) cudaEventRecord(e->ev[2 * n_fwd], st);
             launch_forward(e, dev, fa);
-            if (e->timing) cudaEventRecord(e->ev[2 * n_fwd + 1], st);
+            if (e->timing && 2 * n_fwd + 1 < (int)e->ev.size()) cudaEventRecord(e->ev[2 * n_fwd + 1], st);
             ++n_fwd;
-            if (cnt > 1) launch_compact_live(st, cur, b.n_live + ci, b.ep_len, num_episodes, nxt, b.n_live + ci + 1);
+            if (cnt > 1) launch_compact_live(st, cur, b.n_live + ci, b.ep_len, B, nxt, b.n_live + ci + 1);
             int32_t* tmp = cur; cur = nxt; nxt = tmp;
         }
     } else {
@@ -742,38 +763,95 @@ int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p
             int32_t* nxt = (t & 1) ? b.live_a : b.live_b;
             fa.t = t; fa.live = cur; fa.n_live_ptr = b.n_live + t;
             sa.t = t;
-            if (e->timing) cudaEventRecord(e->ev[2 * t], st);
+            if (e->timing && 2 * n_fwd + 1 < (int)e->ev.size()) cudaEventRecord(e->ev[2 * n_fwd], st);
             launch_forward(e, dev, fa);
-            if (e->timing) cudaEventRecord(e->ev[2 * t + 1], st);
+            if (e->timing && 2 * n_fwd + 1 < (int)e->ev.size()) cudaEventRecord(e->ev[2 * n_fwd + 1], st);
+            ++n_fwd;
             launch_collect_step(st, sa, b, cur, nxt);
         }
-        n_fwd = T;
     }
+    *n_fwd_out = n_fwd;
     launch_gae_time_major(st, b, gamma, lambda);
-    launch_episode_offsets(st, b);
+    launch_episode_offsets(st, b, ids);
     launch_compact(st, env, b, dev.A);
-    if (e->timing) cudaEventRecord(e->ev_t1, st);
     CU_TRY(cudaGetLastError());
+    return TWR_OK;
+}
 
-    unsigned long long h_stats[4];
-    CU_TRY(cudaMemcpyAsync(h_stats, b.stats, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
+struct CollectPlan { EnvParams env; PolicyDev dev; int T; };
+
+static int plan_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, CollectPlan* plan) {
+    if (!e || !p) return fail(TWR_ERR_INVALID, "NULL argument");
+    if (p->eng != e) return fail(TWR_ERR_INVALID, "policy belongs to another engine");
+    // merge() errors on zero chunks (collector/collector.rs:41)
+    if (num_episodes <= 0)
+        return fail(TWR_ERR_INVALID, "Something went wrong. No data in collected data chunks to merge. ");
+    if (num_episodes >= (1ll << 31)) return fail(TWR_ERR_INVALID, "num_episodes too large");
+    int rc = check_spec(spec, &plan->env);
+    if (rc) return rc;
+    if (plan->env.kind == TWR_ENV_GRIDWORLD && plan->env.difficulty < 1)
+        return fail(TWR_ERR_INVALID, "GridWorld reset needs difficulty >= 1 (the reference loops forever at 0)");
+    if ((rc = check_policy_env(p, plan->env, &plan->dev))) return rc;
+    plan->T = horizon_of(plan->env) + 1;
+    return TWR_OK;
+}
+
+static void finish_timing(twr_engine* e, int n_fwd) {
+    if (!e->timing) return;
+    float tot = 0.f, ms = 0.f;
+    const int n = n_fwd < (int)e->ev.size() / 2 ? n_fwd : (int)e->ev.size() / 2;
+    for (int t = 0; t < n; ++t) { cudaEventElapsedTime(&ms, e->ev[2 * t], e->ev[2 * t + 1]); tot += ms; }
+    e->last_fwd_ms = tot; e->last_fwd_launches = n;
+    cudaEventElapsedTime(&e->last_total_ms, e->ev_t0, e->ev_t1);
+}
+
+int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, float gamma,
+                    float lambda, twr_collected* out) {
+    if (!out) return fail(TWR_ERR_INVALID, "NULL argument");
+    CollectPlan plan;
+    int rc = plan_collect(e, spec, p, num_episodes, &plan);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(e->device));
+    if ((rc = ensure_collect_buffers(e, num_episodes, plan.T, plan.env.N, num_episodes))) return rc;
+    cudaStream_t st = e->stream;
+    e->has_last = false;
+    const uint32_t cid = e->collect_id++;
+    // local episode 0 is the LAST episode id, local i is episode i-1: local order == merge order
+    const EnvIds ids{(uint32_t)((int64_t)e->rank * num_episodes), (uint32_t)(num_episodes - 1), (uint32_t)num_episodes};
     if (e->timing) {
-        float tot = 0.f, ms = 0.f;
-        for (int t = 0; t < n_fwd; ++t) { cudaEventElapsedTime(&ms, e->ev[2 * t], e->ev[2 * t + 1]); tot += ms; }
-        e->last_fwd_ms = tot; e->last_fwd_launches = n_fwd;
-        cudaEventElapsedTime(&e->last_total_ms, e->ev_t0, e->ev_t1);
+        while ((int)e->ev.size() < 2 * (plan.T + 1)) { cudaEvent_t ev; cudaEventCreate(&ev); e->ev.push_back(ev); }
+        cudaEventRecord(e->ev_t0, st);
     }
+    int n_fwd = 0;
+    if ((rc = enqueue_collect(e, plan.env, plan.dev, num_episodes, ids, cid, gamma, lambda, 0, &n_fwd))) return rc;
+    if (e->timing) cudaEventRecord(e->ev_t1, st);
+    CU_TRY(cudaMemcpyAsync(e->h_stats, e->buf.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    finish_timing(e, n_fwd);
+    CollectBuffers& b = e->buf;
     twr_collected& c = e->last;
-    c.n_records = (int64_t)h_stats[1];
+    c.n_records = (int64_t)e->h_stats[1];
     c.num_episodes = num_episodes;
-    c.n_cells = env.N; c.num_actions = dev.A;
-    c.successes = (int64_t)h_stats[0];
-    double rs; memcpy(&rs, &h_stats[2], sizeof(double)); c.reward_sum = rs;
+    c.n_cells = plan.env.N; c.num_actions = plan.dev.A;
+    c.successes = (int64_t)e->h_stats[0];
+    double rs; memcpy(&rs, &e->h_stats[2], sizeof(double)); c.reward_sum = rs;
     c.obs = b.out_obs; c.logits = b.out_logits; c.values = b.out_values; c.rewards = b.out_rewards;
-    c.advs = b.out_advs; c.rets = b.out_rets; c.actions = b.out_actions; c.perms = b.out_perms; c.ep_len = b.ep_len;
+    c.advs = b.out_advs; c.rets = b.out_rets; c.actions = b.out_actions; c.perms = b.out_perms; c.ep_len = e->ep_len_id;
     e->has_last = true;
     *out = c;
+    return TWR_OK;
+}
+
+static int copy_out(twr_engine* e, cudaStream_t st, const twr_host_buffers* dst, int64_t at, size_t R, int n_cells, int A) {
+    const CollectBuffers& b = e->buf;
+    if (dst->obs) CU_TRY(cudaMemcpyAsync(dst->obs + at * n_cells, b.out_obs, sizeof(uint16_t) * R * n_cells, cudaMemcpyDeviceToHost, st));
+    if (dst->logits) CU_TRY(cudaMemcpyAsync(dst->logits + at * A, b.out_logits, sizeof(float) * R * A, cudaMemcpyDeviceToHost, st));
+    if (dst->values) CU_TRY(cudaMemcpyAsync(dst->values + at, b.out_values, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
+    if (dst->rewards) CU_TRY(cudaMemcpyAsync(dst->rewards + at, b.out_rewards, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
+    if (dst->advs) CU_TRY(cudaMemcpyAsync(dst->advs + at, b.out_advs, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
+    if (dst->rets) CU_TRY(cudaMemcpyAsync(dst->rets + at, b.out_rets, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
+    if (dst->actions) CU_TRY(cudaMemcpyAsync(dst->actions + at, b.out_actions, R, cudaMemcpyDeviceToHost, st));
+    if (dst->perms) CU_TRY(cudaMemcpyAsync(dst->perms + at, b.out_perms, R, cudaMemcpyDeviceToHost, st));
     return TWR_OK;
 }
 
@@ -785,26 +863,70 @@ int twr_collected_to_host(twr_engine* e, const twr_host_buffers* dst) {
     if ((int64_t)R > dst->capacity) return fail(TWR_ERR_INVALID, "host buffers too small for the collected records");
     CU_TRY(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
-    if (dst->obs) CU_TRY(cudaMemcpyAsync(dst->obs, c.obs, sizeof(uint16_t) * R * c.n_cells, cudaMemcpyDeviceToHost, st));
-    if (dst->logits) CU_TRY(cudaMemcpyAsync(dst->logits, c.logits, sizeof(float) * R * c.num_actions, cudaMemcpyDeviceToHost, st));
-    if (dst->values) CU_TRY(cudaMemcpyAsync(dst->values, c.values, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
-    if (dst->rewards) CU_TRY(cudaMemcpyAsync(dst->rewards, c.rewards, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
-    if (dst->advs) CU_TRY(cudaMemcpyAsync(dst->advs, c.advs, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
-    if (dst->rets) CU_TRY(cudaMemcpyAsync(dst->rets, c.rets, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
-    if (dst->actions) CU_TRY(cudaMemcpyAsync(dst->actions, c.actions, R, cudaMemcpyDeviceToHost, st));
-    if (dst->perms) CU_TRY(cudaMemcpyAsync(dst->perms, c.perms, R, cudaMemcpyDeviceToHost, st));
+    int rc = copy_out(e, st, dst, 0, R, c.n_cells, c.num_actions);
+    if (rc) return rc;
     if (dst->ep_len) CU_TRY(cudaMemcpyAsync(dst->ep_len, c.ep_len, sizeof(int32_t) * (size_t)c.num_episodes, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     return TWR_OK;
 }
 
+// End-to-end collect with host buffers.  Large collects are split into sub-batches of consecutive local
+// episodes so that the D2H copy of sub-batch k (copy stream) overlaps the rollout of sub-batch k+1.
 int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p, const twr_policy_desc* desc,
                          int64_t num_episodes, float gamma, float lambda, const twr_host_buffers* dst, twr_collected* out) {
     if (!e || !p || !dst || !out) return fail(TWR_ERR_INVALID, "NULL argument");
     int rc;
     if (desc && (rc = twr_policy_update(p, desc))) return rc;
-    if ((rc = twr_ppo_collect(e, spec, p, num_episodes, gamma, lambda, out))) return rc;
-    return twr_collected_to_host(e, dst);
+    int split = num_episodes >= 32768 ? 2 : 1;
+    if (const char* sp = getenv("TWISTERL_B200_E2E_SPLIT")) { const int v = atoi(sp); if (v >= 1 && v <= 64) split = v; }
+    if (split > num_episodes) split = (int)num_episodes;
+    if (split == 1) {
+        if ((rc = twr_ppo_collect(e, spec, p, num_episodes, gamma, lambda, out))) return rc;
+        return twr_collected_to_host(e, dst);
+    }
+    CollectPlan plan;
+    if ((rc = plan_collect(e, spec, p, num_episodes, &plan))) return rc;
+    CU_TRY(cudaSetDevice(e->device));
+    const int64_t Bsub = (num_episodes + split - 1) / split;
+    if ((rc = ensure_collect_buffers(e, Bsub, plan.T, plan.env.N, num_episodes))) return rc;
+    e->has_last = false;
+    const uint32_t cid = e->collect_id++;
+    const uint32_t base = (uint32_t)((int64_t)e->rank * num_episodes);
+    int64_t at = 0, successes = 0;
+    double reward_sum = 0.0;
+    int n_fwd = 0;
+    const bool timing = e->timing;
+    e->timing = false;                                  // per-forward events are only kept for the device-resident path
+    for (int k = 0; k < split; ++k) {
+        const int64_t lo = (int64_t)k * Bsub;
+        const int64_t B = lo + Bsub <= num_episodes ? Bsub : num_episodes - lo;
+        if (B <= 0) break;
+        const int which = k & 1;
+        if (k >= 2) CU_TRY(cudaStreamWaitEvent(e->stream, e->ev_copied[which], 0));   // output set free again
+        // global local index = lo + i; episode id = (lo + i + E - 1) mod E
+        const EnvIds ids{base, (uint32_t)((lo + num_episodes - 1) % num_episodes), (uint32_t)num_episodes};
+        if ((rc = enqueue_collect(e, plan.env, plan.dev, B, ids, cid, gamma, lambda, which, &n_fwd))) { e->timing = timing; return rc; }
+        CU_TRY(cudaMemcpyAsync(e->h_stats, e->buf.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU_TRY(cudaEventRecord(e->ev_done[which], e->stream));
+        CU_TRY(cudaStreamSynchronize(e->stream));       // record count of this sub-batch -> host offsets
+        const size_t R = (size_t)e->h_stats[1];
+        successes += (int64_t)e->h_stats[0];
+        double rs; memcpy(&rs, &e->h_stats[2], sizeof(double)); reward_sum += rs;
+        if (at + (int64_t)R > dst->capacity) { e->timing = timing; return fail(TWR_ERR_INVALID, "host buffers too small for the collected records"); }
+        CU_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_done[which], 0));
+        if ((rc = copy_out(e, e->copy_stream, dst, at, R, plan.env.N, plan.dev.A))) { e->timing = timing; return rc; }
+        CU_TRY(cudaEventRecord(e->ev_copied[which], e->copy_stream));
+        at += (int64_t)R;
+    }
+    e->timing = timing;
+    if (dst->ep_len)
+        CU_TRY(cudaMemcpyAsync(dst->ep_len, e->ep_len_id, sizeof(int32_t) * (size_t)num_episodes, cudaMemcpyDeviceToHost, e->copy_stream));
+    CU_TRY(cudaStreamSynchronize(e->copy_stream));
+    twr_collected c{};
+    c.n_records = at; c.num_episodes = num_episodes; c.n_cells = plan.env.N; c.num_actions = plan.dev.A;
+    c.successes = successes; c.reward_sum = reward_sum;    // device pointers stay NULL: the data now lives in `dst`
+    *out = c;
+    return TWR_OK;
 }
 
 int twr_host_alloc(void** ptr, int64_t bytes) {

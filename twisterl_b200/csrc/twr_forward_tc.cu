@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward_tc(PolicyDev p, Forward
                     perm = a.perm_idx[pos];
                 } else if (p.n_perms > 0 && a.t >= 0) {        // get_perm_id, nn/policy.rs:67-77
                     uint32_t w[4];
-                    philox4x32_10(a.env_id_base + (uint32_t)e, (uint32_t)a.t, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
+                    philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)a.t, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
                                   (uint32_t)(a.seed >> 32), w);
                     perm = (int)mulhi_u32(w[0], (uint32_t)p.n_perms);
                 }

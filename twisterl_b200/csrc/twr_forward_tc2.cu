@@ -358,7 +358,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     perm = a.perm_idx[pos];
                 } else if (p.n_perms > 0 && a.t >= 0) {
                     uint32_t w[4];
-                    philox4x32_10(a.env_id_base + (uint32_t)e, (uint32_t)t_cur, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
+                    philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)t_cur, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
                                   (uint32_t)(a.seed >> 32), w);
                     perm = (int)mulhi_u32(w[0], (uint32_t)p.n_perms);
                 }

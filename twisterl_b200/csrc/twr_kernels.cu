@@ -18,12 +18,12 @@ static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + b
 
 // ------------------------------------------------------------------------- K1 ---
 __global__ void __launch_bounds__(256) k_envs_reset(EnvParams p, uint4* __restrict__ cells, uint32_t* __restrict__ meta,
-                                                    int64_t n, uint64_t seed, uint32_t env_id_base, uint32_t cid,
+                                                    int64_t n, uint64_t seed, EnvIds ids, uint32_t cid,
                                                     int32_t* __restrict__ live, int32_t* __restrict__ n_live0) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e == 0 && n_live0) *n_live0 = (int32_t)n;
     if (e >= n) return;
-    const EnvState s = env_reset(p, seed, env_id_base + (uint32_t)e, cid);
+    const EnvState s = env_reset(p, seed, ids.gid((uint32_t)e), cid);
     env_store(cells, meta, e, s);
     if (live) live[e] = (int32_t)e;
 }
@@ -110,9 +110,9 @@ __global__ void __launch_bounds__(256) k_mask_logits(EnvParams p, const uint4* _
 }
 
 void launch_envs_reset(cudaStream_t st, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n, uint64_t seed,
-                       uint32_t env_id_base, uint32_t cid, int32_t* live, int32_t* n_live0) {
+                       EnvIds ids, uint32_t cid, int32_t* live, int32_t* n_live0) {
     if (n <= 0) return;
-    k_envs_reset<<<grid_for(n, 256), 256, 0, st>>>(p, cells, meta, n, seed, env_id_base, cid, live, n_live0);
+    k_envs_reset<<<grid_for(n, 256), 256, 0, st>>>(p, cells, meta, n, seed, ids, cid, live, n_live0);
     TWR_COUNT_LAUNCH();
 }
 void launch_envs_fresh(cudaStream_t st, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n) {
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) k_collect_step(StepArgs a, CollectBuffers
         value = b.values[pos];
         if (a.n_perms > 0) {                                  // get_perm_id, nn/policy.rs:67-77
             uint32_t w[4];
-            philox4x32_10(a.env_id_base + (uint32_t)e, (uint32_t)a.t, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
+            philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)a.t, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
                           (uint32_t)(a.seed >> 32), w);
             perm = (int)mulhi_u32(w[0], (uint32_t)a.n_perms);
         }
@@ -281,15 +281,16 @@ void launch_gae_concat(cudaStream_t st, const float* r, const float* v, const in
 }
 
 // ------------------------------------------------------------------------- K5 ---
-// Exclusive scan of episode lengths in the reference's merge order (collector/collector.rs:40-46:
-// slot 0 = last episode, slots 1.. = episodes 0..n-2).  One CTA; thread i owns a contiguous run.
-__global__ void __launch_bounds__(1024) k_episode_offsets(CollectBuffers b) {
+// Exclusive scan of episode lengths in local order (the env-id rotation of EnvIds already puts the
+// LAST episode id at local 0, i.e. local order == the reference's merge order, collector.rs:40-46).
+// One CTA; thread i owns a contiguous run.  Also scatters ep_len by episode id.
+__global__ void __launch_bounds__(1024) k_episode_offsets(CollectBuffers b, EnvIds ids) {
     __shared__ long long part[1024];
     const int64_t B = b.B;
     const int64_t per = (B + 1023) / 1024;
     const int64_t s0 = (int64_t)threadIdx.x * per, s1 = min(B, s0 + per);
     long long sum = 0;
-    for (int64_t s = s0; s < s1; ++s) sum += b.ep_len[s == 0 ? B - 1 : s - 1];
+    for (int64_t s = s0; s < s1; ++s) sum += b.ep_len[s];
     part[threadIdx.x] = sum;
     __syncthreads();
     for (int d = 1; d < 1024; d <<= 1) {       // Hillis-Steele inclusive scan
@@ -300,15 +301,15 @@ __global__ void __launch_bounds__(1024) k_episode_offsets(CollectBuffers b) {
     }
     long long run = part[threadIdx.x] - sum;
     for (int64_t s = s0; s < s1; ++s) {
-        const int64_t e = (s == 0) ? B - 1 : s - 1;
-        b.ep_off[e] = run;
-        run += b.ep_len[e];
+        b.ep_off[s] = run;
+        run += b.ep_len[s];
+        if (b.ep_len_id) b.ep_len_id[ids.gid((uint32_t)s) - ids.base] = b.ep_len[s];
     }
     if (threadIdx.x == 1023) b.stats[1] = (unsigned long long)part[1023];
 }
 
-void launch_episode_offsets(cudaStream_t st, const CollectBuffers& b) {
-    k_episode_offsets<<<1, 1024, 0, st>>>(b);
+void launch_episode_offsets(cudaStream_t st, const CollectBuffers& b, const EnvIds& ids) {
+    k_episode_offsets<<<1, 1024, 0, st>>>(b, ids);
     TWR_COUNT_LAUNCH();
 }
 

@@ -34,7 +34,9 @@ struct CollectBuffers {
     uint4* rec_state; float4* rec_logits; float* rec_value; float* rec_reward;
     float* rec_adv; float* rec_ret; uint8_t* rec_action; int8_t* rec_perm;
     int32_t* ep_len;      // [B]
-    int64_t* ep_off;      // [B] record offset of episode e in merged order
+    int64_t* ep_off;      // [B] record offset of local episode e (plain local order; the id rotation gives merge order)
+    int32_t* ep_len_id;   // [total episodes] episode length by episode id (filled by k_episode_offsets)
+    int64_t out_base;     // records of earlier sub-batches (pipelined host collect)
     unsigned long long* stats;  // [0] successes, [1] total records ; double at [2] = reward sum
     // compacted outputs
     uint16_t* out_obs; float* out_logits; float* out_values; float* out_rewards;
@@ -43,14 +45,14 @@ struct CollectBuffers {
 
 struct StepArgs {
     EnvParams env;
-    uint64_t seed; uint32_t cid; uint32_t env_id_base;
+    uint64_t seed; uint32_t cid; EnvIds ids;
     int n_perms; int A;
     int t;
 };
 
 // K1: batched Env-trait kernels (parity API + reset)
 void launch_envs_reset(cudaStream_t s, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n,
-                       uint64_t seed, uint32_t env_id_base, uint32_t cid, int32_t* live, int32_t* n_live0);
+                       uint64_t seed, EnvIds ids, uint32_t cid, int32_t* live, int32_t* n_live0);
 void launch_envs_fresh(cudaStream_t s, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n);
 void launch_envs_set_state(cudaStream_t s, const EnvParams& p, uint4* cells, uint32_t* meta, int64_t n,
                            const int64_t* d_states);
@@ -75,13 +77,13 @@ void launch_gae_time_major(cudaStream_t s, const CollectBuffers& b, float gamma,
 void launch_gae_concat(cudaStream_t s, const float* r, const float* v, const int64_t* off, int64_t n_ep,
                        float gamma, float lambda, float* adv, float* ret);
 // K5 episode offsets in merged order + transpose/compaction into concatenated episodes
-void launch_episode_offsets(cudaStream_t s, const CollectBuffers& b);
+void launch_episode_offsets(cudaStream_t s, const CollectBuffers& b, const EnvIds& ids);
 void launch_compact(cudaStream_t s, const EnvParams& p, const CollectBuffers& b, int A);
 
 // K2 policy forward.  `live` may be NULL (identity); n_live_ptr may be NULL (use n).
 struct ForwardArgs {
     EnvParams env;
-    uint64_t seed; uint32_t cid; uint32_t env_id_base; int t;  // twist pick stream
+    uint64_t seed; uint32_t cid; EnvIds ids; int t;  // twist pick stream
     const int32_t* perm_idx;  // explicit per-position twist (parity API) or NULL -> Philox pick
     const uint4* cells; const int32_t* live; const int32_t* n_live_ptr; int64_t n;
     const int32_t* obs_rows;  // optional [n][n_obs] sparse obs given directly (Policy.forward API); overrides cells

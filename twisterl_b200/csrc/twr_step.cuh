@@ -13,7 +13,7 @@ __device__ __forceinline__ void collect_step_body(const StepArgs& a, const Colle
     bool survives = false;
     if (active) {
         EnvState s = env_load(b.cells, b.meta, e);
-        const uint32_t gid = a.env_id_base + (uint32_t)e;
+        const uint32_t gid = a.ids.gid((uint32_t)e);
         const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
         const uint32_t m = env_masks(a.env, s);
         float l[4] = {raw.x, raw.y, raw.z, raw.w};

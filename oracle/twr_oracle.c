@@ -641,3 +641,99 @@ void orc_collected_free(orc_collected* c) {
     free(c->advs); free(c->rets); free(c->actions); free(c->perms);
     memset(c, 0, sizeof(*c));
 }
+
+/* ------------------------------------------------------- solve / evaluate --- */
+
+void orc_single_solve(orc_env* env, const orc_policy* p, int32_t deterministic, uint64_t seed, uint32_t collect_id,
+                      uint32_t stream_id, float* success, float* total, int32_t* actions, int32_t* n_actions) {
+    /* rl/solve.rs:17-71 */
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const int nc = orc_env_num_cells(env), na = orc_env_num_actions(env);
+    float tot = 0.0f;
+    int t = 0;
+    while (!orc_env_is_final(env)) {
+        int32_t obs[ORC_MAX_CELLS];
+        uint8_t masks[16];
+        float probs[16], value;
+        tot += orc_env_reward(env);
+        orc_env_observe(env, obs);
+        orc_env_masks(env, masks);
+        int perm = -1;
+        if (p->n_perms > 0) {
+            const uint32_t ctr[4] = {stream_id, (uint32_t)t, ORC_RNG_PERM, collect_id};
+            uint32_t w[4];
+            orc_philox4x32_10(ctr, key, w);
+            perm = (int)mulhi32(w[0], (uint32_t)p->n_perms);
+        }
+        orc_policy_predict(p, obs, nc, masks, perm, probs, &value);
+        int act = 0;
+        if (deterministic) {
+            act = orc_argmax(probs, na);
+        } else {
+            /* nn/policy.rs:153-167: WeightedIndex -- first index whose cumulative weight exceeds the draw */
+            float tw = 0.0f;
+            for (int i = 0; i < na; ++i) tw += probs[i];
+            if (tw > 0.0f) {
+                const uint32_t ctr[4] = {stream_id, (uint32_t)t, ORC_RNG_SOLVE, collect_id};
+                uint32_t w[4];
+                orc_philox4x32_10(ctr, key, w);
+                const float chosen = orc_u32_to_unit_f32(w[0]) * tw;
+                float cum = 0.0f;
+                int last = 0, found = 0;
+                for (int i = 0; i < na; ++i) {
+                    if (probs[i] > 0.0f) {
+                        cum += probs[i];
+                        last = i;
+                        if (!found && cum > chosen) { act = i; found = 1; }
+                    }
+                }
+                if (!found) act = last;
+            }
+        }
+        orc_env_step(env, act);
+        if (actions) actions[t] = act;
+        ++t;
+    }
+    tot += orc_env_reward(env);
+    *success = orc_env_success(env) ? 1.0f : 0.0f;
+    *total = tot;
+    if (n_actions) *n_actions = t;
+}
+
+void orc_solve(const orc_env* env, const orc_policy* p, int32_t deterministic, int32_t num_searches, uint64_t seed,
+               uint32_t collect_id, uint32_t id0, float* success, float* total, int32_t* actions, int32_t* n_actions) {
+    /* rl/solve.rs:73-101: best = ((0, -inf), []) ; strict tuple '>' keeps the first best */
+    float bs = 0.0f, br = -INFINITY;
+    int bn = 0;
+    int32_t tmp[4096];
+    for (int s = 0; s < num_searches; ++s) {
+        orc_env e = *env;
+        float s1, r1; int32_t n1 = 0;
+        orc_single_solve(&e, p, deterministic, seed, collect_id, id0 + (uint32_t)s, &s1, &r1, tmp, &n1);
+        if (s1 > bs || (s1 == bs && r1 > br)) {
+            bs = s1; br = r1; bn = n1;
+            if (actions) memcpy(actions, tmp, sizeof(int32_t) * (size_t)n1);
+        }
+    }
+    *success = bs; *total = br;
+    if (n_actions) *n_actions = bn;
+}
+
+void orc_evaluate(const orc_env_spec* spec, const orc_policy* p, int32_t num_episodes, int32_t deterministic,
+                  int32_t num_searches, uint64_t seed, uint32_t collect_id, uint32_t reset_base, uint32_t search_base,
+                  float* success_rate, float* mean_reward, float* best_success, float* best_total) {
+    /* rl/evaluate.rs:22-48 (the serial branch; the rayon branch reduces the same per-episode values) */
+    float succ = 0.0f, rew = 0.0f;
+    for (int ep = 0; ep < num_episodes; ++ep) {
+        orc_env env;
+        orc_env_init(&env, spec);
+        orc_env_reset(&env, seed, reset_base + (uint32_t)ep, collect_id);
+        float s1, r1;
+        orc_solve(&env, p, deterministic, num_searches, seed, collect_id, search_base + (uint32_t)(ep * num_searches), &s1, &r1, NULL, NULL);
+        succ += s1; rew += r1;
+        if (best_success) best_success[ep] = s1;
+        if (best_total) best_total[ep] = r1;
+    }
+    *success_rate = succ / (float)num_episodes;
+    *mean_reward = rew / (float)num_episodes;
+}

@@ -33,7 +33,7 @@ extern "C" {
 enum { ORC_ENV_PUZZLE = 0, ORC_ENV_GRIDWORLD = 1 };
 
 /* RNG stream kinds (counter word 2).  Shared, bit for bit, with the CUDA engine. */
-enum { ORC_RNG_RESET = 0, ORC_RNG_PERM = 1, ORC_RNG_SAMPLE = 2 };
+enum { ORC_RNG_RESET = 0, ORC_RNG_PERM = 1, ORC_RNG_SAMPLE = 2, ORC_RNG_SOLVE = 3 };
 
 /* Philox4x32-10 (Salmon et al., SC'11).  counter = (env_id, index, kind, collect_id),
  * key = (seed_lo, seed_hi). */
@@ -133,6 +133,20 @@ int  orc_ppo_collect(const orc_env_spec* spec, const orc_policy* p, int32_t num_
                      float gamma, float lambda, uint64_t seed, uint32_t collect_id,
                      uint32_t env_id_base, int32_t num_threads, orc_collected* out);
 void orc_collected_free(orc_collected* c);
+
+/* ---- solve / evaluate (rust/src/rl/solve.rs, rust/src/rl/evaluate.rs), num_mcts_searches == 0 ---- */
+/* single_solve (solve.rs:17-71) on `env` (modified in place) with Philox stream id `stream_id`:
+ * twist pick (stream_id, t, PERM), weighted draw (stream_id, t, SOLVE).  actions may be NULL. */
+void orc_single_solve(orc_env* env, const orc_policy* p, int32_t deterministic, uint64_t seed, uint32_t collect_id,
+                      uint32_t stream_id, float* success, float* total, int32_t* actions, int32_t* n_actions);
+/* solve (solve.rs:73-101): best of num_searches from a copy of `env`; search s uses stream id0 + s */
+void orc_solve(const orc_env* env, const orc_policy* p, int32_t deterministic, int32_t num_searches, uint64_t seed,
+               uint32_t collect_id, uint32_t id0, float* success, float* total, int32_t* actions, int32_t* n_actions);
+/* evaluate (evaluate.rs:22-89): episode ep resets from stream (reset_base + ep) and searches with ids
+ * search_base + ep*num_searches + s.  best_success/best_total: [num_episodes] or NULL. */
+void orc_evaluate(const orc_env_spec* spec, const orc_policy* p, int32_t num_episodes, int32_t deterministic,
+                  int32_t num_searches, uint64_t seed, uint32_t collect_id, uint32_t reset_base, uint32_t search_base,
+                  float* success_rate, float* mean_reward, float* best_success, float* best_total);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,104 @@
+"""GPU parity of collector.evaluate / collector.solve against the oracle's
+restatement of rust/src/rl/solve.rs and rust/src/rl/evaluate.rs on the shared Philox streams."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import synth_state_dict, trained15, transpose_twists
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+PRECISION = os.environ.get("TWISTERL_B200_PRECISION", "fp32")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import twisterl_b200 as tw
+    tw.configure(device=0, precision=PRECISION, seed=0x1234ABCD)
+    return tw.default_engine()
+
+
+def _evaluate(eng, env, pol, n, det, searches, cid):
+    from twisterl_b200 import _lib
+    import twisterl_b200 as tw
+    spec = tw.env.spec_from_env(env)
+    s, r = C.c_float(), C.c_float()
+    eng.set_collect_id(cid)
+    _lib.check(_lib.load().twr_evaluate(eng._h, C.byref(spec), pol.device_handle(eng), n, int(det), searches,
+                                        C.byref(s), C.byref(r)))
+    return float(s.value), float(r.value)
+
+
+@pytest.mark.parametrize("det,searches", [(True, 1), (False, 1), (False, 6)])
+def test_evaluate_matches_oracle(eng, det, searches):
+    import twisterl_b200 as tw
+    from parity import make_policies
+    _, sd = trained15()
+    pol, opol = make_policies(sd, 256)
+    ospec = orc.puzzle_spec(4, 4, 10, 2, 256)
+    env = tw.env.Puzzle(4, 4, 10, 2, 256)
+    n = 200
+    s, r = _evaluate(eng, env, pol, n, det, searches, cid=7)
+    os_, or_, bs, bt = orc.evaluate(ospec, opol, n, det, searches, seed=eng.seed, collect_id=7)
+    # identical streams: results agree except where ulp-level logit differences flip an argmax tie or move a
+    # weighted draw across a bin edge (rare) -- means must agree closely
+    assert abs(s - os_) <= 2.0 / n and abs(r - or_) <= 0.05
+    assert 0.0 <= s <= 1.0
+
+
+def test_evaluate_edge_cases_and_api(eng):
+    import twisterl_b200 as tw
+    from parity import make_policies
+    _, sd = trained15()
+    pol, _ = make_policies(sd, 256)
+    env = tw.env.Puzzle(4, 4, 0, 2, 256)                      # difficulty 0: already solved, reward 1.0
+    assert tw.collector.evaluate(env, pol, 16, False, 1, 0, 0, 1.4, 1, 32) == (1.0, 1.0)
+    s, r = _evaluate(eng, env, pol, 8, False, 0, cid=1)       # zero searches: solve()'s initial best
+    assert s == 0.0 and r == float("-inf")
+    with pytest.raises(NotImplementedError):
+        tw.collector.evaluate(env, pol, 4, False, 1, 3, 0, 1.4, 1, 1)
+    # keyword form used by rl/algorithm.py:98
+    out = tw.collector.evaluate(env, pol, num_episodes=4, deterministic=True, num_searches=2, num_mcts_searches=0, seed=1,
+                                C=1.4, max_expand_depth=1, num_cores=4)
+    assert out == (1.0, 1.0)
+    g = tw.env.GridWorld(5, 5, 64, 6)
+    gp, _ = make_policies(synth_state_dict(5, 625, 512, 128, 4), 625)
+    if PRECISION == "fp32":
+        s, r = tw.collector.evaluate(g, gp, 64, False, 2, 0, 0, 1.4, 1, 1)
+        assert 0.0 <= s <= 1.0 and -40.0 < r <= 1.0
+
+
+def test_solve_matches_oracle_and_replays(eng):
+    import twisterl_b200 as tw
+    from parity import make_policies
+    _, sd = trained15()
+    obs_perms, act_perms = transpose_twists(4)
+    for perms in (((), ()), (obs_perms, act_perms)):
+        pol, opol = make_policies(sd, 256, *perms)
+        env = tw.env.Puzzle(4, 4, 1, 2, 256)
+        start = [1, 5, 2, 3, 4, 0, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15]     # two moves from solved
+        env.set_state(start)
+        (succ, rew), acts = tw.collector.solve(env, pol, True, 1, 0, 1.4, 1)
+        assert env.get_state() == start                                   # the env itself is not advanced
+        oenv = orc.Env(orc.puzzle_spec(4, 4, 1, 2, 256)); oenv.set_state(start)
+        if not perms[0]:
+            (os_, or_), oacts = orc.solve(oenv, opol, True, 1, seed=eng.seed)
+            assert (succ, acts) == (os_, oacts) and abs(rew - or_) < 1e-6
+        assert succ == 1.0 and len(acts) >= 2
+        # the returned action list replays to a solved board with the returned reward
+        tot = np.float32(0)
+        for a in acts:
+            tot = np.float32(tot + np.float32(oenv.reward()))
+            oenv.step(a)
+        tot = np.float32(tot + np.float32(oenv.reward()))
+        assert oenv.success() and abs(float(tot) - rew) < 1e-6
+    # the 8-puzzle of the reference notebook (examples/puzzle.ipynb): sampled best-of-100 from a hard start
+    pol8, _ = make_policies(synth_state_dict(8, 81, 512, 256, 4), 81)
+    env8 = tw.env.Puzzle(3, 3, 1, 2, 256)
+    env8.set_state([8, 7, 5, 3, 2, 0, 4, 6, 1])
+    (s8, r8), a8 = tw.collector.solve(env8, pol8, False, 100, 0, 1.4, 1)
+    assert s8 in (0.0, 1.0) and len(a8) <= 256
+    if s8 == 0.0:
+        assert len(a8) == 256 and abs(r8 - (255 * (-0.5 / 256) + (-0.5 / 256) + -0.5)) < 1e-3

@@ -187,10 +187,39 @@ class AZCollector(PyBaseCollector):
                                   "there is no CPU fallback")
 
 
+def _no_mcts(num_mcts_searches):
+    if int(num_mcts_searches) != 0:
+        raise NotImplementedError("MCTS-guided solve/evaluate (num_mcts_searches > 0) is not implemented on the device "
+                                  "path yet; there is no CPU fallback")
+
+
 def solve(env, policy, deterministic, num_searches, num_mcts_searches, C, max_expand_depth):
-    raise NotImplementedError("collector.solve is not implemented on the device path yet (SURVEY.md 8f row f1)")
+    """`collector.solve` (python_interface/env.rs:180-191; rl/solve.rs:73-101): best of `num_searches` rollouts
+    from the env's CURRENT state -> ((success, reward), actions)."""
+    _no_mcts(num_mcts_searches)
+    spec_from_env(env)                       # rejects envs without a device implementation
+    eng = _lib.default_engine()
+    import ctypes as ct
+    batch = env._b()
+    if batch.engine is not eng:
+        raise RuntimeError("env state lives on another engine")
+    cap = int(batch.depth()[0]) + 1
+    acts = np.zeros(cap, dtype=np.int32)
+    succ, rew, n = ct.c_float(), ct.c_float(), ct.c_int32()
+    _lib.check(_lib.load().twr_solve(eng._h, batch._h, policy.device_handle(eng), int(bool(deterministic)), int(num_searches),
+                                     ct.byref(succ), ct.byref(rew), _lib.ptr(acts), cap, ct.byref(n)))
+    return (float(succ.value), float(rew.value)), [int(a) for a in acts[: n.value]]
 
 
 def evaluate(env, policy, num_episodes, deterministic, num_searches, num_mcts_searches, seed, C, max_expand_depth,
              num_cores):
-    raise NotImplementedError("collector.evaluate is not implemented on the device path yet (SURVEY.md 8f row f1)")
+    """`collector.evaluate` (python_interface/env.rs:194-207; rl/evaluate.rs:22-89) -> (success rate, mean reward).
+    `seed` is ignored like in the reference; `num_cores` is accepted for compatibility."""
+    _no_mcts(num_mcts_searches)
+    spec = spec_from_env(env)
+    eng = _lib.default_engine()
+    import ctypes as ct
+    s, r = ct.c_float(), ct.c_float()
+    _lib.check(_lib.load().twr_evaluate(eng._h, ct.byref(spec), policy.device_handle(eng), int(num_episodes),
+                                        int(bool(deterministic)), int(num_searches), ct.byref(s), ct.byref(r)))
+    return float(s.value), float(r.value)

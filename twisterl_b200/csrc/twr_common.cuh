@@ -14,7 +14,7 @@
 #define TWR_MAX_CELLS_PUZZLE 16
 #define TWR_MAX_CELLS 32
 
-enum : uint32_t { TWR_RNG_RESET = 0, TWR_RNG_PERM = 1, TWR_RNG_SAMPLE = 2 };
+enum : uint32_t { TWR_RNG_RESET = 0, TWR_RNG_PERM = 1, TWR_RNG_SAMPLE = 2, TWR_RNG_SOLVE = 3 };
 
 struct EnvParams {
     int kind;  // 0 puzzle, 1 grid_world
@@ -27,7 +27,11 @@ struct EnvParams {
 // (collector/collector.rs:40-46): local 0 is the LAST episode id, local i is episode i-1.
 struct EnvIds {
     uint32_t base, off, mod;
-    __host__ __device__ __forceinline__ uint32_t gid(uint32_t e) const { return base + (mod ? (e + off) % mod : e); }
+    uint32_t div;   // > 1: `div` consecutive local envs share one id (the searches of one evaluate() episode)
+    __host__ __device__ __forceinline__ uint32_t gid(uint32_t e) const {
+        if (div > 1) e /= div;
+        return base + (mod ? (e + off) % mod : e);
+    }
 };
 
 // ------------------------------------------------------------------ Philox ---

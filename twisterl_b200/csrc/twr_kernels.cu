@@ -408,3 +408,93 @@ void launch_compact(cudaStream_t st, const EnvParams& p, const CollectBuffers& b
     k_compact<<<grid, dim3(32, 8), 0, st>>>(p, b, A);
     TWR_COUNT_LAUNCH();
 }
+
+// ------------------------------------------------------------------------- f1 ---
+// One iteration of single_solve's loop (rl/solve.rs:30-60) per live env: a final state adds its reward and
+// retires; otherwise total += reward(s), probs = masked exp / (sum + 1e-6) (Policy::predict,
+// nn/policy.rs:43-47), action = argmax (deterministic) or a draw proportional to probs (nn/policy.rs:153-167),
+// then Env::step.
+__global__ void __launch_bounds__(256) k_solve_step(SolveArgs a, const int32_t* __restrict__ live_cur, int32_t* __restrict__ live_next) {
+    const int nl = a.n_live[a.t];
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    bool survives = false;
+    int e = 0;
+    if (pos < nl) {
+        e = live_cur[pos];
+        EnvState s = env_load(a.cells, a.meta, e);
+        const float rew = env_reward(a.env, s);
+        const float tot = a.total[e] + rew;
+        a.total[e] = tot;
+        if (env_is_final(a.env, s)) {
+            a.success[e] = env_success(a.env, s) ? 1 : 0;
+            a.n_steps[e] = a.t;
+        } else {
+            const uint32_t m = env_masks(a.env, s);
+            const float4 raw = a.logits[pos];
+            const float l[4] = {raw.x, raw.y, raw.z, raw.w};
+            float pr[4], sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { pr[i] = (i < a.A && ((m >> i) & 1u)) ? expf(l[i]) : 0.0f; sum += pr[i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pr[i] = pr[i] / (sum + 0.000001f);
+            int act = 0;
+            if (a.deterministic) {
+                float bv = pr[0];
+#pragma unroll
+                for (int i = 1; i < 4; ++i) if (i < a.A && pr[i] > bv) { bv = pr[i]; act = i; }
+            } else {
+                float tw = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (i < a.A) tw += pr[i];
+                if (tw > 0.0f) {                       // WeightedIndex: first i whose cumulative weight exceeds the draw
+                    uint32_t w[4];
+                    philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)a.t, TWR_RNG_SOLVE, a.cid, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w);
+                    const float chosen = u32_to_unit_f32(w[0]) * tw;
+                    float cum = 0.0f;
+                    int last = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (i < a.A && pr[i] > 0.0f) {
+                            cum += pr[i];
+                            last = i;
+                            if (!found && cum > chosen) { act = i; found = true; }
+                        }
+                    }
+                    if (!found) act = last;
+                }
+            }
+            if (a.act_rec) a.act_rec[(int64_t)a.t * a.B + e] = (uint8_t)act;
+            env_step(a.env, s, act);
+            env_store(a.cells, a.meta, e, s);
+            survives = true;
+        }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, survives);
+    if (bal) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&a.n_live[a.t + 1], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (survives) live_next[base + __popc(bal & ((1u << lane) - 1u))] = e;
+    }
+}
+
+void launch_solve_step(cudaStream_t st, const SolveArgs& a, const int32_t* live_cur, int32_t* live_next) {
+    k_solve_step<<<grid_for(a.B, 256), 256, 0, st>>>(a, live_cur, live_next);
+    TWR_COUNT_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) k_envs_broadcast(const uint4* __restrict__ sc, const uint32_t* __restrict__ sm,
+                                                        uint4* __restrict__ cells, uint32_t* __restrict__ meta, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    cells[e] = sc[0];
+    meta[e] = sm[0];
+}
+
+void launch_envs_broadcast(cudaStream_t st, const uint4* sc, const uint32_t* sm, uint4* cells, uint32_t* meta, int64_t n) {
+    if (n <= 0) return;
+    k_envs_broadcast<<<grid_for(n, 256), 256, 0, st>>>(sc, sm, cells, meta, n);
+    TWR_COUNT_LAUNCH();
+}

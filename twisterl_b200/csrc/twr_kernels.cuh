@@ -107,3 +107,13 @@ size_t forward_tc2_pack_bytes(const PolicyDev& p);
 void   launch_forward_tc2_pack(cudaStream_t s, const PolicyDev& p, void* pack);
 int    forward_tc_can_fuse(const PolicyDev& p);   // 1 when launch_forward_tc will run the fusable pair kernel
 bool   launch_forward_tc2(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a, const void* pack);  // false: tensor map unavailable
+
+// f1: batched single_solve step (rust/src/rl/solve.rs:17-71) for every live env
+struct SolveArgs {
+    EnvParams env; uint64_t seed; uint32_t cid; EnvIds ids; int A; int t; int deterministic; int64_t B;
+    uint4* cells; uint32_t* meta; const float4* logits; int32_t* n_live;   // n_live[t], n_live[t+1]
+    float* total; uint8_t* success; uint8_t* act_rec;  // act_rec [T][B] or NULL
+    int32_t* n_steps;   // [B] number of actions taken
+};
+void launch_solve_step(cudaStream_t s, const SolveArgs& a, const int32_t* live_cur, int32_t* live_next);
+void launch_envs_broadcast(cudaStream_t s, const uint4* src_cells, const uint32_t* src_meta, uint4* cells, uint32_t* meta, int64_t n);

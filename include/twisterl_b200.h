@@ -236,6 +236,18 @@ int  twr_evaluate(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, 
 int  twr_solve(twr_engine* e, twr_envs* start, const twr_policy* p, int32_t deterministic, int32_t num_searches,
                float* success, float* reward, int32_t* actions, int32_t max_actions, int32_t* n_actions);
 
+/* AZCollector::collect (rust/src/collector/az.rs:112-130; python_interface/collector.rs:172-188): per record a
+ * batched MCTS (predict_probs_mcts, rust/src/rl/search.rs:104-189) whose leaves are evaluated by the same
+ * forward kernel as the PPO path.  In the result `logits` holds the MCTS visit distribution (what the reference
+ * stores in CollectedData.logits), `rets` holds additional_data["remaining_values"] (az.rs:93), `rewards` and
+ * `actions` the per-record reward / drawn action; `values`, `advs` are zero and `perms` is -1. */
+int  twr_az_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes,
+                    int32_t num_mcts_searches, float C, int32_t max_expand_depth, twr_collected* out);
+/* predict_probs_mcts for every env of `v` at once (parity API): probs / visit counts [n][num_actions].  Env i
+ * draws from Philox stream env_id_base + i at record index t. */
+int  twr_mcts_probs(twr_engine* e, const twr_policy* p, twr_envs* v, int32_t n_sims, float C, int32_t max_expand_depth,
+                    uint32_t env_id_base, uint32_t collect_id, int32_t t, float* probs, int32_t* visits);
+
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for the e2e path */
 int  twr_host_alloc(void** ptr, int64_t bytes);
 void twr_host_free(void* ptr);

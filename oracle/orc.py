@@ -304,6 +304,43 @@ def solve(env: Env, policy: Policy, deterministic, num_searches, seed=0, collect
     return (float(s.value), float(r.value)), acts[: n.value].tolist()
 
 
+class _AzCollected(C.Structure):
+    _fields_ = [("n_records", C.c_int64), ("num_episodes", C.c_int32), ("n_cells", C.c_int32), ("num_actions", C.c_int32),
+                ("ep_len", C.POINTER(C.c_int32)), ("obs", C.POINTER(C.c_int32)), ("probs", C.POINTER(C.c_float)),
+                ("rewards", C.POINTER(C.c_float)), ("actions", C.POINTER(C.c_int32)),
+                ("remaining_values", C.POINTER(C.c_float))]
+
+
+def mcts_probs(env: Env, policy: Policy, n_sims, c_puct, max_expand_depth, seed=0, collect_id=0, stream_id=0, t=0):
+    """(probs, visit counts) of predict_probs_mcts (rl/search.rs:104-189) from the env's current state."""
+    probs = np.zeros(policy.num_actions, dtype=np.float32)
+    visits = np.zeros(policy.num_actions, dtype=np.int32)
+    f = lib().orc_mcts_probs
+    f.argtypes = [C.POINTER(_Env), C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32,
+                  C.c_void_p, C.c_void_p]
+    f(C.byref(env._e), policy._h, int(n_sims), float(c_puct), int(max_expand_depth), int(seed), int(collect_id),
+      int(stream_id), int(t), probs.ctypes.data, visits.ctypes.data)
+    return probs, visits
+
+
+def az_collect(spec: EnvSpec, policy: Policy, num_episodes, n_sims, c_puct, max_expand_depth, seed=0, collect_id=0,
+               env_id_base=0) -> dict:
+    c = _AzCollected()
+    f = lib().orc_az_collect
+    f.argtypes = [C.POINTER(EnvSpec), C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_uint64, C.c_uint32,
+                  C.c_uint32, C.POINTER(_AzCollected)]
+    if f(C.byref(spec), policy._h, int(num_episodes), int(n_sims), float(c_puct), int(max_expand_depth), int(seed),
+         int(collect_id), int(env_id_base), C.byref(c)) != 0:
+        raise RuntimeError("oracle az_collect failed")
+    R, nc, na = c.n_records, c.n_cells, c.num_actions
+    arr = lambda ptr, shape, dt: np.ctypeslib.as_array(ptr, shape=shape).astype(dt, copy=True)
+    out = dict(n_records=int(R), ep_len=arr(c.ep_len, (c.num_episodes,), np.int32), obs=arr(c.obs, (R, nc), np.int32),
+               probs=arr(c.probs, (R, na), np.float32), rewards=arr(c.rewards, (R,), np.float32),
+               actions=arr(c.actions, (R,), np.int32), remaining_values=arr(c.remaining_values, (R,), np.float32))
+    lib().orc_az_collected_free(C.byref(c))
+    return out
+
+
 def evaluate(spec: EnvSpec, policy: Policy, num_episodes, deterministic, num_searches, seed=0, collect_id=0,
              reset_base=0, search_base=0):
     """(success_rate, mean_reward, per-episode best success, per-episode best reward) (rl/evaluate.rs:22-89)."""

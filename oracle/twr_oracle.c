@@ -737,3 +737,192 @@ void orc_evaluate(const orc_env_spec* spec, const orc_policy* p, int32_t num_epi
     *success_rate = succ / (float)num_episodes;
     *mean_reward = rew / (float)num_episodes;
 }
+
+/* ---------------------------------------------------------------- AlphaZero --- */
+
+typedef struct { orc_env state; int action, parent, first_child, n_children; float prior, value_sum; uint32_t visits; } mnode;
+typedef struct { mnode* nodes; int n, cap; } mtree;
+
+static int tree_add(mtree* t, const mnode* nd) {
+    if (t->n == t->cap) { t->cap = t->cap ? t->cap * 2 : 256; t->nodes = (mnode*)realloc(t->nodes, sizeof(mnode) * (size_t)t->cap); }
+    t->nodes[t->n] = *nd;
+    return t->n++;
+}
+
+/* weighted draw like rand's WeightedIndex (nn/policy.rs:153-167): first index whose cumulative weight exceeds
+ * u * total; 0 when every weight is zero (the reference prints an error and returns 0) */
+static int weighted_index(const float* w, int n, float u) {
+    float tw = 0.0f;
+    for (int i = 0; i < n; ++i) tw += w[i];
+    if (!(tw > 0.0f)) return 0;
+    const float chosen = u * tw;
+    float cum = 0.0f;
+    int last = 0;
+    for (int i = 0; i < n; ++i) {
+        if (w[i] > 0.0f) {
+            cum += w[i]; last = i;
+            if (cum > chosen) return i;
+        }
+    }
+    return last;
+}
+
+static void mcts_expand(mtree* t, int idx, const float* priors, int na) {
+    /* search.rs:56-75: one child per action with prior > 0, in action order */
+    t->nodes[idx].first_child = t->n;
+    int cnt = 0;
+    for (int a = 0; a < na; ++a) {
+        if (priors[a] <= 0.0f) continue;
+        mnode c;
+        memset(&c, 0, sizeof(c));
+        c.state = t->nodes[idx].state;
+        orc_env_step(&c.state, a);
+        c.action = a; c.parent = idx; c.prior = priors[a]; c.first_child = -1;
+        tree_add(t, &c);
+        ++cnt;
+    }
+    t->nodes[idx].n_children = cnt;
+}
+
+void orc_mcts_probs(const orc_env* env, const orc_policy* p, int32_t n_sims, float C, int32_t max_expand_depth,
+                    uint64_t seed, uint32_t collect_id, uint32_t stream_id, int32_t t_step, float* probs, int32_t* visits) {
+    /* search.rs:104-189 */
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const int nc = orc_env_num_cells(env), na = orc_env_num_actions(env);
+    const int med = max_expand_depth > 1 ? max_expand_depth : 1;
+    mtree tr = {0, 0, 0};
+    int32_t obs[ORC_MAX_CELLS];
+    uint8_t masks[16];
+    float pr[16], value;
+    mnode root;
+    memset(&root, 0, sizeof(root));
+    root.state = *env; root.action = -1; root.parent = -1; root.visits = 1; root.first_child = -1;
+    tree_add(&tr, &root);
+    orc_env_observe(env, obs); orc_env_masks(env, masks);
+    orc_policy_full_predict(p, obs, nc, masks, pr, &value);
+    mcts_expand(&tr, 0, pr, na);
+    for (int sim = 0; sim < n_sims; ++sim) {
+        int node = 0;
+        while (tr.nodes[node].n_children > 0) {                      /* next(): argmax UCB, strict '>' (search.rs:77-91) */
+            const mnode* par = &tr.nodes[node];
+            int best = -1; float best_ucb = -INFINITY;
+            for (int k = 0; k < par->n_children; ++k) {
+                const mnode* ch = &tr.nodes[par->first_child + k];
+                const float q = ch->visits == 0 ? 0.0f : ch->value_sum / (float)ch->visits;      /* search.rs:29-39 */
+                const float ucb = q + C * (sqrtf((float)par->visits) / ((float)ch->visits + 1.0f)) * ch->prior;
+                if (ucb > best_ucb) { best = par->first_child + k; best_ucb = ucb; }
+            }
+            if (best < 0) break;
+            node = best;
+        }
+        float v = 0.0f;
+        for (int d = 0; d < max_expand_depth; ++d) {
+            const orc_env* st = &tr.nodes[node].state;
+            v = orc_env_reward(st);
+            if (orc_env_is_final(st)) break;
+            float nv;
+            orc_env_observe(st, obs); orc_env_masks(st, masks);
+            orc_policy_full_predict(p, obs, nc, masks, pr, &nv);
+            mcts_expand(&tr, node, pr, na);
+            const uint32_t ctr[4] = {stream_id, (uint32_t)((t_step * (n_sims + 1) + sim) * med + d), ORC_RNG_MCTS, collect_id};
+            uint32_t w[4];
+            orc_philox4x32_10(ctr, key, w);
+            float cp[16];
+            const mnode* par = &tr.nodes[node];
+            for (int k = 0; k < par->n_children; ++k) cp[k] = tr.nodes[par->first_child + k].prior;
+            node = par->first_child + weighted_index(cp, par->n_children, orc_u32_to_unit_f32(w[0]));   /* next_sample */
+            v = nv;
+        }
+        for (int b = node; b >= 0; b = tr.nodes[b].parent) { tr.nodes[b].value_sum += v; tr.nodes[b].visits += 1; }
+    }
+    float sum = 0.0f;
+    for (int a = 0; a < na; ++a) { probs[a] = 0.0f; if (visits) visits[a] = 0; }
+    for (int k = 0; k < tr.nodes[0].n_children; ++k) {
+        const mnode* ch = &tr.nodes[tr.nodes[0].first_child + k];
+        probs[ch->action] = (float)ch->visits;
+        if (visits) visits[ch->action] = (int32_t)ch->visits;
+    }
+    for (int a = 0; a < na; ++a) sum += probs[a];
+    if (sum > 0.0f) { for (int a = 0; a < na; ++a) probs[a] /= sum; }
+    else { for (int a = 0; a < na; ++a) probs[a] = 1.0f / (float)na; }
+    free(tr.nodes);
+}
+
+int orc_az_collect(const orc_env_spec* spec, const orc_policy* p, int32_t num_episodes, int32_t n_sims, float C,
+                   int32_t max_expand_depth, uint64_t seed, uint32_t collect_id, uint32_t env_id_base, orc_az_collected* out) {
+    /* az.rs:51-130 */
+    memset(out, 0, sizeof(*out));
+    if (num_episodes <= 0) return -1;
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    orc_env tmp; orc_env_init(&tmp, spec);
+    const int nc = orc_env_num_cells(&tmp), na = orc_env_num_actions(&tmp);
+    typedef struct { int n; int32_t* obs; float* probs; float* rew; int32_t* act; float* rem; } ep_t;
+    ep_t* eps = (ep_t*)calloc((size_t)num_episodes, sizeof(ep_t));
+    int64_t R = 0;
+    for (int ep = 0; ep < num_episodes; ++ep) {
+        orc_env env; orc_env_init(&env, spec);
+        const uint32_t id = env_id_base + (uint32_t)ep;
+        orc_env_reset(&env, seed, id, collect_id);
+        int cap = 64, n = 0;
+        ep_t* E = &eps[ep];
+        E->obs = (int32_t*)malloc(sizeof(int32_t) * (size_t)cap * nc); E->probs = (float*)malloc(sizeof(float) * (size_t)cap * na);
+        E->rew = (float*)malloc(sizeof(float) * cap); E->act = (int32_t*)malloc(sizeof(int32_t) * cap);
+        float total = 0.0f;
+        float* totals = (float*)malloc(sizeof(float) * cap);
+        for (;;) {
+            if (n == cap) {
+                cap *= 2;
+                E->obs = (int32_t*)realloc(E->obs, sizeof(int32_t) * (size_t)cap * nc); E->probs = (float*)realloc(E->probs, sizeof(float) * (size_t)cap * na);
+                E->rew = (float*)realloc(E->rew, sizeof(float) * cap); E->act = (int32_t*)realloc(E->act, sizeof(int32_t) * cap);
+                totals = (float*)realloc(totals, sizeof(float) * cap);
+            }
+            orc_mcts_probs(&env, p, n_sims, C, max_expand_depth, seed, collect_id, id, n, E->probs + (size_t)n * na, NULL);
+            const uint32_t ctr[4] = {id, (uint32_t)n, ORC_RNG_AZ_ACT, collect_id};
+            uint32_t w[4];
+            orc_philox4x32_10(ctr, key, w);
+            const int action = weighted_index(E->probs + (size_t)n * na, na, orc_u32_to_unit_f32(w[0]));
+            const float val = orc_env_reward(&env);
+            totals[n] = total;
+            total += val;
+            orc_env_observe(&env, E->obs + (size_t)n * nc);
+            E->rew[n] = val; E->act[n] = action;
+            ++n;
+            if (orc_env_is_final(&env)) break;
+            orc_env_step(&env, action);
+        }
+        E->n = n;
+        E->rem = (float*)malloc(sizeof(float) * n);
+        for (int t = 0; t < n; ++t) E->rem[t] = total - totals[t];          /* az.rs:93 */
+        free(totals);
+        R += n;
+    }
+    out->n_records = R; out->num_episodes = num_episodes; out->n_cells = nc; out->num_actions = na;
+    out->ep_len = (int32_t*)malloc(sizeof(int32_t) * (size_t)num_episodes);
+    out->obs = (int32_t*)malloc(sizeof(int32_t) * (size_t)R * nc); out->probs = (float*)malloc(sizeof(float) * (size_t)R * na);
+    out->rewards = (float*)malloc(sizeof(float) * (size_t)R); out->actions = (int32_t*)malloc(sizeof(int32_t) * (size_t)R);
+    out->remaining_values = (float*)malloc(sizeof(float) * (size_t)R);
+    int32_t* order = (int32_t*)malloc(sizeof(int32_t) * (size_t)num_episodes);
+    orc_merge_order(num_episodes, order);
+    int64_t off = 0;
+    for (int s2 = 0; s2 < num_episodes; ++s2) {
+        const ep_t* E = &eps[order[s2]];
+        const size_t n = (size_t)E->n;
+        memcpy(out->obs + off * nc, E->obs, sizeof(int32_t) * n * nc);
+        memcpy(out->probs + off * na, E->probs, sizeof(float) * n * na);
+        memcpy(out->rewards + off, E->rew, sizeof(float) * n);
+        memcpy(out->actions + off, E->act, sizeof(int32_t) * n);
+        memcpy(out->remaining_values + off, E->rem, sizeof(float) * n);
+        off += E->n;
+    }
+    for (int ep = 0; ep < num_episodes; ++ep) {
+        out->ep_len[ep] = eps[ep].n;
+        free(eps[ep].obs); free(eps[ep].probs); free(eps[ep].rew); free(eps[ep].act); free(eps[ep].rem);
+    }
+    free(order); free(eps);
+    return 0;
+}
+
+void orc_az_collected_free(orc_az_collected* c) {
+    free(c->ep_len); free(c->obs); free(c->probs); free(c->rewards); free(c->actions); free(c->remaining_values);
+    memset(c, 0, sizeof(*c));
+}

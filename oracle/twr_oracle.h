@@ -33,7 +33,7 @@ extern "C" {
 enum { ORC_ENV_PUZZLE = 0, ORC_ENV_GRIDWORLD = 1 };
 
 /* RNG stream kinds (counter word 2).  Shared, bit for bit, with the CUDA engine. */
-enum { ORC_RNG_RESET = 0, ORC_RNG_PERM = 1, ORC_RNG_SAMPLE = 2, ORC_RNG_SOLVE = 3 };
+enum { ORC_RNG_RESET = 0, ORC_RNG_PERM = 1, ORC_RNG_SAMPLE = 2, ORC_RNG_SOLVE = 3, ORC_RNG_MCTS = 4, ORC_RNG_AZ_ACT = 5 };
 
 /* Philox4x32-10 (Salmon et al., SC'11).  counter = (env_id, index, kind, collect_id),
  * key = (seed_lo, seed_hi). */
@@ -147,6 +147,21 @@ void orc_solve(const orc_env* env, const orc_policy* p, int32_t deterministic, i
 void orc_evaluate(const orc_env_spec* spec, const orc_policy* p, int32_t num_episodes, int32_t deterministic,
                   int32_t num_searches, uint64_t seed, uint32_t collect_id, uint32_t reset_base, uint32_t search_base,
                   float* success_rate, float* mean_reward, float* best_success, float* best_total);
+
+/* ---- AlphaZero path (rust/src/rl/search.rs, rust/src/rl/tree.rs, rust/src/collector/az.rs) ---- */
+/* predict_probs_mcts (search.rs:104-189) from `env`; the child draw of simulation `sim`, expansion round d uses
+ * Philox (stream_id, (t*(n_sims+1)+sim)*max(1,max_expand_depth)+d, MCTS, collect_id).  visits may be NULL. */
+void orc_mcts_probs(const orc_env* env, const orc_policy* p, int32_t n_sims, float C, int32_t max_expand_depth,
+                    uint64_t seed, uint32_t collect_id, uint32_t stream_id, int32_t t, float* probs, int32_t* visits);
+typedef struct {
+    int64_t n_records; int32_t num_episodes, n_cells, num_actions;
+    int32_t* ep_len; int32_t* obs; float* probs; float* rewards; int32_t* actions; float* remaining_values;
+} orc_az_collected;
+/* AZCollector::collect (az.rs:112-130), merged order; the action draw of step t uses (id, t, AZ_ACT, cid) */
+int  orc_az_collect(const orc_env_spec* spec, const orc_policy* p, int32_t num_episodes, int32_t n_sims, float C,
+                    int32_t max_expand_depth, uint64_t seed, uint32_t collect_id, uint32_t env_id_base,
+                    orc_az_collected* out);
+void orc_az_collected_free(orc_az_collected* c);
 
 #ifdef __cplusplus
 }

@@ -99,7 +99,10 @@ def test_ppo_collector_constructor_keywords():
     with pytest.raises(TypeError):
         tw.collector.PPOCollector(8, 0.9)
     az = tw.collector.AZCollector(num_episodes=4, num_mcts_searches=8, C=1.4, max_expand_depth=2, num_cores=1)
-    with pytest.raises(NotImplementedError):
+    assert (az.num_episodes, az.num_mcts_searches, az.C, az.max_expand_depth, az.num_cores) == (4, 8, 1.4, 2, 1)
+    with pytest.raises(TypeError):                      # AZ_CONFIG's stray "seed" key is rejected like in the reference
+        tw.collector.AZCollector(num_episodes=4, num_mcts_searches=8, C=1.4, max_expand_depth=2, num_cores=1, seed=123)
+    with pytest.raises(TypeError):
         az.collect(None, None)
 
 

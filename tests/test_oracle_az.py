@@ -1,0 +1,55 @@
+"""Pins the oracle's AlphaZero path (rust/src/rl/search.rs, tree.rs, collector/az.rs restated in
+oracle/twr_oracle.c) through properties the reference code guarantees."""
+import numpy as np
+
+from helpers import synth_state_dict, trained15
+from oracle import orc
+
+
+def test_mcts_probs_properties():                     # rl/search.rs:104-189
+    _, sd = trained15()
+    p = orc.Policy.from_torch_state_dict(sd)
+    spec = orc.puzzle_spec(4, 4, 6, 2, 256)
+    env = orc.Env(spec)
+    env.set_state([1, 0, 2, 3] + list(range(4, 16)))   # blank in the top row: action 1 (up) is illegal
+    probs, visits = orc.mcts_probs(env, p, 64, 1.41, 1, seed=1)
+    # one backup per simulation passes through exactly one root child; masked actions get no child
+    assert visits.sum() == 64 and visits[1] == 0
+    assert np.allclose(probs, visits / 64.0) and abs(probs.sum() - 1.0) < 1e-6
+    assert probs.argmax() == 0                         # the solving move (blank left) dominates
+    # zero simulations: no visits -> uniform (search.rs:183-186)
+    p0, v0 = orc.mcts_probs(env, p, 0, 1.41, 1)
+    assert v0.sum() == 0 and np.allclose(p0, 0.25)
+    # max_expand_depth 0: value 0 is backed up from the selected root child, visits still add up
+    p1, v1 = orc.mcts_probs(env, p, 10, 1.41, 0)
+    assert v1.sum() == 10
+    # deterministic given the stream, different streams differ somewhere in general
+    a = orc.mcts_probs(env, p, 200, 1.41, 2, seed=5, stream_id=3)[1]
+    b = orc.mcts_probs(env, p, 200, 1.41, 2, seed=5, stream_id=3)[1]
+    assert (a == b).all() and a.sum() == 200
+
+
+def test_az_collect_structure():                      # collector/az.rs:51-130
+    sd = synth_state_dict(4, 81, 64, 32, 4)
+    p = orc.Policy.from_torch_state_dict(sd)
+    spec = orc.puzzle_spec(3, 3, 3, 2, 256)
+    d = orc.az_collect(spec, p, 9, 12, 1.41, 1, seed=2, collect_id=1)
+    assert d["n_records"] == d["ep_len"].sum() == len(d["remaining_values"])
+    assert np.allclose(d["probs"].sum(axis=1), 1.0, atol=1e-6)
+    order = orc.merge_order(9)
+    off = 0
+    for ep in order:
+        n = int(d["ep_len"][ep])
+        env = orc.Env(spec); env.reset(seed=2, env_id=int(ep), collect_id=1)
+        tot = np.float32(0); prefix = []
+        for t in range(n):
+            assert env.observe() == d["obs"][off + t].tolist()
+            assert np.float32(env.reward()) == d["rewards"][off + t]
+            assert env.is_final() == (t == n - 1)        # terminal state recorded (az.rs:84-86)
+            prefix.append(tot); tot = np.float32(tot + d["rewards"][off + t])
+            masks = env.masks()
+            assert all(d["probs"][off + t][a] == 0 for a in range(4) if not masks[a])
+            env.step(int(d["actions"][off + t]))
+        want = np.array([np.float32(tot - q) for q in prefix], dtype=np.float32)   # az.rs:93
+        assert np.array_equal(want, d["remaining_values"][off:off + n])
+        off += n

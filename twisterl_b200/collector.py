@@ -175,16 +175,36 @@ class PPOCollector(PyBaseCollector):
 
 class AZCollector(PyBaseCollector):
     """`collector.AZCollector(num_episodes, num_mcts_searches, C, max_expand_depth, num_cores)`
-    (python_interface/collector.rs:172-188).  Batched MCTS is SURVEY.md section 8 row a22/a23 -- not built
-    yet; constructing works (the reference trainer does it eagerly), collecting raises."""
+    (python_interface/collector.rs:172-188; AZCollector::collect rust/src/collector/az.rs:112-130): batched MCTS on the
+    device, leaves evaluated by the same forward kernel as the PPO path."""
 
-    def __init__(self, num_episodes, num_mcts_searches, C, max_expand_depth, num_cores):
+    def __init__(self, num_episodes, num_mcts_searches, C, max_expand_depth, num_cores, *, engine=None):
         self.num_episodes, self.num_mcts_searches = int(num_episodes), int(num_mcts_searches)
         self.C, self.max_expand_depth, self.num_cores = float(C), int(max_expand_depth), int(num_cores)
+        self._engine = engine
 
-    def collect(self, env, policy):
-        raise NotImplementedError("AZCollector.collect (batched MCTS on the device) is not implemented yet; "
-                                  "there is no CPU fallback")
+    @property
+    def engine(self) -> _lib.Engine:
+        return self._engine or _lib.default_engine()
+
+    def collect(self, env, policy: Policy) -> CollectedData:
+        if not isinstance(policy, Policy):
+            raise TypeError("argument 'policy': expected twisterl.nn.Policy")
+        spec = spec_from_env(env)
+        eng = self.engine
+        c = _lib.Collected()
+        _lib.check(_lib.load().twr_az_collect(eng._h, C.byref(spec), policy.device_handle(eng), self.num_episodes,
+                                              self.num_mcts_searches, self.C, self.max_expand_depth, C.byref(c)))
+        R = int(c.n_records)
+        hb, arr, holders = _host_buffers(R, c.n_cells, c.num_actions, int(c.num_episodes), False)
+        _lib.check(_lib.load().twr_collected_to_host(eng._h, C.byref(hb)))
+        # az.rs:97-104: obs, probs (in .logits), perms all None; values / rewards / actions stay empty
+        data = CollectedData(arr["obs"], arr["logits"], [], [], [], np.full(R, -1, dtype=np.int8))
+        data.set_additional_data_item("remaining_values", arr["rets"])
+        data.ep_len = arr["ep_len"]
+        data.step_rewards, data.step_actions = arr["rewards"], arr["actions"]    # extras, not part of the reference object
+        data.stats = dict(episodes=int(c.num_episodes), successes=int(c.successes), reward_sum=float(c.reward_sum), records=R)
+        return data
 
 
 def _no_mcts(num_mcts_searches):

@@ -14,7 +14,7 @@
 #define TWR_MAX_CELLS_PUZZLE 16
 #define TWR_MAX_CELLS 32
 
-enum : uint32_t { TWR_RNG_RESET = 0, TWR_RNG_PERM = 1, TWR_RNG_SAMPLE = 2, TWR_RNG_SOLVE = 3 };
+enum : uint32_t { TWR_RNG_RESET = 0, TWR_RNG_PERM = 1, TWR_RNG_SAMPLE = 2, TWR_RNG_SOLVE = 3, TWR_RNG_MCTS = 4, TWR_RNG_AZ_ACT = 5 };
 
 struct EnvParams {
     int kind;  // 0 puzzle, 1 grid_world

@@ -1058,6 +1058,156 @@ int twr_solve(twr_engine* e, twr_envs* start, const twr_policy* p, int32_t deter
     return TWR_OK;
 }
 
+
+// ------------------------------------------------------------- AlphaZero (K6) ---
+struct MctsMem {
+    Staging<uint4> cells; Staging<uint32_t> meta; Staging<int32_t> parent, first_child, n_nodes, fwd_list, fwd_env, fwd_count, cur_node;
+    Staging<uint8_t> n_children, action, active; Staging<float> prior, value_sum, cur_value; Staging<uint32_t> visits;
+    int alloc(int64_t B, int P, MctsPool* pool, MctsArgs* a) {
+        const size_t n = (size_t)B * (size_t)P;
+        int rc;
+        if ((rc = cells.alloc(n)) || (rc = meta.alloc(n)) || (rc = parent.alloc(n)) || (rc = first_child.alloc(n)) ||
+            (rc = n_children.alloc(n)) || (rc = action.alloc(n)) || (rc = prior.alloc(n)) || (rc = visits.alloc(n)) ||
+            (rc = value_sum.alloc(n)) || (rc = n_nodes.alloc((size_t)B)) || (rc = fwd_list.alloc((size_t)B)) ||
+            (rc = fwd_env.alloc((size_t)B)) || (rc = fwd_count.alloc(2)) || (rc = cur_node.alloc((size_t)B)) ||
+            (rc = cur_value.alloc((size_t)B)) || (rc = active.alloc((size_t)B))) return rc;
+        pool->B = B; pool->P = P; pool->cells = cells.d; pool->meta = meta.d; pool->parent = parent.d;
+        pool->first_child = first_child.d; pool->n_children = n_children.d; pool->action = action.d; pool->prior = prior.d;
+        pool->visits = visits.d; pool->value_sum = value_sum.d; pool->n_nodes = n_nodes.d;
+        a->fwd_list = fwd_list.d; a->fwd_env = fwd_env.d; a->fwd_count = fwd_count.d; a->cur_node = cur_node.d;
+        a->cur_value = cur_value.d; a->active = active.d;
+        return TWR_OK;
+    }
+};
+
+static int mcts_pool_nodes(int A, int n_sims, int med) { return 1 + A * (n_sims * (med > 1 ? med : 1) + 1); }
+
+// predict_probs_mcts (rl/search.rs:104-189) for every live env, in lockstep over the simulations
+static void enqueue_mcts(twr_engine* e, const PolicyDev& dev, MctsArgs& a, const int32_t* live, const int32_t* n_live, int64_t B) {
+    cudaStream_t st = e->stream;
+    ForwardArgs fa{};
+    fa.env = a.env; fa.seed = e->seed; fa.cid = a.cid; fa.ids = a.ids; fa.t = -1;
+    fa.cells = a.pool.cells; fa.live = a.fwd_list; fa.n = B;
+    fa.logits = const_cast<float4*>(a.logits); fa.values = const_cast<float*>(a.values);
+    launch_mcts_begin(st, a, live, n_live, B);
+    fa.n_live_ptr = a.fwd_count;
+    launch_forward(e, dev, fa);
+    launch_mcts_expand(st, a, 0, 0, 0, 0, B);
+    int round = 1;
+    for (int sim = 0; sim < a.n_sims; ++sim) {
+        int which = round & 1;
+        launch_mcts_select(st, a, live, n_live, sim, which, B);
+        ++round;
+        for (int d = 0; d < a.max_expand_depth; ++d) {
+            if (d > 0) { which = round & 1; launch_mcts_pre(st, a, live, n_live, which, B); ++round; }
+            fa.n_live_ptr = a.fwd_count + which;
+            launch_forward(e, dev, fa);
+            launch_mcts_expand(st, a, 1, sim, d, which, B);
+        }
+    }
+}
+
+int twr_mcts_probs(twr_engine* e, const twr_policy* p, twr_envs* v, int32_t n_sims, float C, int32_t max_expand_depth,
+                   uint32_t env_id_base, uint32_t collect_id, int32_t t, float* probs, int32_t* visits) {
+    if (!e || !p || !v || !probs || !visits) return fail(TWR_ERR_INVALID, "NULL argument");
+    if (p->eng != e || v->eng != e) return fail(TWR_ERR_INVALID, "policy/envs belong to another engine");
+    if (n_sims < 0 || max_expand_depth < 0 || t < 0) return fail(TWR_ERR_INVALID, "negative argument");
+    if (p->dev.n_perms > 0) return fail(TWR_ERR_UNSUPPORTED, "MCTS with twists (full_predict over all perms) is not implemented; the AZ trainer clears them (rl/az.py:24-26)");
+    if (v->n == 0) return TWR_OK;
+    PolicyDev dev;
+    int rc = check_policy_env(p, v->p, &dev);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(e->device));
+    const int64_t B = v->n;
+    const int P = mcts_pool_nodes(dev.A, n_sims, max_expand_depth);
+    if ((double)B * P >= 2147483647.0) return fail(TWR_ERR_INVALID, "MCTS node pool too large");
+    MctsArgs a{};
+    MctsMem mem;
+    a.pool.A = dev.A;
+    if ((rc = mem.alloc(B, P, &a.pool, &a))) return rc;
+    Staging<float4> logits; Staging<float> values, d_probs; Staging<int32_t> live, n_live, d_vis;
+    if ((rc = logits.alloc((size_t)B)) || (rc = values.alloc((size_t)B)) || (rc = live.alloc((size_t)B)) || (rc = n_live.alloc(1)) ||
+        (rc = d_probs.alloc((size_t)B * dev.A)) || (rc = d_vis.alloc((size_t)B * dev.A))) return rc;
+    std::vector<int32_t> iota((size_t)B);
+    for (int64_t i = 0; i < B; ++i) iota[(size_t)i] = (int32_t)i;
+    const int32_t b32 = (int32_t)B;
+    CU_TRY(cudaMemcpyAsync(live.d, iota.data(), sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, e->stream));
+    CU_TRY(cudaMemcpyAsync(n_live.d, &b32, sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    a.env = v->p; a.seed = e->seed; a.cid = collect_id; a.ids = EnvIds{env_id_base, 0u, 0u, 0u};
+    a.t = t; a.n_sims = n_sims; a.max_expand_depth = max_expand_depth; a.C = C;
+    a.env_cells = v->cells; a.env_meta = v->meta; a.logits = logits.d; a.values = values.d;
+    enqueue_mcts(e, dev, a, live.d, n_live.d, B);
+    launch_mcts_read(e->stream, a, B, d_probs.d, d_vis.d);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(probs, d_probs.d, sizeof(float) * (size_t)B * dev.A, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(visits, d_vis.d, sizeof(int32_t) * (size_t)B * dev.A, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return TWR_OK;
+}
+
+int twr_az_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, int32_t num_mcts_searches,
+                   float C, int32_t max_expand_depth, twr_collected* out) {
+    if (!out) return fail(TWR_ERR_INVALID, "NULL argument");
+    CollectPlan plan;
+    int rc = plan_collect(e, spec, p, num_episodes, &plan);
+    if (rc) return rc;
+    if (num_mcts_searches < 0 || max_expand_depth < 0) return fail(TWR_ERR_INVALID, "negative argument");
+    if (plan.dev.n_perms > 0) return fail(TWR_ERR_UNSUPPORTED, "MCTS with twists (full_predict over all perms) is not implemented; the AZ trainer clears them (rl/az.py:24-26)");
+    CU_TRY(cudaSetDevice(e->device));
+    const int64_t B = num_episodes;
+    const int T = plan.T;
+    const int P = mcts_pool_nodes(plan.dev.A, num_mcts_searches, max_expand_depth);
+    if ((double)B * P >= 2147483647.0) return fail(TWR_ERR_INVALID, "MCTS node pool too large (num_episodes * (1 + A*(n_sims*depth+1)) must be < 2^31)");
+    if ((rc = ensure_collect_buffers(e, B, T, plan.env.N, B))) return rc;
+    MctsArgs a{};
+    MctsMem mem;
+    a.pool.A = plan.dev.A;
+    if ((rc = mem.alloc(B, P, &a.pool, &a))) return rc;
+    CollectBuffers& b = e->buf;
+    cudaStream_t st = e->stream;
+    e->has_last = false;
+    b.B = B;
+    select_outset(e, 0);
+    const uint32_t cid = e->collect_id++;
+    const EnvIds ids{(uint32_t)((int64_t)e->rank * B), (uint32_t)(B - 1), (uint32_t)B, 0u};
+    CU_TRY(cudaMemsetAsync(b.n_live, 0, sizeof(int32_t) * (size_t)(T + 1), st));
+    CU_TRY(cudaMemsetAsync(b.stats, 0, sizeof(unsigned long long) * 4, st));
+    launch_envs_reset(st, plan.env, b.cells, b.meta, B, e->seed, ids, cid, b.live_a, b.n_live);
+    a.env = plan.env; a.seed = e->seed; a.cid = cid; a.ids = ids; a.n_sims = num_mcts_searches;
+    a.max_expand_depth = max_expand_depth; a.C = C;
+    a.env_cells = b.cells; a.env_meta = b.meta; a.logits = b.logits; a.values = b.values;
+    for (int t = 0; t < T; ++t) {
+        int32_t* cur = (t & 1) ? b.live_b : b.live_a;
+        int32_t* nxt = (t & 1) ? b.live_a : b.live_b;
+        a.t = t;
+        enqueue_mcts(e, plan.dev, a, cur, b.n_live + t, B);
+        launch_az_finish(st, a, b, cur, nxt);
+        if ((t & 7) == 7) {                      // stop early once every episode has ended (MCTS steps are expensive)
+            int32_t left = 0;
+            CU_TRY(cudaMemcpyAsync(&left, b.n_live + t + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            if (left == 0) break;
+        }
+    }
+    launch_az_remaining(st, b);
+    launch_episode_offsets(st, b, ids);
+    launch_compact(st, plan.env, b, plan.dev.A);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(e->h_stats, b.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    twr_collected& c = e->last;
+    c.n_records = (int64_t)e->h_stats[1];
+    c.num_episodes = num_episodes;
+    c.n_cells = plan.env.N; c.num_actions = plan.dev.A;
+    c.successes = (int64_t)e->h_stats[0];
+    double rs; memcpy(&rs, &e->h_stats[2], sizeof(double)); c.reward_sum = rs;
+    c.obs = b.out_obs; c.logits = b.out_logits; c.values = b.out_values; c.rewards = b.out_rewards;
+    c.advs = b.out_advs; c.rets = b.out_rets; c.actions = b.out_actions; c.perms = b.out_perms; c.ep_len = e->ep_len_id;
+    e->has_last = true;
+    *out = c;
+    return TWR_OK;
+}
+
 int twr_host_alloc(void** ptr, int64_t bytes) {
     if (!ptr || bytes < 0) return fail(TWR_ERR_INVALID, "bad argument");
     CU_TRY(cudaHostAlloc(ptr, (size_t)(bytes ? bytes : 1), cudaHostAllocDefault));

@@ -117,3 +117,28 @@ struct SolveArgs {
 };
 void launch_solve_step(cudaStream_t s, const SolveArgs& a, const int32_t* live_cur, int32_t* live_next);
 void launch_envs_broadcast(cudaStream_t s, const uint4* src_cells, const uint32_t* src_meta, uint4* cells, uint32_t* meta, int64_t n);
+
+// K6: batched MCTS (twr_mcts.cu)
+struct MctsPool {
+    int64_t B; int P; int A;                   // node (e, i) lives at e*P + i, root at i = 0
+    uint4* cells; uint32_t* meta;              // the node's env (MCTSNode.state)
+    int32_t* parent; int32_t* first_child; uint8_t* n_children; uint8_t* action;
+    float* prior; uint32_t* visits; float* value_sum;
+    int32_t* n_nodes;                          // [B]
+};
+struct MctsArgs {
+    EnvParams env; uint64_t seed; uint32_t cid; EnvIds ids;
+    int t; int n_sims; int max_expand_depth; float C;
+    MctsPool pool;
+    const uint4* env_cells; const uint32_t* env_meta;    // the envs being searched from
+    int32_t* fwd_list; int32_t* fwd_env; int32_t* fwd_count;   // leaf batch: node indices, env ids, two counters
+    const float4* logits; const float* values;           // forward outputs, indexed by leaf-batch position
+    int32_t* cur_node; float* cur_value; uint8_t* active; // per env, current simulation
+};
+void launch_mcts_begin(cudaStream_t s, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int64_t max_n);
+void launch_mcts_expand(cudaStream_t s, const MctsArgs& a, int mode, int sim, int d, int which, int64_t max_n);
+void launch_mcts_select(cudaStream_t s, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int sim, int which, int64_t max_n);
+void launch_mcts_pre(cudaStream_t s, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int which, int64_t max_n);
+void launch_mcts_read(cudaStream_t s, const MctsArgs& a, int64_t n, float* probs, int32_t* visits);
+void launch_az_finish(cudaStream_t s, const MctsArgs& a, const CollectBuffers& b, const int32_t* live, int32_t* live_next);
+void launch_az_remaining(cudaStream_t s, const CollectBuffers& b);

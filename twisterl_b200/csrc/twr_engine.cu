@@ -559,14 +559,15 @@ int twr_debug_forward_profile(twr_engine* e, const twr_policy* p, twr_envs* v, i
     if (rc) return rc;
     CU_TRY(cudaSetDevice(e->device));
     Staging<float4> d_logits; Staging<float> d_values; Staging<long long> d_dbg;
-    if ((rc = d_logits.alloc((size_t)v->n)) || (rc = d_values.alloc((size_t)v->n)) || (rc = d_dbg.alloc((size_t)max_ctas * 16))) return rc;
-    CU_TRY(cudaMemsetAsync(d_dbg.d, 0, sizeof(long long) * (size_t)max_ctas * 16, e->stream));
+    if ((rc = d_logits.alloc((size_t)v->n)) || (rc = d_values.alloc((size_t)v->n)) || (rc = d_dbg.alloc((size_t)148 * 16 + 256))) return rc;
+    if (max_ctas < 148 + 16) return fail(TWR_ERR_INVALID, "counters buffer must hold 148*16 + 256 int64");
+    CU_TRY(cudaMemsetAsync(d_dbg.d, 0, sizeof(long long) * ((size_t)148 * 16 + 256), e->stream));
     ForwardArgs a{};
     a.env = v->p; a.seed = e->seed; a.t = -1; a.cells = v->cells; a.n = v->n;
     a.logits = d_logits.d; a.values = d_values.d; a.dbg = d_dbg.d; a.dbg_flags = flags;
     launch_forward(e, dev, a);
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaMemcpyAsync(counters, d_dbg.d, sizeof(long long) * (size_t)max_ctas * 16, cudaMemcpyDeviceToHost, e->stream));
+    CU_TRY(cudaMemcpyAsync(counters, d_dbg.d, sizeof(long long) * ((size_t)148 * 16 + 256), cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     return TWR_OK;
 }

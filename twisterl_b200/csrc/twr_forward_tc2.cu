@@ -45,7 +45,8 @@ constexpr int SM_B1 = SM_HEADW + 8192;
 constexpr int SM_EMBB = SM_B1 + 1024;
 constexpr int SM_ROWS = SM_EMBB + 4096;
 constexpr int SM_PART = SM_ROWS + TM * MAX_OBS;           // [2][128][8] float: head partial sums of the upper column half
-constexpr int SM_BARS = SM_PART + 2 * TM * 8 * 4;
+constexpr int SM_PERM = SM_PART + 2 * TM * 8 * 4;         // [4][128] int8: twist index of the tiles in flight
+constexpr int SM_BARS = SM_PERM + 4 * TM;
 constexpr int SM_TOTAL = SM_BARS + 512;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
@@ -191,6 +192,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     float* b1s = reinterpret_cast<float*>(smem + SM_B1);
     float* embb = reinterpret_cast<float*>(smem + SM_EMBB);
     float* part_s = reinterpret_cast<float*>(smem + SM_PART);
+    int8_t* perm_s = reinterpret_cast<int8_t*>(smem + SM_PERM);
     uint8_t* rows_s = smem + SM_ROWS;
     const int NC = t.NC, NKB1 = t.NKB1, H = t.H;
 
@@ -224,6 +226,9 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     const uint32_t tmem = *tmem_slot;
     const uint32_t D2_COL = 0, D1_COL = 256;
     const bool timed = a.dbg != nullptr;
+    // event trace of CTA 0 (first 8 items, 32 slots each) behind the per-CTA counters: clock64 stamps
+    long long* trace = (timed && blockIdx.x == 0) ? a.dbg + 148 * 16 : nullptr;
+    auto stamp = [&](int item, int ev) { if (trace && item < 8) trace[item * 32 + ev] = clock64(); };
 
     if (warp == 0) {
         // =============================== TMA producer (both CTAs) ===================
@@ -267,7 +272,9 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             for (int it = 0; it < n_items; ++it) {
                 mbar_wait_cluster_t(bar(B_A1_FULL), it & 1, w_a1, timed);
                 tc_fence_after();
+                stamp(it, 0);
                 auto g1 = [&](int c) {
+                    stamp(it, 1 + c);
                     const uint32_t buf = d1use & 1u;
                     const uint32_t d = tmem + D1_COL + buf * 128u;
                     for (int kb = 0; kb < NKB1; ++kb) {
@@ -293,6 +300,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     mbar_wait_cluster_t(bar(B_A2_FULL0 + buf), (a2use >> 1) & 1u, w_a2, timed);
                     tc_fence_after();
                     if (j == 0) { mbar_wait_cluster_t(bar(B_D2_EMPTY), (it & 1) ^ 1, w_d2, timed); tc_fence_after(); }
+                    stamp(it, 5 + j);
                     const uint32_t a_base = tmem + D1_COL + buf * 128u;
                     const uint32_t d = tmem + D2_COL;
                     for (int kb = 0; kb < 2; ++kb) {
@@ -318,6 +326,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 g1(0);
                 for (int c = 1; c < NC; ++c) { g1(c); g2(c - 1); }
                 g2(NC - 1);
+                stamp(it, 9);
             }
             if (a.dbg) {
                 long long* d = a.dbg + blockIdx.x * 16;
@@ -335,50 +344,82 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         const int n_obs = p.n_obs;
         uint32_t d1use = 0;
         int perm_cur = -1, perm_next = -1;
-        long long w_d1 = 0, w_d2f = 0, w_a1e = 0;
+        long long w_d1 = 0, w_d2f = 0, w_a1e = 0, c_epi1 = 0, c_build = 0, c_epi2 = 0;
         const long long t_begin = clock64();
         const uint32_t l_a1_full = lbar(B_A1_FULL), l_d2_empty = lbar(B_D2_EMPTY);
         const uint32_t l_a2_full0 = lbar(B_A2_FULL0), l_a2_full1 = lbar(B_A2_FULL1);
 
-        auto build_a1 = [&](int it) -> int {
-            mbar_wait_t(bar(B_A1_EMPTY), (it & 1) ^ 1, w_a1e, timed);
-            const int64_t pos = tile_of(it % my_tiles) * TM + row;
+        // Global loads of the env state for item `it`, issued early (at the start of the previous item) so
+        // their latency is off the critical path of the one-hot build.
+        struct Pre { int64_t pos; int64_t e; uint4 c; };
+        auto prefetch = [&](int it) -> Pre {
+            Pre q; q.pos = tile_of(it % my_tiles) * TM + row; q.e = 0; q.c = make_uint4(0, 0, 0, 0);
+            if (q.pos < n) {
+                q.e = a.live ? a.live[q.pos] : q.pos;
+                if (!a.obs_rows) q.c = __ldcg(a.cells + q.e);   // written by the partner thread's fused step >= 1 item earlier
+            }
+            return q;
+        };
+        auto build_a1 = [&](int it, const Pre& q) -> int {
+            const int64_t pos = q.pos;
             const int t_cur = a.t + it / my_tiles;
             int perm = -1;
-            EnvState s; s.lo = 0; s.hi = 0; s.blank = 0; s.depth = 0;
-            int64_t e = 0;
+            EnvState s; s.blank = 0; s.depth = 0;
+            s.lo = (uint64_t)q.c.x | ((uint64_t)q.c.y << 32);
+            s.hi = (uint64_t)q.c.z | ((uint64_t)q.c.w << 32);
             if (pos < n) {
-                e = a.live ? a.live[pos] : pos;
-                if (!a.obs_rows) {
-                    const uint4 c = __ldcg(a.cells + e);     // written by this thread's own fused step one item earlier
-                    s.lo = (uint64_t)c.x | ((uint64_t)c.y << 32);
-                    s.hi = (uint64_t)c.z | ((uint64_t)c.w << 32);
-                }
                 if (a.perm_idx) {
                     perm = a.perm_idx[pos];
                 } else if (p.n_perms > 0 && a.t >= 0) {
                     uint32_t w[4];
-                    philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)t_cur, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
+                    philox4x32_10(a.ids.gid((uint32_t)q.e), (uint32_t)t_cur, TWR_RNG_PERM, a.cid, (uint32_t)a.seed,
                                   (uint32_t)(a.seed >> 32), w);
                     perm = (int)mulhi_u32(w[0], (uint32_t)p.n_perms);
                 }
             }
-            for (int i = 0; i < n_obs; ++i) {
-                const uint32_t old = rows_s[row * MAX_OBS + i];
-                if (old != 0xFF || it > 0)
-                    *reinterpret_cast<__half*>(smem + SM_A1 + (old >> 6) * TILE_BYTES + tile_off(row, old & 63u)) = __ushort_as_half(0);
+            // One-hot row of this env: zero the whole row (NKB1 x 128 B, eight 16-byte stores per k-block, no
+            // bookkeeping of the previous tile's ones), then set one fp16 1.0 per observation index.
+            const uint32_t rx = (uint32_t)row & 7u;
+            const uint32_t row_base = ((uint32_t)row >> 3) * 1024u + rx * 128u;
+            const bool fast = a.env.kind == 0 && !a.obs_rows && perm < 0 && n_obs <= 16;   // Puzzle, no twist
+            if (threadIdx.x == 192) stamp(it, 20);
+            mbar_wait_t(bar(B_A1_EMPTY), (it & 1) ^ 1, w_a1e, timed);      // GEMM1 of the previous item is done with A1
+            if (threadIdx.x == 192) stamp(it, 21);
+            // the 32 rows of this warp are 4 KB contiguous per k-block: lanes write consecutive 16-byte chunks
+            // (conflict-free), then the warp syncs before anyone sets a one in a row another lane zeroed
+            for (int kb = 0; kb < NKB1; ++kb) {
+                uint4* dst = reinterpret_cast<uint4*>(smem + SM_A1 + kb * TILE_BYTES + quarter * 4096) + lane;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j * 32] = make_uint4(0, 0, 0, 0);
             }
-            for (int i = 0; i < n_obs; ++i) {
-                int r = 0;
-                if (pos < n) {
-                    r = a.obs_rows ? a.obs_rows[pos * n_obs + i] : i * a.env.N + (int)env_board(a.env, s, i);
-                    if (perm >= 0) r = p.obs_perms[(size_t)perm * p.obs_size + r];
+            __syncwarp();
+            if (fast) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (i < n_obs) {
+                        const uint32_t v = (uint32_t)(((i < 8) ? s.lo : s.hi) >> (8 * (i & 7))) & 0xFFu;
+                        const uint32_t r = pos < n ? (uint32_t)(i * a.env.N) + v : 0u;
+                        const uint32_t k = r & 63u;
+                        *reinterpret_cast<__half*>(smem + SM_A1 + (r >> 6) * TILE_BYTES + row_base + ((((k >> 3) ^ rx) & 7u) << 4) + (k & 7u) * 2u) =
+                            __ushort_as_half(0x3C00);
+                    }
                 }
-                rows_s[row * MAX_OBS + i] = (uint8_t)r;
-                *reinterpret_cast<__half*>(smem + SM_A1 + (r >> 6) * TILE_BYTES + tile_off(row, (uint32_t)r & 63u)) = __ushort_as_half(0x3C00);
+            } else {
+                for (int i = 0; i < n_obs; ++i) {
+                    uint32_t r = 0;
+                    if (pos < n) {
+                        r = a.obs_rows ? (uint32_t)a.obs_rows[pos * n_obs + i] : (uint32_t)(i * a.env.N) + env_board(a.env, s, i);
+                        if (perm >= 0) r = (uint32_t)p.obs_perms[(size_t)perm * p.obs_size + r];   // twist-in, policy.rs:81-83
+                    }
+                    const uint32_t k = r & 63u;
+                    *reinterpret_cast<__half*>(smem + SM_A1 + (r >> 6) * TILE_BYTES + row_base + ((((k >> 3) ^ rx) & 7u) << 4) + (k & 7u) * 2u) =
+                        __ushort_as_half(0x3C00);
+                }
             }
+            perm_s[(it & 3) * TM + row] = (int8_t)perm;
             fence_async_smem();
             mbar_arrive_cluster(l_a1_full);
+            if (threadIdx.x == 192) stamp(it, 22);
             return perm;
         };
         // relu(x + bias) -> packed fp16 hi pair / lo pair (x = hi + lo to ~22 bits)
@@ -395,14 +436,22 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         // them); with a single tile per pair the next item is the same envs one step later, whose state
         // only exists after this item's fused env step
         const bool build_early = my_tiles > 1 || t_count == 1;
-        if (chalf == 0) perm_next = build_a1(0);
+        if (chalf == 1) perm_next = build_a1(0, prefetch(0));          // the upper-half warps own the one-hot operand
         for (int it = 0; it < n_items; ++it) {
-            perm_cur = perm_next;
+            Pre pre_next; pre_next.pos = 0; pre_next.e = 0; pre_next.c = make_uint4(0, 0, 0, 0);
+            if (build_early && chalf == 1 && it + 1 < n_items) {
+                // with >= 2 tiles per pair, item it+1's env state was last written by the fused step of item
+                // it+1-my_tiles <= it-1 (lower-half threads); barrier 3 orders that step before these loads
+                if (t_count > 1 && it >= 1) asm volatile("bar.sync 3, %0;" ::"n"(NEPI) : "memory");
+                pre_next = prefetch(it + 1);
+            }
             // ---- epilogue 1: this thread's 64 columns of the D1 chunk, rewritten in place as the fp16 A operand
             for (int c = 0; c < NC; ++c) {
                 const uint32_t buf = d1use & 1u;
                 mbar_wait_t(bar(B_D1_FULL0 + buf), (d1use >> 1) & 1u, w_d1, timed);
                 tc_fence_after();
+                if (threadIdx.x == 64) stamp(it, 10 + c);
+                const long long t_e1 = timed ? clock64() : 0;
                 if (!(a.dbg_flags & 1)) {
                     uint32_t v0[32], v1[32];
                     const uint32_t taddr = tmem + lane_addr + D1_COL + buf * 128u + (uint32_t)chalf * 64u;
@@ -423,14 +472,22 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 }
                 tc_fence_before();
                 mbar_arrive_cluster(buf ? l_a2_full1 : l_a2_full0);
+                if (timed) c_epi1 += clock64() - t_e1;
+                if (threadIdx.x == 64) stamp(it, 14 + c);
                 ++d1use;
             }
             // ---- next tile's one-hot operand, so its GEMM1 overlaps this tile's heads
-            if (build_early && chalf == 0 && it + 1 < n_items) perm_next = build_a1(it + 1);
+            {
+                const long long t_b = timed ? clock64() : 0;
+                if (build_early && chalf == 1 && it + 1 < n_items) perm_next = build_a1(it + 1, pre_next);
+                if (timed) c_build += clock64() - t_b;
+            }
 
             // ---- epilogue 2: heads on CUDA cores; each thread reduces its 128 columns of the accumulator row
             mbar_wait_t(bar(B_D2_FULL), it & 1, w_d2f, timed);
             tc_fence_after();
+            if (threadIdx.x == 64) stamp(it, 18);
+            const long long t_e2 = timed ? clock64() : 0;
             float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int q = 0; q < 2; ++q) {
@@ -464,6 +521,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 const bool active = pos < n;
                 float out[4] = {0.f, 0.f, 0.f, 0.f};
                 float value = 0.f;
+                perm_cur = perm_s[(it & 3) * TM + row];             // written by the partner thread when it built this tile
                 if (active) {
                     const float4 o4 = *reinterpret_cast<const float4*>(ps);
                     acc[0] += o4.x; acc[1] += o4.y; acc[2] += o4.z; acc[3] += o4.w; acc[4] += ps[4];
@@ -495,12 +553,19 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     a.logits[pos] = make_float4(out[0], out[1], out[2], out[3]);
                     a.values[pos] = value;
                 }
-                if (!build_early && it + 1 < n_items) perm_next = build_a1(it + 1);
+                // publish "step of item `it` done" to the upper-half threads (matched by their bar.sync 3 at item it+1)
+                if (build_early && t_count > 1 && it + 2 < n_items) asm volatile("bar.arrive 3, %0;" ::"n"(NEPI) : "memory");
             }
+            if (!build_early && it + 1 < n_items) {                    // single tile per pair: the next item is these envs one step later
+                asm volatile("bar.sync 2, %0;" ::"n"(NEPI) : "memory");  // their fused env step (lower-half threads) is done
+                if (chalf == 1) perm_next = build_a1(it + 1, prefetch(it + 1));
+            }
+            if (timed) c_epi2 += clock64() - t_e2;
+            if (threadIdx.x == 64) stamp(it, 19);
         }
         if (a.dbg && threadIdx.x == 64) {
             long long* d = a.dbg + blockIdx.x * 16;
-            d[9] = clock64() - t_begin; d[10] = w_d1; d[11] = w_d2f; d[12] = w_a1e;
+            d[9] = clock64() - t_begin; d[10] = w_d1; d[11] = w_d2f; d[12] = w_a1e; d[13] = c_epi1; d[14] = c_build; d[15] = c_epi2;
         }
     }
 

@@ -8,8 +8,8 @@
 // ingest rate, measured with the pipeline wait counters).
 //
 //   CTA 0 (leader): warp 1 issues all MMAs; its mbarriers collect the arrivals of both CTAs
-//   CTA 1 (peer)  : warp 1 relays "my half of ring slot s has landed" to the leader; epilogue warps
-//                   arrive remotely (mapa + mbarrier.arrive.release.cluster) on the leader's barriers
+//   CTA 1 (peer)  : its TMA loads credit the leader's `full` barrier (2-SM TMA); epilogue warps
+//                   arrive remotely (mapa + mbarrier.arrive on the shared::cluster address) on the leader's barriers
 //   both          : warp 0 streams this CTA's half tiles with cp.async.bulk into its own ring;
 //                   warps 2..5 are the epilogue of this CTA's 128 envs; tcgen05.commit.cta_group::2
 //                   (multicast) publishes accumulators / frees ring slots in both CTAs.
@@ -36,6 +36,7 @@ constexpr int HALF_BYTES = 8192;
 constexpr int NSLOTS = 8;
 constexpr int MAX_KB1 = 4;
 constexpr int MAX_OBS = 32;
+constexpr int NCOPIES = 1;              // replicas of the operand image (8 copies measured: no gain -- the bound is per-SM ingest, not L2 slices)
 
 constexpr int SM_A1 = 0;
 constexpr int SM_RING = SM_A1 + MAX_KB1 * TILE_BYTES;
@@ -74,14 +75,17 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");   // default .release.cta like cutlass ClusterBarrier::arrive
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {   // acquire at cluster scope
+// Waits on barriers that also collect remote arrivals.  Default (.acquire.cta) semantics like cutlass
+// ClusterBarrier::wait: a cluster-scope acquire costs a CCTL.IVALL (L1 invalidate, ~400+ cycles) per wait, and no
+// generic-proxy data crosses CTAs here -- operands travel through TMEM / the async proxy.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     for (uint32_t spins = 0; !done; ++spins) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (!done && spins > (1u << 22)) __trap();
@@ -93,15 +97,6 @@ __device__ __forceinline__ void mbar_wait_cluster_t(uint32_t bar, uint32_t parit
     mbar_wait_cluster(bar, parity);
     acc += clock64() - t0;
 }
-// peer -> leader progress word (monotonic count of ring-slot uses whose peer half has landed)
-__device__ __forceinline__ void st_release_cluster(uint32_t cluster_addr, uint32_t v) {
-    asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_cluster(uint32_t cta_addr) {
-    uint32_t v;
-    asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(cta_addr) : "memory");
-    return v;
-}
 __device__ __forceinline__ void tc2_commit(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -111,6 +106,22 @@ __device__ __forceinline__ void tc2_mma(uint32_t d_tmem, uint64_t a_desc, uint64
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// A-operand reuse: `fill` keeps the A tile in the tensor core's collector buffer, `lastuse` consumes it without
+// re-reading shared memory (GEMM1 multiplies the same one-hot A by the hi and the lo half of the table)
+__device__ __forceinline__ void tc2_mma_fill(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc2_mma_lastuse(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc2_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -161,7 +172,8 @@ __global__ void __launch_bounds__(256) k_tc2_pack(PolicyDev p, Tc2Params t, __ha
         }
         const __half hi = __float2half_rn(x);
         const __half v = lo_part ? __float2half_rn(x - __half2float(hi)) : hi;
-        *reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(pack) + gslot * TILE_BYTES + off) = v;
+        for (int cp = 0; cp < NCOPIES; ++cp)
+            *reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(pack) + ((size_t)cp * 2 * spr + gslot) * TILE_BYTES + off) = v;
     }
 }
 
@@ -235,7 +247,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         // Each CTA fetches ITS half of every operand tile into its own ring; both halves credit the
         // leader's `full` barrier, so the MMA issuer waits on one local barrier per ring slot.
         if (lane == 0) {
-            const int img_row0 = crank * (int)slots_per_rank(t) * (TILE_BYTES / 128);   // tensor-map row of this rank's image
+            const int img_row0 = ((pair_id % NCOPIES) * 2 + crank) * (int)slots_per_rank(t) * (TILE_BYTES / 128);   // tensor-map row of this pair's copy, this rank's image
             const int g1_row0 = img_row0, g2_row0 = img_row0 + (int)slots_g1(t) * (TILE_BYTES / 128);
             uint32_t use = 0;
             long long w_empty = 0;
@@ -285,8 +297,8 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                         if (!(a.dbg_flags & 8)) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                tc2_mma(d, ad + 2u * ks, bh + 2u * ks, IDESC_256x128, (kb | ks) != 0);
-                                tc2_mma(d, ad + 2u * ks, bl + 2u * ks, IDESC_256x128, 1u);
+                                tc2_mma_fill(d, ad + 2u * ks, bh + 2u * ks, IDESC_256x128, (kb | ks) != 0);
+                                tc2_mma_lastuse(d, ad + 2u * ks, bl + 2u * ks, IDESC_256x128, 1u);
                             }
                         }
                         tc2_commit(bar(B_EMPTY0 + slot));
@@ -619,7 +631,7 @@ int forward_tc2_supported(const PolicyDev& p) { return p.H == 256; }
 
 size_t forward_tc2_pack_bytes(const PolicyDev& p) {
     if (!forward_tc2_supported(p)) return 0;
-    return 2 * slots_per_rank(make_params2(p)) * TILE_BYTES;
+    return (size_t)NCOPIES * 2 * slots_per_rank(make_params2(p)) * TILE_BYTES;
 }
 
 void launch_forward_tc2_pack(cudaStream_t st, const PolicyDev& p, void* pack) {

@@ -153,10 +153,16 @@ def run_ours(args, rank, local_rank, world):
                     stream=stream.cuda_stream)
 
     sd = synth_weights()
+    obs_perms, act_perms = ([], [])
+    if args.twists:      # {identity, main-diagonal transpose} twist set of SURVEY.md section 8a row T (BASELINE config 5)
+        T = [(i % 4) * 4 + (i // 4) for i in range(16)]
+        obs_perms = [list(range(256)), [T[i] * 16 + T[v] for i in range(16) for v in range(16)]]
+        act_perms = [[0, 1, 2, 3], [1, 0, 3, 2]]
     pol = twn.Policy(twn.EmbeddingBag(sd["embeddings.weight"].T, sd["embeddings.bias"], True, [256], 0),
                      twn.Sequential([twn.Linear(sd["common.0.weight"].T.flatten(), sd["common.0.bias"], True)]),
                      twn.Sequential([twn.Linear(sd["action.0.weight"].T.flatten(), sd["action.0.bias"], False)]),
-                     twn.Sequential([twn.Linear(sd["value.0.weight"].T.flatten(), sd["value.0.bias"], False)]), [], [])
+                     twn.Sequential([twn.Linear(sd["value.0.weight"].T.flatten(), sd["value.0.bias"], False)]),
+                     obs_perms, act_perms)
     env = tw.env.Puzzle(4, 4, args.difficulty, 2, 256)
     col = twc.PPOCollector(args.episodes, 0.995, 0.995, 32, engine=eng)
     hpol = pol.device_handle(eng)
@@ -256,7 +262,7 @@ def run_ours(args, rank, local_rank, world):
                                    f"difficulty {args.difficulty}, depth budget {2 * args.difficulty}, synthetic N(0,0.05^2) weights",
                        "episodes_per_gpu": args.episodes, "records_per_step": records / args.steps,
                        "l2": "working set per step (records + compacted output, > 1.5 GB at 65536 envs) exceeds the 126 MB L2; no flush needed",
-                       "precision": args.precision},
+                       "precision": args.precision, "twists": bool(args.twists)},
             "clocks": clocks,
             "e2e": {"value": e2e_records / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "twr_ppo_collect_host (pinned host buffers)"},
@@ -300,6 +306,7 @@ def main():
     ap.add_argument("--difficulty", type=int, default=128)
     ap.add_argument("--ref-episodes", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--twists", action="store_true", help="enable the {identity, transpose} twist set (BASELINE config 5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

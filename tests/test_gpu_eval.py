@@ -102,3 +102,28 @@ def test_solve_matches_oracle_and_replays(eng):
     assert s8 in (0.0, 1.0) and len(a8) <= 256
     if s8 == 0.0:
         assert len(a8) == 256 and abs(r8 - (255 * (-0.5 / 256) + (-0.5 / 256) + -0.5)) < 1e-3
+
+
+def test_collect_torch_device_handoff(eng):
+    """f2: torch CUDA tensors aliasing the engine's output must equal the host copy of the same collect."""
+    torch = pytest.importorskip("torch")
+    import twisterl_b200 as tw
+    from parity import make_policies
+    _, sd = trained15()
+    pol, _ = make_policies(sd, 256)
+    env = tw.env.Puzzle(4, 4, 8, 2, 256)
+    col = tw.collector.PPOCollector(300, 0.995, 0.995, 1, engine=eng)
+    eng.set_collect_id(4)
+    ref = col.collect(env, pol)
+    eng.set_collect_id(4)
+    t = col.collect_torch(env, pol)
+    assert t["obs"].is_cuda and t["obs"].shape == (len(ref.values_array), 256)
+    dense = np.zeros((len(ref.values_array), 256), np.float32)
+    np.put_along_axis(dense, ref.obs_array.astype(np.int64), 1.0, axis=1)
+    assert np.array_equal(t["obs"].cpu().numpy(), dense)
+    assert np.array_equal(t["logits"].cpu().numpy(), ref.logits_array)
+    assert np.array_equal(t["actions"].cpu().numpy(), ref.actions_array.astype(np.int64))
+    assert np.array_equal(t["advs"].cpu().numpy(), ref.additional_array("advs"))
+    assert np.array_equal(t["rets"].cpu().numpy(), ref.additional_array("rets"))
+    assert np.array_equal(t["perms"].cpu().numpy(), ref.perms_array.astype(np.int64))
+    assert t["stats"]["records"] == len(ref.values_array)

@@ -155,6 +155,35 @@ class PPOCollector(PyBaseCollector):
                                                self.gamma, self.lambda_, C.byref(out)))
         return out
 
+    def collect_torch(self, env, policy: Policy, dense_obs: bool = True):
+        """Device hand-off for a GPU trainer: run the collect and return torch CUDA tensors that
+        alias the engine's output buffers (valid until the next collect on this engine) -- what
+        `PPO.data_to_torch` (src/twisterl/rl/ppo.py:25-61) builds through Python lists and an H2D copy.
+        Keys: obs (dense one-hot float [R, obs_size] or int64 indices [R, cells]), logits, actions, advs, rets, perms,
+        values, rewards."""
+        import torch
+        c = self.collect_device(env, policy)
+        R, N, A = int(c.n_records), int(c.n_cells), int(c.num_actions)
+        dev = torch.device("cuda", self.engine.device)
+
+        def view(ptr, shape, typestr):
+            class _H:
+                __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
+            return torch.as_tensor(_H(), device=dev)
+
+        idx = view(c.obs, (R, N), "<u2").to(torch.int64)
+        out = {"logits": view(c.logits, (R, A), "<f4"), "values": view(c.values, (R,), "<f4"),
+               "rewards": view(c.rewards, (R,), "<f4"), "advs": view(c.advs, (R,), "<f4"), "rets": view(c.rets, (R,), "<f4"),
+               "actions": view(c.actions, (R,), "|u1").to(torch.int64), "perms": view(c.perms, (R,), "|i1").to(torch.int64)}
+        if dense_obs:
+            obs = torch.zeros((R, N * N), dtype=torch.float32, device=dev)
+            obs.scatter_(1, idx, 1.0)
+            out["obs"] = obs
+        else:
+            out["obs"] = idx
+        out["stats"] = dict(episodes=int(c.num_episodes), successes=int(c.successes), reward_sum=float(c.reward_sum), records=R)
+        return out
+
     def collect(self, env, policy: Policy) -> CollectedData:
         if not isinstance(policy, Policy):
             raise TypeError("argument 'policy': expected twisterl.nn.Policy")

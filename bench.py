@@ -221,7 +221,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- e2e: the C-ABI call with HOST buffers (weights H2D, CollectedData D2H inside the timed region)
     cap = int(L.twr_max_records(C.byref(tw.env.spec_from_env(env)), args.episodes))
-    hb, arrs, holders = twc._host_buffers(cap, 16, 4, args.episodes, pinned=True)
+    hb, arrs, holders = twc._host_buffers(cap, 16, 4, args.episodes, pinned=True, obs_u8=True)   # obs as u8 indices (obs_size 256)
     desc = pol.desc()
     spec = tw.env.spec_from_env(env)
     out = _lib.Collected()
@@ -244,7 +244,8 @@ def run_ours(args, rank, local_rank, world):
         sm = e2e.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         e2e_s, e2e_records = float(mx[0]), float(sm[1])
     rec_per_step = e2e_records / e2e_steps / world
-    d2h = int(rec_per_step * (16 * 2 + 4 * 4 + 4 * 4 + 1 + 1) + args.episodes * 4)
+    d2h = int(rec_per_step * sum(a.dtype.itemsize * int(np.prod(a.shape[1:])) for k, a in arrs.items() if k != "ep_len")
+              + arrs["ep_len"].nbytes)
     h2d = nblob * 4
 
     if rank == 0:

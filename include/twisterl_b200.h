@@ -212,6 +212,9 @@ typedef struct {
     uint8_t*  actions;
     int8_t*   perms;
     int32_t*  ep_len;       /* [num_episodes] or NULL */
+    uint8_t*  obs_u8;       /* alternative to `obs` for envs with obs_size <= 256 (both puzzles): the same indices,
+                             * one byte each -- halves the largest D2H stream of twr_ppo_collect_host.  Used when
+                             * `obs` is NULL; the binding widens to usize either way (CollectedData.obs is Vec<Vec<usize>>) */
 } twr_host_buffers;
 
 /* D2H of the last collect into caller buffers (any field may be NULL to skip it) */

@@ -436,9 +436,14 @@ def test_collect_host_pipelined_matches_plain(eng, monkeypatch):
     L = _lib.load()
     spec = tw.env.spec_from_env(env)
     cap = int(L.twr_max_records(C.byref(spec), E))
-    for split in ("3", "7"):
-        monkeypatch.setenv("TWISTERL_B200_E2E_SPLIT", split)
-        hb, arr, _ = twc._host_buffers(cap, 16, 4, E, pinned=True)
+    for split, parts, u8 in (("3", None, False), ("7", None, True), ("1", None, True), (None, "600,300,100", True)):
+        monkeypatch.delenv("TWISTERL_B200_E2E_SPLIT", raising=False)
+        monkeypatch.delenv("TWISTERL_B200_E2E_PARTS", raising=False)
+        if split:
+            monkeypatch.setenv("TWISTERL_B200_E2E_SPLIT", split)
+        if parts:
+            monkeypatch.setenv("TWISTERL_B200_E2E_PARTS", parts)     # unequal sub-batches
+        hb, arr, _ = twc._host_buffers(cap, 16, 4, E, pinned=True, obs_u8=u8)   # u8: one-byte observation indices
         out = _lib.Collected()
         eng.set_collect_id(21)
         _lib.check(L.twr_ppo_collect_host(eng._h, C.byref(spec), pol.device_handle(eng), None, E, 0.995, 0.995,

@@ -59,7 +59,7 @@ class Collected(C.Structure):
 class HostBuffers(C.Structure):
     _fields_ = [("capacity", C.c_int64), ("obs", C.c_void_p), ("logits", C.c_void_p), ("values", C.c_void_p),
                 ("rewards", C.c_void_p), ("advs", C.c_void_p), ("rets", C.c_void_p), ("actions", C.c_void_p),
-                ("perms", C.c_void_p), ("ep_len", C.c_void_p)]
+                ("perms", C.c_void_p), ("ep_len", C.c_void_p), ("obs_u8", C.c_void_p)]
 
 
 # every symbol include/twisterl_b200.h declares (tests check the library exports all of them)

@@ -88,9 +88,11 @@ class CollectedData:
             self._additional[k] = cat(self._additional[k], v) if k in self._additional else v
 
 
-def _host_buffers(cap: int, n_cells: int, n_actions: int, num_episodes: int, pinned: bool):
+def _host_buffers(cap: int, n_cells: int, n_actions: int, num_episodes: int, pinned: bool, obs_u8: bool = False):
+    """Caller-owned host buffers of one collect.  `obs_u8` asks twr_ppo_collect_host for one-byte observation
+    indices (obs_size <= 256) through twr_host_buffers.obs_u8 instead of the u16 `obs` field."""
     mk = (lambda shape, dt: _lib.PinnedArray(shape, dt)) if pinned else None
-    fields = dict(obs=((cap, n_cells), np.uint16), logits=((cap, n_actions), np.float32), values=((cap,), np.float32),
+    fields = dict(obs=((cap, n_cells), np.uint8 if obs_u8 else np.uint16), logits=((cap, n_actions), np.float32), values=((cap,), np.float32),
                   rewards=((cap,), np.float32), advs=((cap,), np.float32), rets=((cap,), np.float32),
                   actions=((cap,), np.uint8), perms=((cap,), np.int8), ep_len=((num_episodes,), np.int32))
     holders, arrays = {}, {}
@@ -100,8 +102,10 @@ def _host_buffers(cap: int, n_cells: int, n_actions: int, num_episodes: int, pin
             arrays[k] = holders[k].array
         else:
             arrays[k] = np.empty(shape, dtype=dt)
-    hb = _lib.HostBuffers(cap, *[C.c_void_p(arrays[k].ctypes.data) for k in
-                                 ("obs", "logits", "values", "rewards", "advs", "rets", "actions", "perms", "ep_len")])
+    ptr = {k: C.c_void_p(arrays[k].ctypes.data) for k in arrays}
+    hb = _lib.HostBuffers(cap, None if obs_u8 else ptr["obs"], *[ptr[k] for k in
+                          ("logits", "values", "rewards", "advs", "rets", "actions", "perms", "ep_len")],
+                          ptr["obs"] if obs_u8 else None)
     return hb, arrays, holders
 
 

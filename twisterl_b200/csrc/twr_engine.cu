@@ -817,6 +817,7 @@ int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p
     if ((rc = ensure_collect_buffers(e, num_episodes, plan.T, plan.env.N, num_episodes))) return rc;
     cudaStream_t st = e->stream;
     e->has_last = false;
+    e->buf.obs_u8 = 0;
     const uint32_t cid = e->collect_id++;
     // local episode 0 is the LAST episode id, local i is episode i-1: local order == merge order
     const EnvIds ids{(uint32_t)((int64_t)e->rank * num_episodes), (uint32_t)(num_episodes - 1), (uint32_t)num_episodes};
@@ -847,6 +848,7 @@ int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p
 static int copy_out(twr_engine* e, cudaStream_t st, const twr_host_buffers* dst, int64_t at, size_t R, int n_cells, int A) {
     const CollectBuffers& b = e->buf;
     if (dst->obs) CU_TRY(cudaMemcpyAsync(dst->obs + at * n_cells, b.out_obs, sizeof(uint16_t) * R * n_cells, cudaMemcpyDeviceToHost, st));
+    else if (dst->obs_u8) CU_TRY(cudaMemcpyAsync(dst->obs_u8 + at * n_cells, b.out_obs, R * n_cells, cudaMemcpyDeviceToHost, st));
     if (dst->logits) CU_TRY(cudaMemcpyAsync(dst->logits + at * A, b.out_logits, sizeof(float) * R * A, cudaMemcpyDeviceToHost, st));
     if (dst->values) CU_TRY(cudaMemcpyAsync(dst->values + at, b.out_values, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
     if (dst->rewards) CU_TRY(cudaMemcpyAsync(dst->rewards + at, b.out_rewards, sizeof(float) * R, cudaMemcpyDeviceToHost, st));
@@ -863,6 +865,8 @@ int twr_collected_to_host(twr_engine* e, const twr_host_buffers* dst) {
     const twr_collected& c = e->last;
     const size_t R = (size_t)c.n_records;
     if ((int64_t)R > dst->capacity) return fail(TWR_ERR_INVALID, "host buffers too small for the collected records");
+    if (!dst->obs && dst->obs_u8)
+        return fail(TWR_ERR_UNSUPPORTED, "obs_u8 is produced by twr_ppo_collect_host only (the device-resident result holds u16 indices)");
     CU_TRY(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
     int rc = copy_out(e, st, dst, 0, R, c.n_cells, c.num_actions);
@@ -879,47 +883,73 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
     if (!e || !p || !dst || !out) return fail(TWR_ERR_INVALID, "NULL argument");
     int rc;
     if (desc && (rc = twr_policy_update(p, desc))) return rc;
-    int split = num_episodes >= 32768 ? 2 : 1;
-    if (const char* sp = getenv("TWISTERL_B200_E2E_SPLIT")) { const int v = atoi(sp); if (v >= 1 && v <= 64) split = v; }
-    if (split > num_episodes) split = (int)num_episodes;
-    if (split == 1) {
+    CollectPlan plan;
+    if ((rc = plan_collect(e, spec, p, num_episodes, &plan))) return rc;
+    const bool u8 = !dst->obs && dst->obs_u8;
+    if (u8 && plan.dev.obs_size > 256) return fail(TWR_ERR_INVALID, "obs_u8 needs obs_size <= 256");
+    CU_TRY(cudaSetDevice(e->device));
+    // Sub-batch sizes.  The rollout kernel works in rounds of (#SM pairs x 256) envs, so the first sub-batch is a whole
+    // number of rounds (at least half of the episodes) and the remainder -- whose copy is the exposed tail -- is smaller.
+    std::vector<int64_t> parts;
+    if (const char* ps = getenv("TWISTERL_B200_E2E_PARTS")) {         // explicit sizes "a,b,c" (must sum to num_episodes)
+        int64_t sum = 0;
+        for (const char* q = ps; *q;) { char* end; const long long v = strtoll(q, &end, 10); if (end == q || v <= 0) break; parts.push_back(v); sum += v; q = *end ? end + 1 : end; }
+        if (sum != num_episodes) parts.clear();
+    }
+    if (parts.empty()) {
+        int split = num_episodes >= 32768 ? 2 : 1;
+        if (const char* sp = getenv("TWISTERL_B200_E2E_SPLIT")) { const int v = atoi(sp); if (v >= 1 && v <= 64) split = v; }
+        if (split > num_episodes) split = (int)num_episodes;
+        int sms = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+        const int64_t round = (int64_t)(sms / 2) * 256;
+        if (split == 2 && e->precision == TWR_PREC_F16X2 && round > 0 && !getenv("TWISTERL_B200_E2E_SPLIT")) {
+            const int64_t first = ((num_episodes / 2 + round - 1) / round) * round;
+            if (first < num_episodes) { parts.push_back(first); parts.push_back(num_episodes - first); }
+        }
+        if (parts.empty()) {
+            const int64_t Bsub = (num_episodes + split - 1) / split;
+            for (int64_t lo = 0; lo < num_episodes; lo += Bsub) parts.push_back(lo + Bsub <= num_episodes ? Bsub : num_episodes - lo);
+        }
+    }
+    if (parts.size() == 1 && !u8) {
         if ((rc = twr_ppo_collect(e, spec, p, num_episodes, gamma, lambda, out))) return rc;
         return twr_collected_to_host(e, dst);
     }
-    CollectPlan plan;
-    if ((rc = plan_collect(e, spec, p, num_episodes, &plan))) return rc;
-    CU_TRY(cudaSetDevice(e->device));
-    const int64_t Bsub = (num_episodes + split - 1) / split;
-    if ((rc = ensure_collect_buffers(e, Bsub, plan.T, plan.env.N, num_episodes))) return rc;
+    int64_t Bmax = 0;
+    for (int64_t v : parts) Bmax = v > Bmax ? v : Bmax;
+    if ((rc = ensure_collect_buffers(e, Bmax, plan.T, plan.env.N, num_episodes))) return rc;
     e->has_last = false;
     const uint32_t cid = e->collect_id++;
     const uint32_t base = (uint32_t)((int64_t)e->rank * num_episodes);
-    int64_t at = 0, successes = 0;
+    int64_t at = 0, successes = 0, lo = 0;
     double reward_sum = 0.0;
     int n_fwd = 0;
     const bool timing = e->timing;
     e->timing = false;                                  // per-forward events are only kept for the device-resident path
-    for (int k = 0; k < split; ++k) {
-        const int64_t lo = (int64_t)k * Bsub;
-        const int64_t B = lo + Bsub <= num_episodes ? Bsub : num_episodes - lo;
-        if (B <= 0) break;
-        const int which = k & 1;
+    e->buf.obs_u8 = u8 ? 1 : 0;
+    auto bail = [&](int code) { e->timing = timing; e->buf.obs_u8 = 0; return code; };
+    for (size_t k = 0; k < parts.size(); ++k) {
+        const int64_t B = parts[k];
+        const int which = (int)(k & 1);
         if (k >= 2) CU_TRY(cudaStreamWaitEvent(e->stream, e->ev_copied[which], 0));   // output set free again
         // global local index = lo + i; episode id = (lo + i + E - 1) mod E
         const EnvIds ids{base, (uint32_t)((lo + num_episodes - 1) % num_episodes), (uint32_t)num_episodes};
-        if ((rc = enqueue_collect(e, plan.env, plan.dev, B, ids, cid, gamma, lambda, which, &n_fwd))) { e->timing = timing; return rc; }
+        if ((rc = enqueue_collect(e, plan.env, plan.dev, B, ids, cid, gamma, lambda, which, &n_fwd))) return bail(rc);
         CU_TRY(cudaMemcpyAsync(e->h_stats, e->buf.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, e->stream));
         CU_TRY(cudaEventRecord(e->ev_done[which], e->stream));
         CU_TRY(cudaStreamSynchronize(e->stream));       // record count of this sub-batch -> host offsets
         const size_t R = (size_t)e->h_stats[1];
         successes += (int64_t)e->h_stats[0];
         double rs; memcpy(&rs, &e->h_stats[2], sizeof(double)); reward_sum += rs;
-        if (at + (int64_t)R > dst->capacity) { e->timing = timing; return fail(TWR_ERR_INVALID, "host buffers too small for the collected records"); }
+        if (at + (int64_t)R > dst->capacity) return bail(fail(TWR_ERR_INVALID, "host buffers too small for the collected records"));
         CU_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_done[which], 0));
-        if ((rc = copy_out(e, e->copy_stream, dst, at, R, plan.env.N, plan.dev.A))) { e->timing = timing; return rc; }
+        if ((rc = copy_out(e, e->copy_stream, dst, at, R, plan.env.N, plan.dev.A))) return bail(rc);
         CU_TRY(cudaEventRecord(e->ev_copied[which], e->copy_stream));
         at += (int64_t)R;
+        lo += B;
     }
+    e->buf.obs_u8 = 0;
     e->timing = timing;
     if (dst->ep_len)
         CU_TRY(cudaMemcpyAsync(dst->ep_len, e->ep_len_id, sizeof(int32_t) * (size_t)num_episodes, cudaMemcpyDeviceToHost, e->copy_stream));

@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
         const int nt = min(32, lens[ey] - t0);
         if (e0 + ey >= b.B || nt <= 0) continue;
         uint16_t* dst = b.out_obs + (offs[ey] + t0) * p.N;
+        uint8_t* dst8 = reinterpret_cast<uint8_t*>(b.out_obs) + (offs[ey] + t0) * p.N;
         for (int j = threadIdx.x; j < nt * p.N; j += 32) {
             const uint4 q = tile_q[j / p.N][ey];
             EnvState s;
@@ -398,7 +399,8 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
             s.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
             s.blank = 0; s.depth = 0;
             const int i = j % p.N;
-            dst[j] = (uint16_t)(i * p.N + (int)env_board(p, s, i));
+            const int idx = i * p.N + (int)env_board(p, s, i);
+            if (b.obs_u8) dst8[j] = (uint8_t)idx; else dst[j] = (uint16_t)idx;
         }
     }
 }

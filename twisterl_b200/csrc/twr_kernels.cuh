@@ -37,6 +37,7 @@ struct CollectBuffers {
     int64_t* ep_off;      // [B] record offset of local episode e (plain local order; the id rotation gives merge order)
     int32_t* ep_len_id;   // [total episodes] episode length by episode id (filled by k_episode_offsets)
     int64_t out_base;     // records of earlier sub-batches (pipelined host collect)
+    int obs_u8;           // compaction writes one byte per observation index (twr_host_buffers.obs_u8)
     unsigned long long* stats;  // [0] successes, [1] total records ; double at [2] = reward sum
     // compacted outputs
     uint16_t* out_obs; float* out_logits; float* out_values; float* out_rewards;

@@ -457,3 +457,34 @@ def test_collect_host_pipelined_matches_plain(eng, monkeypatch):
         assert np.array_equal(arr["rewards"][:R], ref.rewards_array) and np.array_equal(arr["perms"][:R], ref.perms_array)
         assert np.array_equal(arr["advs"][:R], ref.additional_array("advs"))
         assert np.array_equal(arr["rets"][:R], ref.additional_array("rets"))
+
+
+@pytest.mark.parametrize("E,difficulty,chunk,trained", [(65536, 128, None, False), (60000, 6, "8", True), (57100, 20, "5", False)])
+def test_collect_balanced_schedule_matches_plain(eng, monkeypatch, E, difficulty, chunk, trained):
+    """The persistent pair kernel cuts left-over tile groups along time and hands them from CTA pair to CTA pair
+    (Sched in twr_forward_tc2.cu).  Scheduling must not change a single byte: the same collect with the balanced
+    schedule off (TWISTERL_B200_BALANCE=0, oracle-checked by the replay tests) gives identical records."""
+    if PRECISION != "f16x2":
+        pytest.skip("the fused persistent kernel is the f16x2 path")
+    import twisterl_b200 as tw
+    from parity import make_policies
+    sd = trained15()[1] if trained else synth_state_dict(3, 256, 512, 256, 4)
+    pol, _ = make_policies(sd, 256, *(transpose_twists(4) if trained else ((), ())))
+    env = tw.env.Puzzle(4, 4, difficulty, 2, 256)
+    col = tw.collector.PPOCollector(E, 0.995, 0.995, 32, engine=eng)
+    if chunk:
+        monkeypatch.setenv("TWISTERL_B200_CHUNK", chunk)
+    out = []
+    for bal in ("0", "2", "6"):
+        monkeypatch.setenv("TWISTERL_B200_BALANCE", bal)
+        eng.set_collect_id(9)
+        d = col.collect(env, pol)
+        out.append(d)
+    ref = out[0]
+    for d in out[1:]:
+        assert np.array_equal(d.ep_len, ref.ep_len) and d.stats == ref.stats
+        assert np.array_equal(d.obs_array, ref.obs_array) and np.array_equal(d.actions_array, ref.actions_array)
+        assert np.array_equal(d.logits_array, ref.logits_array) and np.array_equal(d.values_array, ref.values_array)
+        assert np.array_equal(d.rewards_array, ref.rewards_array) and np.array_equal(d.perms_array, ref.perms_array)
+        assert np.array_equal(d.additional_array("advs"), ref.additional_array("advs"))
+        assert np.array_equal(d.additional_array("rets"), ref.additional_array("rets"))

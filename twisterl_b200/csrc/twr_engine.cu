@@ -91,6 +91,8 @@ struct twr_engine {
     int32_t* ep_len_id = nullptr; int64_t cap_E = 0;
     int64_t cap_B = 0; int cap_T = 0; int64_t cap_R = 0; int cap_cells = 0;
     cudaStream_t copy_stream = nullptr;
+    int32_t* bal_flags = nullptr;   // hand-off counters of the balanced pair-kernel schedule (one per CTA pair)
+    int bal_delta = 2;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     unsigned long long* h_stats = nullptr;   // pinned
     bool has_last = false;
@@ -194,6 +196,7 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
     }
     cudaEventCreate(&e->ev_t0); cudaEventCreate(&e->ev_t1);
     cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+    if (cudaMalloc(reinterpret_cast<void**>(&e->bal_flags), 1024 * sizeof(int32_t)) != cudaSuccess) e->bal_flags = nullptr;
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming);
@@ -227,6 +230,7 @@ void twr_engine_destroy(twr_engine* e) {
     dev_free(e->ep_len_id);
     for (int i = 0; i < 2; ++i) { if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]); }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    if (e->bal_flags) cudaFree(e->bal_flags);
     if (e->h_stats) cudaFreeHost(e->h_stats);
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
     if (e->ev_t1) cudaEventDestroy(e->ev_t1);
@@ -743,6 +747,8 @@ static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev&
         // CTA pair, finished envs idle), then the live list is re-compacted.  Short episodes use chunk 1.
         int chunk = T / 8 < 1 ? 1 : (T / 8 > 32 ? 32 : T / 8);
         if (const char* c = getenv("TWISTERL_B200_CHUNK")) { const int v = atoi(c); if (v >= 1) chunk = v; }
+        int bal_delta = e->bal_delta;
+        if (const char* c = getenv("TWISTERL_B200_BALANCE")) bal_delta = atoi(c);   // 0 switches the time-split schedule off
         CU_TRY(cudaMemsetAsync(b.ep_len, 0, sizeof(int32_t) * (size_t)B, st));
         int32_t* cur = b.live_a;
         int32_t* nxt = b.live_b;
@@ -752,6 +758,11 @@ static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev&
             sa.t = t0;
             fa.fused = 1; fa.step = sa; fa.cb = b; fa.live_next = cnt == 1 ? nxt : nullptr;
             if (cnt == 1) { fa.cb.n_live = b.n_live + ci - t0; }   // collect_step_body appends at n_live[t+1]
+            fa.bal_flags = nullptr; fa.bal_delta = 0;
+            if (cnt >= 4 && e->bal_flags && bal_delta > 0) {
+                CU_TRY(cudaMemsetAsync(e->bal_flags, 0, 1024 * sizeof(int32_t), st));
+                fa.bal_flags = e->bal_flags; fa.bal_delta = bal_delta;
+            }
             if (e->timing && 2 * n_fwd + 1 < (int)e->ev.size()) cudaEventRecord(e->ev[2 * n_fwd], st);
             launch_forward(e, dev, fa);
             if (e->timing && 2 * n_fwd + 1 < (int)e->ev.size()) cudaEventRecord(e->ev[2 * n_fwd + 1], st);

@@ -177,6 +177,62 @@ __global__ void __launch_bounds__(256) k_tc2_pack(PolicyDev p, Tc2Params t, __ha
     }
 }
 
+// Item schedule of one CTA pair for a launch of T steps over G groups (256-env tiles pairs) on P pairs.
+// Plain: the pair owns groups pair, pair+P, ... and walks them step-major.  Balanced (T >= 4, >= 3 own groups per
+// pair, G % P != 0): the G % P left-over groups are cut along time into pieces of <= Lp steps; piece k of a group
+// runs on the pair after the one that ran piece k-1, at item slots 2*step (+ bal_delta per hand-off), so no pair
+// does more than floor(G/P)*T + Lp items instead of (floor(G/P)+1)*T.  scripts/sim_balance.py is the host model.
+struct Sched {
+    int n_items, lanes, T, P;
+    int nA, nB, sA0, pA0, gA;   // dependent piece A = steps [sA0, sA0+nA) of extra group gA; head piece B = steps [0, nB) of gA+1
+};
+__device__ __forceinline__ Sched make_sched(int G, int P, int T, int pair, int delta) {
+    Sched s;
+    s.T = T; s.P = P; s.nA = 0; s.nB = 0; s.sA0 = 0; s.pA0 = 0; s.gA = 0;
+    const int base = G / P, rem = G % P;
+    if (delta > 0 && T >= 4 && base >= 3 && rem > 0) {
+        s.lanes = base;
+        const int X = rem * T;
+        int Lp = (X + P - 1) / P;
+        if (Lp < 4) Lp = 4;
+        const int x0 = min(X, pair * Lp), x1 = min(X, x0 + Lp), nX = x1 - x0;
+        if (nX > 0) {
+            s.gA = x0 / T; s.sA0 = x0 % T;
+            s.nA = min(nX, T - s.sA0); s.nB = nX - s.nA;
+            const int dA = s.sA0 > 0 ? delta * (pair - (s.gA * T) / Lp) : 0;
+            s.pA0 = 2 * s.sA0 + dA;
+        }
+        s.n_items = base * T + nX;
+    } else {
+        s.lanes = (G - pair + P - 1) / P;
+        s.n_items = s.lanes * T;
+    }
+    return s;
+}
+// item i of `pair` -> (group, step); extra = 1 for piece A, 2 for piece B, 0 for an own group
+__device__ __forceinline__ void sched_item(const Sched& s, int pair, int i, int& group, int& step, int& extra) {
+    if (s.nA + s.nB == 0) { group = pair + (i % s.lanes) * s.P; step = i / s.lanes; extra = 0; return; }
+    const int ja = i - s.pA0;
+    if (!(i & 1) && (i >> 1) < s.nB) { group = s.lanes * s.P + s.gA + 1; step = i >> 1; extra = 2; return; }
+    if (ja >= 0 && !(ja & 1) && (ja >> 1) < s.nA) { group = s.lanes * s.P + s.gA; step = s.sA0 + (ja >> 1); extra = 1; return; }
+    const int before = min(s.nB, (i + 1) >> 1) + (ja > 0 ? min(s.nA, (ja + 1) >> 1) : 0);
+    const int m = i - before;
+    group = pair + (m % s.lanes) * s.P; step = m / s.lanes; extra = 0;
+}
+// one lane polls the hand-off counter of an extra group (acquire, gpu scope); the warp barrier orders the other lanes
+__device__ __forceinline__ void wait_handoff(const int32_t* flag, int target) {
+    if ((threadIdx.x & 31) == 0) {
+        int v = 0;
+        for (uint32_t spins = 0;; ++spins) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v >= target) break;
+            if (spins > (1u << 22)) __trap();
+            __nanosleep(100);
+        }
+    }
+    __syncwarp();
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -187,13 +243,13 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     const int pair_id = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
     const int n_groups = (n_tiles + 1) / 2;
     if (pair_id >= n_groups) return;                           // pair-uniform
-    const int my_tiles = (n_groups - pair_id + n_pairs - 1) / n_pairs;
     // Work items: (step, tile) pairs, all steps of this launch for all tiles owned by this pair, step-major.
     // With t_count > 1 the kernel is persistent over time: a tile's envs stay with this pair for the whole
     // chunk, finished envs idle, and the live list is re-compacted between launches.
     const int t_count = a.t_count > 0 ? a.t_count : 1;
-    const int n_items = my_tiles * t_count;
-    auto tile_of = [&](int it) -> int64_t { return ((int64_t)pair_id + (int64_t)it * n_pairs) * 2 + crank; };
+    const Sched sch = make_sched(n_groups, n_pairs, t_count, pair_id, (a.fused && a.bal_flags) ? a.bal_delta : 0);
+    const int my_tiles = sch.lanes;
+    const int n_items = sch.n_items;
 
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + SM_BARS;
@@ -363,9 +419,13 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
 
         // Global loads of the env state for item `it`, issued early (at the start of the previous item) so
         // their latency is off the critical path of the one-hot build.
-        struct Pre { int64_t pos; int64_t e; uint4 c; };
+        struct Pre { int64_t pos; int64_t e; uint4 c; int step; };
         auto prefetch = [&](int it) -> Pre {
-            Pre q; q.pos = tile_of(it % my_tiles) * TM + row; q.e = 0; q.c = make_uint4(0, 0, 0, 0);
+            int group, step, extra;
+            sched_item(sch, pair_id, it, group, step, extra);
+            // first step of a piece whose earlier steps ran on another pair: wait until both of its CTAs published them
+            if (extra == 1 && step == sch.sA0 && sch.sA0 > 0) wait_handoff(a.bal_flags + sch.gA, 2 * sch.sA0);
+            Pre q; q.pos = ((int64_t)group * 2 + crank) * TM + row; q.e = 0; q.c = make_uint4(0, 0, 0, 0); q.step = step;
             if (q.pos < n) {
                 q.e = a.live ? a.live[q.pos] : q.pos;
                 if (!a.obs_rows) q.c = __ldcg(a.cells + q.e);   // written by the partner thread's fused step >= 1 item earlier
@@ -374,7 +434,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         };
         auto build_a1 = [&](int it, const Pre& q) -> int {
             const int64_t pos = q.pos;
-            const int t_cur = a.t + it / my_tiles;
+            const int t_cur = a.t + q.step;
             int perm = -1;
             EnvState s; s.blank = 0; s.depth = 0;
             s.lo = (uint64_t)q.c.x | ((uint64_t)q.c.y << 32);
@@ -450,7 +510,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         const bool build_early = my_tiles > 1 || t_count == 1;
         if (chalf == 1) perm_next = build_a1(0, prefetch(0));          // the upper-half warps own the one-hot operand
         for (int it = 0; it < n_items; ++it) {
-            Pre pre_next; pre_next.pos = 0; pre_next.e = 0; pre_next.c = make_uint4(0, 0, 0, 0);
+            Pre pre_next; pre_next.pos = 0; pre_next.e = 0; pre_next.c = make_uint4(0, 0, 0, 0); pre_next.step = 0;
             if (build_early && chalf == 1 && it + 1 < n_items) {
                 // with >= 2 tiles per pair, item it+1's env state was last written by the fused step of item
                 // it+1-my_tiles <= it-1 (lower-half threads); barrier 3 orders that step before these loads
@@ -528,7 +588,9 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 ps[4] = acc[4];
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");     // the 8 epilogue warps only
-            const int64_t pos = tile_of(it % my_tiles) * TM + row;
+            int group_cur, step_cur, extra_cur;
+            sched_item(sch, pair_id, it, group_cur, step_cur, extra_cur);
+            const int64_t pos = ((int64_t)group_cur * 2 + crank) * TM + row;
             if (chalf == 0) {                                          // warp-uniform: whole warps take this branch
                 const bool active = pos < n;
                 float out[4] = {0.f, 0.f, 0.f, 0.f};
@@ -556,7 +618,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 if (a.fused) {
                     const int e = active ? (a.live ? a.live[pos] : (int)pos) : 0;
                     StepArgs sa = a.step;
-                    sa.t = a.t + it / my_tiles;
+                    sa.t = a.t + step_cur;
                     // inside a multi-step chunk an env that already recorded its terminal state idles
                     const bool alive = active && (t_count == 1 || a.cb.ep_len[e] == 0);
                     collect_step_body(sa, a.cb, alive, e, make_float4(out[0], out[1], out[2], out[3]), value, perm_cur,
@@ -564,6 +626,11 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 } else if (active) {
                     a.logits[pos] = make_float4(out[0], out[1], out[2], out[3]);
                     a.values[pos] = value;
+                }
+                if (extra_cur) {
+                    // a time-split group: publish this CTA's finished step to the pair that runs the next piece
+                    asm volatile("bar.sync 4, %0;" ::"n"(NEPI / 2) : "memory");
+                    if (threadIdx.x == 64) { __threadfence(); atomicAdd(a.bal_flags + (group_cur - sch.lanes * sch.P), 1); }
                 }
                 // publish "step of item `it` done" to the upper-half threads (matched by their bar.sync 3 at item it+1)
                 if (build_early && t_count > 1 && it + 2 < n_items) asm volatile("bar.arrive 3, %0;" ::"n"(NEPI) : "memory");

@@ -92,6 +92,9 @@ struct ForwardArgs {
     // fused collect step (k_forward_tc2 only): when `fused` != 0 the epilogue does k_collect_step's work
     int fused; StepArgs step; CollectBuffers cb; int32_t* live_next;
     int t_count;      // steps t .. t+t_count-1 in this launch (fused pair kernel only; 0/1 = one step)
+    // balanced item schedule of the persistent pair kernel: groups beyond a whole number per CTA pair are cut along
+    // TIME into pieces handed from pair to pair; bal_flags[g] counts the finished steps of such a group (zeroed per launch)
+    int32_t* bal_flags; int bal_delta;   // bal_delta: extra item slots granted to each hand-off (0 = balancing off)
     int dbg_flags;    // debug experiments (k_forward_tc2): 1 skip epilogue-1 TMEM traffic, 2 skip TMA copies, 4 skip GEMM2 MMAs, 8 skip GEMM1 MMAs
     long long* dbg;   // optional [gridDim][16] cycle counters written by k_forward_tc (debug/profiling)
 };

@@ -27,6 +27,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FLOP_PER_STEP = {"puzzle15": 272_896, "puzzle8": 269_312, "gridworld": 145_152}
+EXECUTED_TENSOR_FLOP_PER_STEP = {"puzzle15": 2 * (2 * 256 * 512) + 3 * (2 * 512 * 256)}   # f16x2: 2 + 3 MMA passes
 METRIC = "rollout env-steps/sec incl. policy fwd (puzzle15 PPO)"
 UNIT = "env-steps/s"
 
@@ -268,13 +269,22 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_records / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "twr_ppo_collect_host (pinned host buffers)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "k_forward_fp32" if args.precision == "fp32" else "k_forward_tc",
+            "roofline": {"bound": "tensor", "kernel": "k_forward_fp32" if args.precision == "fp32" else "k_forward_tc2",
                          "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
-                         "frac": (achieved / pk["bf16"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / pk["bf16"]) if achieved else None,
+                         # dram read+write bytes of one k_forward_tc2 launch (32 steps x 65536 envs), profiles/r1c_tc2_summary.md
+                         "traffic": 39_811_328 if (args.precision == "f16x2" and args.episodes == 65536) else None,
                          "peak_source": pk["src"] + " bf16_tflops_sustained",
                          "forward_ms_per_launch": fwd_ms / max(fwd_launches, 1), "forward_share_of_step": fwd_ms / ms,
                          "algorithmic_flop_per_env_step": FLOP_PER_STEP["puzzle15"]},
         }
+        if args.precision == "f16x2" and achieved:
+            # what the tensor pipe executes for the fp32-grade result: the embedding as a dense one-hot GEMM (x2: table
+            # hi/lo) and the hidden layer as 3 split products -- the tensor-pipe utilisation ncu reports follows this figure
+            ex = EXECUTED_TENSOR_FLOP_PER_STEP["puzzle15"]
+            line["roofline"]["executed_tensor_flop_per_env_step"] = ex
+            line["roofline"]["executed"] = achieved * ex / FLOP_PER_STEP["puzzle15"]
+            line["roofline"]["executed_frac"] = line["roofline"]["executed"] / pk["bf16"]
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             rate0, _ = cpu_collect_rate(sd, 256, args.difficulty, cores)

@@ -44,8 +44,7 @@ constexpr int SM_MISC = SM_RING + NSLOTS * TILE_BYTES;
 constexpr int SM_HEADW = SM_MISC;
 constexpr int SM_B1 = SM_HEADW + 8192;
 constexpr int SM_EMBB = SM_B1 + 1024;
-constexpr int SM_ROWS = SM_EMBB + 4096;
-constexpr int SM_PART = SM_ROWS + TM * MAX_OBS;           // [2][128][8] float: head partial sums of the upper column half
+constexpr int SM_PART = SM_EMBB + 4096;                   // [2][128][8] float: head partial sums of the upper column half
 constexpr int SM_PERM = SM_PART + 2 * TM * 8 * 4;         // [4][128] int8: twist index of the tiles in flight
 constexpr int SM_BARS = SM_PERM + 4 * TM;
 constexpr int SM_TOTAL = SM_BARS + 512;
@@ -261,7 +260,6 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     float* embb = reinterpret_cast<float*>(smem + SM_EMBB);
     float* part_s = reinterpret_cast<float*>(smem + SM_PART);
     int8_t* perm_s = reinterpret_cast<int8_t*>(smem + SM_PERM);
-    uint8_t* rows_s = smem + SM_ROWS;
     const int NC = t.NC, NKB1 = t.NKB1, H = t.H;
 
     if (threadIdx.x == 0) {
@@ -281,7 +279,6 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         b1s[i] = p.b1[i];
     }
     for (int i = threadIdx.x; i < t.E; i += NTHREADS) embb[i] = p.emb_b[i];
-    for (int i = threadIdx.x; i < TM * MAX_OBS; i += NTHREADS) rows_s[i] = 0xFF;
     if (warp == 1) {   // both CTAs, same warp id: allocates the same 512 columns in both SMs
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
@@ -719,6 +716,27 @@ bool launch_forward_tc2(cudaStream_t st, const PolicyDev& p, const ForwardArgs& 
     const int n_groups = (n_tiles + 1) / 2, max_pairs = g_sms / 2;
     const int grid = (n_groups < max_pairs ? n_groups : max_pairs) * 2;
     cudaFuncSetAttribute(k_forward_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
+    // The balanced schedule lets a pair wait for another pair's progress, which needs every cluster of the grid to
+    // be resident at once: query it once and keep the plain schedule when the device cannot hold them all.
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(max_pairs * 2)); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SM_TOTAL;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        max_clusters = cudaOccupancyMaxActiveClusters(&nc, k_forward_tc2, &cfg) == cudaSuccess ? nc : 0;
+        cudaGetLastError();
+    }
+    if (a.bal_flags && max_clusters < grid / 2) {
+        ForwardArgs plain = a;
+        plain.bal_flags = nullptr; plain.bal_delta = 0;
+        k_forward_tc2<<<grid, NTHREADS, SM_TOTAL, st>>>(p, plain, make_params2(p), tmap);
+        g_twr_launches.fetch_add(1, std::memory_order_relaxed);
+        return true;
+    }
     k_forward_tc2<<<grid, NTHREADS, SM_TOTAL, st>>>(p, a, make_params2(p), tmap);
     g_twr_launches.fetch_add(1, std::memory_order_relaxed);
     return true;

@@ -233,22 +233,36 @@ __device__ __forceinline__ void gae_step(float r, float v, float v_next, float a
     adv = __fsub_rn(ret, v);
 }
 
-__global__ void __launch_bounds__(256) k_gae_time_major(CollectBuffers b, float gamma, float lambda) {
+// One thread per env, reverse scan over its time-major records.  The loads of 8 steps are issued before the
+// (serial) recursion runs over them, so each warp keeps 16 independent 128-byte requests in flight.
+__global__ void __launch_bounds__(64) k_gae_time_major(CollectBuffers b, float gamma, float lambda) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= b.B) return;
     const int n = b.ep_len[e];
     if (n <= 0) return;
-    int64_t r = (int64_t)(n - 1) * b.B + e;
-    float rew = b.rec_reward[r], v = b.rec_value[r];
-    float adv = __fsub_rn(rew, v), ret = rew;
-    b.rec_adv[r] = adv; b.rec_ret[r] = ret;
-    float v_next = v;
-    for (int t = n - 2; t >= 0; --t) {
-        r -= b.B;
-        rew = b.rec_reward[r]; v = b.rec_value[r];
-        gae_step(rew, v, v_next, adv, gamma, lambda, adv, ret);
-        b.rec_adv[r] = adv; b.rec_ret[r] = ret;
-        v_next = v;
+    constexpr int U = 8;
+    float adv = 0.f, ret = 0.f, v_next = 0.f;
+    for (int t1 = n - 1; t1 >= 0; t1 -= U) {          // block of steps t1, t1-1, .., t1-U+1
+        float rw[U], vl[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int t = t1 - j;
+            if (t >= 0) {
+                const int64_t r = (int64_t)t * b.B + e;
+                rw[j] = __ldcs(b.rec_reward + r); vl[j] = __ldcs(b.rec_value + r);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int t = t1 - j;
+            if (t >= 0) {
+                if (t == n - 1) { adv = __fsub_rn(rw[j], vl[j]); ret = rw[j]; }
+                else gae_step(rw[j], vl[j], v_next, adv, gamma, lambda, adv, ret);
+                const int64_t r = (int64_t)t * b.B + e;
+                b.rec_adv[r] = adv; b.rec_ret[r] = ret;
+                v_next = vl[j];
+            }
+        }
     }
 }
 
@@ -270,7 +284,7 @@ __global__ void __launch_bounds__(256) k_gae_concat(const float* __restrict__ rw
 }
 
 void launch_gae_time_major(cudaStream_t st, const CollectBuffers& b, float gamma, float lambda) {
-    k_gae_time_major<<<grid_for(b.B, 256), 256, 0, st>>>(b, gamma, lambda);
+    k_gae_time_major<<<grid_for(b.B, 64), 64, 0, st>>>(b, gamma, lambda);
     TWR_COUNT_LAUNCH();
 }
 void launch_gae_concat(cudaStream_t st, const float* r, const float* v, const int64_t* off, int64_t n_ep, float gamma,
@@ -283,29 +297,42 @@ void launch_gae_concat(cudaStream_t st, const float* r, const float* v, const in
 // ------------------------------------------------------------------------- K5 ---
 // Exclusive scan of episode lengths in local order (the env-id rotation of EnvIds already puts the
 // LAST episode id at local 0, i.e. local order == the reference's merge order, collector.rs:40-46).
-// One CTA; thread i owns a contiguous run.  Also scatters ep_len by episode id.
+// One CTA of 32 warps; warp w owns a contiguous segment that it walks 32 lengths at a time with coalesced loads
+// and a shuffle scan (pass 1: segment totals, pass 2: offsets).  Also scatters ep_len by episode id.
 __global__ void __launch_bounds__(1024) k_episode_offsets(CollectBuffers b, EnvIds ids) {
-    __shared__ long long part[1024];
+    __shared__ long long seg_total[32];
     const int64_t B = b.B;
-    const int64_t per = (B + 1023) / 1024;
-    const int64_t s0 = (int64_t)threadIdx.x * per, s1 = min(B, s0 + per);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t per = ((B + 1023) / 1024) * 32;               // lengths per warp, a multiple of 32
+    const int64_t s0 = (int64_t)warp * per, s1 = min(B, s0 + per);
     long long sum = 0;
-    for (int64_t s = s0; s < s1; ++s) sum += b.ep_len[s];
-    part[threadIdx.x] = sum;
+    for (int64_t s = s0 + lane; s < s1; s += 32) sum += b.ep_len[s];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if (lane == 0) seg_total[warp] = sum;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {       // Hillis-Steele inclusive scan
-        long long v = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    long long run = 0;
+    for (int w = 0; w < warp; ++w) run += seg_total[w];
+    for (int64_t c = s0; c < s1; c += 32) {
+        const int64_t s = c + lane;
+        const int len = s < s1 ? b.ep_len[s] : 0;
+        long long inc = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long v = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += v;
+        }
+        if (s < s1) {
+            b.ep_off[s] = run + inc - len;
+            if (b.ep_len_id) b.ep_len_id[ids.gid((uint32_t)s) - ids.base] = len;
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    long long run = part[threadIdx.x] - sum;
-    for (int64_t s = s0; s < s1; ++s) {
-        b.ep_off[s] = run;
-        run += b.ep_len[s];
-        if (b.ep_len_id) b.ep_len_id[ids.gid((uint32_t)s) - ids.base] = b.ep_len[s];
+    if (threadIdx.x == 1023) {
+        long long total = 0;
+        for (int w = 0; w < 32; ++w) total += seg_total[w];
+        b.stats[1] = (unsigned long long)total;
     }
-    if (threadIdx.x == 1023) b.stats[1] = (unsigned long long)part[1023];
 }
 
 void launch_episode_offsets(cudaStream_t st, const CollectBuffers& b, const EnvIds& ids) {

@@ -99,7 +99,11 @@ typedef struct {
     const float* emb_vectors;  /* [obs_size][emb_size]  (EmbeddingBag vec_vectors) */
     const float* emb_bias;     /* [emb_size] */
     int32_t obs_size, emb_size, emb_apply_relu;
-    int32_t obs_shape[2], obs_shape_len, conv_dim; /* EmbeddingBag obs_shape / conv_dim */
+    /* EmbeddingBag obs_shape / conv_dim.  obs_shape_len == 2 is the Conv1dPolicy path (rust/src/nn/layers.rs:63-77,
+     * src/twisterl/nn/utils.py:68-75): emb_vectors is [obs_size = obs_shape[conv_dim]][v] with
+     * v = emb_size / obs_shape[1 - conv_dim], emb_bias stays [emb_size]; the observation indices then range over
+     * obs_shape[0] * obs_shape[1]. */
+    int32_t obs_shape[2], obs_shape_len, conv_dim;
     const twr_linear_desc* common;     int32_t n_common;
     const twr_linear_desc* action_net; int32_t n_action;
     const twr_linear_desc* value_net;  int32_t n_value;

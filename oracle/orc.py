@@ -212,6 +212,20 @@ class Policy:
             p.set_perms(obs_perms, act_perms)
         return p
 
+    @classmethod
+    def from_conv1d_state_dict(cls, sd, obs_shape, conv_dim, obs_perms=(), act_perms=()):
+        """Conv1dPolicy weights -> oracle policy, mirroring embeddingbag_to_rust's Conv1d branch
+        (src/twisterl/nn/utils.py:68-75): vectors = conv weight [v, n_in, 1] squeezed and transposed, zero bias."""
+        g = lambda k: np.asarray(sd[k], dtype=np.float32)
+        p = cls()
+        w = g("conv_layer.weight")[:, :, 0]
+        p.set_embedding(w.T, np.zeros(w.shape[0] * obs_shape[1 - conv_dim], np.float32), True, list(obs_shape), conv_dim)
+        for net, which in (("common", NET_COMMON), ("action", NET_ACTION), ("value", NET_VALUE)):
+            p.add_linear(which, g(f"{net}.0.weight").T.flatten(), g(f"{net}.0.bias"), net == "common")
+        if len(obs_perms):
+            p.set_perms(obs_perms, act_perms)
+        return p
+
     def _call(self, fn, obs, masks, perm):
         o = np.ascontiguousarray(obs, dtype=np.int32)
         out = np.zeros(256, dtype=np.float32)

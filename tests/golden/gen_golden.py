@@ -14,6 +14,8 @@ Outputs (tests/golden/):
                            without twists and with the {identity, transpose} twist set
   policy_synth.npz      -- same for seeded synthetic weights on the puzzle8 / grid_world shapes
                            (weights are regenerated from the seed at test time, only I/O is stored)
+  policy_conv1d.npz     -- the reference's torch Conv1dPolicy (both conv_dim values, with and without twists) on
+                           seeded synthetic weights, puzzle15 shape
 """
 import json
 import re
@@ -39,10 +41,10 @@ sys.modules["twisterl.twisterl"] = stub
 import twisterl  # noqa: E402
 
 twisterl.twisterl = stub
-from twisterl.nn.policy import BasicPolicy  # noqa: E402
+from twisterl.nn.policy import BasicPolicy, Conv1dPolicy  # noqa: E402
 
 sys.path.insert(0, str(OUT.parent))
-from helpers import scramble_states, synth_state_dict, transpose_twists  # noqa: E402
+from helpers import scramble_states, synth_conv_state_dict, synth_state_dict, transpose_twists  # noqa: E402
 
 
 def parse_boards(text, names):
@@ -154,6 +156,32 @@ def main():
         out[f"{name}.states"] = st; out[f"{name}.logits"] = l; out[f"{name}.values"] = v
         out[f"{name}.seed"] = np.int64(seed); out[f"{name}.hidden"] = np.int64(hidden)
     np.savez(OUT / "policy_synth.npz", **out)
+
+    # ---- Conv1dPolicy (2-D EmbeddingBag path, nn/layers.rs:63-77) on the puzzle15 shape
+    out = {}
+    rng = np.random.default_rng(151)
+    st = scramble_states(rng, 256, 4, 4, 64)
+    x = one_hot(st)
+    obs_perms, act_perms = transpose_twists(4)
+    perm_idx = rng.integers(0, 2, size=len(st)).astype(np.int64)
+    out["states"] = st; out["twist_perm_idx"] = perm_idx.astype(np.int32)
+    for conv_dim in (0, 1):
+        seed = 1510 + conv_dim
+        csd = synth_conv_state_dict(seed, 16, 32, 512, 256, 4)
+        for tag, perms in (("plain", ((), ())), ("twist", (obs_perms, act_perms))):
+            pol = Conv1dPolicy([16, 16], 4, 512, conv_dim=conv_dim, common_layers=(256,), obs_perms=perms[0],
+                               act_perms=perms[1])
+            with torch.no_grad():
+                pol.conv_layer.weight.copy_(torch.as_tensor(csd["conv_layer.weight"]))
+                for name in ("common", "action", "value"):
+                    getattr(pol, name)[0].weight.copy_(torch.as_tensor(csd[f"{name}.0.weight"]))
+                    getattr(pol, name)[0].bias.copy_(torch.as_tensor(csd[f"{name}.0.bias"]))
+                pol.eval()
+                l, v = pol(x) if tag == "plain" else pol(x, perm_indices=torch.as_tensor(perm_idx))
+            out[f"dim{conv_dim}.{tag}.logits"] = l.numpy().astype(np.float32)
+            out[f"dim{conv_dim}.{tag}.values"] = v.numpy().astype(np.float32).reshape(-1)
+        out[f"dim{conv_dim}.seed"] = np.int64(seed)
+    np.savez(OUT / "policy_conv1d.npz", **out)
     print("golden fixtures written to", OUT)
 
 

@@ -20,6 +20,18 @@ def synth_state_dict(seed, obs_size, emb, hidden, n_act):
             "value.0.weight": f(1, hidden), "value.0.bias": b(1)}
 
 
+def synth_conv_state_dict(seed, n_in, v, emb, hidden, n_act):
+    """Seeded weights of a Conv1dPolicy (src/twisterl/nn/policy.py:205-266): conv kernel [v, n_in, 1] without bias
+    (larger scale than the Linear embedding: only N vectors are summed into each slice)."""
+    g = np.random.default_rng(seed)
+    f = lambda sc, *s: (g.standard_normal(s) * sc).astype(np.float32)
+    b = lambda n: g.uniform(-0.05, 0.05, size=n).astype(np.float32)
+    return {"conv_layer.weight": f(0.2, v, n_in, 1),
+            "common.0.weight": f(0.05, hidden, emb), "common.0.bias": b(hidden),
+            "action.0.weight": f(0.05, n_act, hidden), "action.0.bias": b(n_act),
+            "value.0.weight": f(0.05, 1, hidden), "value.0.bias": b(1)}
+
+
 def transpose_twists(w):
     """{identity, main-diagonal transpose} twist set for a square w x w puzzle."""
     N = w * w

@@ -18,6 +18,18 @@ def make_policies(sd, obs_size, obs_perms=(), act_perms=()):
     return pol, orc.Policy.from_torch_state_dict(sd, obs_perms, act_perms)
 
 
+def make_conv1d_policies(sd, obs_shape, conv_dim, obs_perms=(), act_perms=()):
+    """(device policy, oracle policy) of a Conv1dPolicy, via Conv1dPolicy.to_rust()'s layouts (nn/policy.py:259-266)."""
+    from twisterl_b200 import nn as twn
+    w = np.asarray(sd["conv_layer.weight"], np.float32)[:, :, 0]
+    pol = twn.Policy(twn.EmbeddingBag(w.T.tolist(), [0.0] * (w.shape[0] * obs_shape[1 - conv_dim]), True, list(obs_shape), conv_dim),
+                     twn.Sequential([twn.Linear(sd["common.0.weight"].T.flatten(), sd["common.0.bias"], True)]),
+                     twn.Sequential([twn.Linear(sd["action.0.weight"].T.flatten(), sd["action.0.bias"], False)]),
+                     twn.Sequential([twn.Linear(sd["value.0.weight"].T.flatten(), sd["value.0.bias"], False)]),
+                     [list(p) for p in obs_perms], [list(p) for p in act_perms])
+    return pol, orc.Policy.from_conv1d_state_dict(sd, obs_shape, conv_dim, obs_perms, act_perms)
+
+
 def check_collect_against_oracle(data, spec, opol, seed, collect_id, gamma, lam, tol, env_id_base=0,
                                  max_episodes=None, near_tie=1e-4):
     """Replay check (north_star: 'bit-exact under forced or replayed action sequences').

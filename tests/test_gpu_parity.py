@@ -214,9 +214,9 @@ def test_policy_scalar_api_and_unsupported_shapes(eng):
     deep = tw.nn.Policy(pol.embeddings, tw.nn.Sequential(pol.common.layers * 2), pol.action_net, pol.value_net, [], [])
     with pytest.raises(RuntimeError, match="one common"):
         deep.device_handle(eng)
-    conv = tw.nn.Policy(tw.nn.EmbeddingBag(np.zeros((16, 32)), np.zeros(512), True, [16, 16], 0), pol.common,
+    conv = tw.nn.Policy(tw.nn.EmbeddingBag(np.zeros((15, 32)), np.zeros(512), True, [16, 16], 0), pol.common,
                         pol.action_net, pol.value_net, [], [])
-    with pytest.raises(RuntimeError, match="1-D EmbeddingBag"):
+    with pytest.raises(RuntimeError, match="obs_shape\\[conv_dim\\] vectors"):     # Conv1d table with a missing row
         conv.device_handle(eng)
 
 
@@ -488,3 +488,35 @@ def test_collect_balanced_schedule_matches_plain(eng, monkeypatch, E, difficulty
         assert np.array_equal(d.rewards_array, ref.rewards_array) and np.array_equal(d.perms_array, ref.perms_array)
         assert np.array_equal(d.additional_array("advs"), ref.additional_array("advs"))
         assert np.array_equal(d.additional_array("rets"), ref.additional_array("rets"))
+
+
+@pytest.mark.parametrize("conv_dim", [0, 1])
+def test_conv1d_policy_forward_and_collect(eng, conv_dim):
+    """Conv1dPolicy (2-D EmbeddingBag path, nn/layers.rs:63-77) on the device -- forward against
+    the reference's own torch Conv1dPolicy (golden fixture), +/- twists, then a collect replayed through the oracle."""
+    import twisterl_b200 as tw
+    from helpers import synth_conv_state_dict
+    from parity import check_collect_against_oracle, make_conv1d_policies
+    from twisterl_b200.nn import forward_obs
+    g = np.load(GOLDEN / "policy_conv1d.npz")
+    sd = synth_conv_state_dict(int(g[f"dim{conv_dim}.seed"]), 16, 32, 512, 256, 4)
+    obs = obs_from_states(g["states"])
+    pol, opol = make_conv1d_policies(sd, [16, 16], conv_dim)
+    l, v = forward_obs(eng, pol, obs, None)
+    assert _close(l, g[f"dim{conv_dim}.plain.logits"], TOL) and _close(v, g[f"dim{conv_dim}.plain.values"], TOL)
+    tpol, topol = make_conv1d_policies(sd, [16, 16], conv_dim, *transpose_twists(4))
+    l, v = forward_obs(eng, tpol, obs, g["twist_perm_idx"])
+    assert _close(l, g[f"dim{conv_dim}.twist.logits"], TOL) and _close(v, g[f"dim{conv_dim}.twist.values"], TOL)
+    ospec = orc.puzzle_spec(4, 4, 5, 2, 256)
+    env = tw.env.Puzzle(4, 4, 5, 2, 256)
+    col = tw.collector.PPOCollector(200, 0.995, 0.995, 1, engine=eng)
+    eng.set_collect_id(31)
+    data = col.collect(env, tpol)
+    rep = check_collect_against_oracle(data, ospec, topol, seed=eng.seed, collect_id=31, gamma=0.995, lam=0.995, tol=TOL)
+    assert rep["records"] == len(data.values_array)
+    # weight refresh keeps working on the expanded table (twr_policy_update re-expands)
+    sd2 = synth_conv_state_dict(77, 16, 32, 512, 256, 4)
+    pol2, opol2 = make_conv1d_policies(sd2, [16, 16], conv_dim)
+    l2, _ = forward_obs(eng, pol2, obs[:8], None)
+    ref = np.array([opol2.raw_predict(o)[0] for o in obs[:8]])
+    assert _close(l2, ref, TOL)

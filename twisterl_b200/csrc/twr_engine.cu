@@ -273,8 +273,7 @@ int twr_engine_last_timing(const twr_engine* e, float* forward_ms, float* total_
 static int validate_desc(const twr_policy_desc* d) {
     if (!d || !d->emb_vectors || !d->emb_bias) return fail(TWR_ERR_INVALID, "policy desc / embedding is NULL");
     if (d->obs_shape_len != 1)
-        return fail(TWR_ERR_UNSUPPORTED, "only the 1-D EmbeddingBag path (BasicPolicy) runs on the device; "
-                                         "the conv1d 2-D path (Conv1dPolicy) is not implemented");
+        return fail(TWR_ERR_UNSUPPORTED, "EmbeddingBag obs_shape must have 1 (BasicPolicy) or 2 (Conv1dPolicy) dimensions");
     if (!d->emb_apply_relu) return fail(TWR_ERR_UNSUPPORTED, "EmbeddingBag without ReLU is not implemented");
     if (d->n_common != 1 || !d->common) return fail(TWR_ERR_UNSUPPORTED, "exactly one common Linear layer is implemented");
     if (d->n_action != 1 || !d->action_net || d->n_value != 1 || !d->value_net)
@@ -295,6 +294,35 @@ static int validate_desc(const twr_policy_desc* d) {
         for (int64_t i = 0; i < (int64_t)d->n_perms * a.out; ++i)
             if (d->act_perms[i] < 0 || d->act_perms[i] >= a.out) return fail(TWR_ERR_INVALID, "act_perms entry out of range");
     }
+    return TWR_OK;
+}
+
+// Conv1dPolicy (nn/layers.rs:63-77): observation index i adds vectors[row] into the output slice
+// [col*v, (col+1)*v), (row, col) = (i / shape[1], i % shape[1]) swapped when conv_dim == 1.  That is the 1-D
+// EmbeddingBag of a block-sparse table T[i][col*v + k] = vectors[row][k]; adding the table's exact zeros leaves
+// every fp32 partial sum unchanged, so the device path runs the expanded table through the same kernels.
+// Returns a desc whose embedding points into `store` (obs_shape_len == 1 descs pass through untouched).
+static int expand_conv1d(const twr_policy_desc* d, twr_policy_desc* out, std::vector<float>* store) {
+    *out = *d;
+    if (!d || d->obs_shape_len != 2) return TWR_OK;
+    if (!d->emb_vectors) return fail(TWR_ERR_INVALID, "policy desc / embedding is NULL");
+    const int s0 = d->obs_shape[0], s1 = d->obs_shape[1];
+    if (s0 < 1 || s1 < 1 || (d->conv_dim != 0 && d->conv_dim != 1)) return fail(TWR_ERR_INVALID, "bad obs_shape / conv_dim");
+    const int n_vec = d->conv_dim == 0 ? s0 : s1, n_col = d->conv_dim == 0 ? s1 : s0;
+    if (d->obs_size != n_vec) return fail(TWR_ERR_INVALID, "conv1d EmbeddingBag needs obs_shape[conv_dim] vectors");
+    if (d->emb_size % n_col) return fail(TWR_ERR_INVALID, "conv1d EmbeddingBag: bias length must be vector length x obs_shape[1-conv_dim]");
+    const int v = d->emb_size / n_col;
+    const int64_t full = (int64_t)s0 * s1;
+    if (full >= 65536) return fail(TWR_ERR_UNSUPPORTED, "obs_size must be in 1..65535");
+    store->assign((size_t)full * d->emb_size, 0.0f);
+    for (int64_t i = 0; i < full; ++i) {
+        int row = (int)(i / s1), col = (int)(i % s1);
+        if (d->conv_dim == 1) { const int t = row; row = col; col = t; }
+        memcpy(store->data() + (size_t)i * d->emb_size + (size_t)col * v, d->emb_vectors + (size_t)row * v, sizeof(float) * (size_t)v);
+    }
+    out->emb_vectors = store->data();
+    out->obs_size = (int32_t)full;
+    out->obs_shape_len = 1; out->obs_shape[0] = (int32_t)full; out->obs_shape[1] = 0; out->conv_dim = 0;
     return TWR_OK;
 }
 
@@ -322,11 +350,16 @@ static int upload_policy(twr_policy* p, const twr_policy_desc* d) {
     return TWR_OK;
 }
 
-int twr_policy_create(twr_engine* e, const twr_policy_desc* d, twr_policy** out) {
+int twr_policy_create(twr_engine* e, const twr_policy_desc* d_in, twr_policy** out) {
     if (!e || !out) return fail(TWR_ERR_INVALID, "engine/out is NULL");
     *out = nullptr;
-    int rc = validate_desc(d);
+    if (!d_in) return fail(TWR_ERR_INVALID, "policy desc / embedding is NULL");
+    twr_policy_desc flat;
+    std::vector<float> table;
+    int rc = expand_conv1d(d_in, &flat, &table);
     if (rc) return rc;
+    const twr_policy_desc* d = &flat;
+    if ((rc = validate_desc(d))) return rc;
     CU_TRY(cudaSetDevice(e->device));
     const int E = d->emb_size, H = d->common[0].out, A = d->action_net[0].out;
     twr_policy* p = new twr_policy();
@@ -372,10 +405,15 @@ int twr_policy_create(twr_engine* e, const twr_policy_desc* d, twr_policy** out)
     return TWR_OK;
 }
 
-int twr_policy_update(twr_policy* p, const twr_policy_desc* d) {
+int twr_policy_update(twr_policy* p, const twr_policy_desc* d_in) {
     if (!p) return fail(TWR_ERR_INVALID, "policy is NULL");
-    int rc = validate_desc(d);
+    if (!d_in) return fail(TWR_ERR_INVALID, "policy desc / embedding is NULL");
+    twr_policy_desc flat;
+    std::vector<float> table;
+    int rc = expand_conv1d(d_in, &flat, &table);
     if (rc) return rc;
+    const twr_policy_desc* d = &flat;
+    if ((rc = validate_desc(d))) return rc;
     CU_TRY(cudaSetDevice(p->eng->device));
     return upload_policy(p, d);
 }

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TWR_ABI_VERSION 1
+#define TWR_ABI_VERSION 2
 
 typedef enum {
     TWR_OK = 0,
@@ -233,14 +233,17 @@ int  twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p
                           const twr_policy_desc* desc, int64_t num_episodes, float gamma, float lambda,
                           const twr_host_buffers* dst, twr_collected* out);
 
-/* collector.evaluate (rust/src/rl/evaluate.rs:22-89, python_interface/env.rs:194-207) without MCTS:
+/* collector.evaluate (rust/src/rl/evaluate.rs:22-89, python_interface/env.rs:194-207).  With num_mcts_searches > 0
+ * every step's action distribution is predict_probs_mcts of the current state (rl/solve.rs:37-48) instead of Policy::predict:
  * num_episodes x [reset, best of num_searches rollouts of single_solve (rl/solve.rs:17-101)] run as one
  * device batch.  Returns (mean success, mean total reward) of the per-episode best (success, reward). */
 int  twr_evaluate(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes,
-                  int32_t deterministic, int32_t num_searches, float* success_rate, float* mean_reward);
+                  int32_t deterministic, int32_t num_searches, int32_t num_mcts_searches, float C,
+                  int32_t max_expand_depth, float* success_rate, float* mean_reward);
 /* collector.solve (rl/solve.rs:73-101) from the state held by the one-env batch `start`: best of
  * num_searches rollouts; writes its action list (actions may be NULL to only query the score). */
 int  twr_solve(twr_engine* e, twr_envs* start, const twr_policy* p, int32_t deterministic, int32_t num_searches,
+               int32_t num_mcts_searches, float C, int32_t max_expand_depth,
                float* success, float* reward, int32_t* actions, int32_t max_actions, int32_t* n_actions);
 
 /* AZCollector::collect (rust/src/collector/az.rs:112-130; python_interface/collector.rs:172-188): per record a

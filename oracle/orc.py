@@ -73,6 +73,12 @@ def lib():
                                 C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_int32)]
         L.orc_evaluate.argtypes = [C.POINTER(EnvSpec), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32,
                                    C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
+        L.orc_solve_mcts.argtypes = [C.POINTER(_Env), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32,
+                                     C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                     C.c_void_p, C.POINTER(C.c_int32)]
+        L.orc_evaluate_mcts.argtypes = [C.POINTER(EnvSpec), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                        C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float),
+                                        C.POINTER(C.c_float), C.c_void_p, C.c_void_p]
         L.orc_ppo_collect.argtypes = [C.POINTER(EnvSpec), C.c_void_p, C.c_int32, C.c_float, C.c_float,
                                       C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.POINTER(_Collected)]
     return _lib
@@ -309,12 +315,14 @@ def time_ppo_collect(spec: EnvSpec, policy: Policy, num_episodes, gamma, lam, se
     return n, dt
 
 
-def solve(env: Env, policy: Policy, deterministic, num_searches, seed=0, collect_id=0, id0=0):
+def solve(env: Env, policy: Policy, deterministic, num_searches, seed=0, collect_id=0, id0=0, num_mcts_searches=0,
+          c_puct=1.41, max_expand_depth=1):
     """((success, reward), actions) like collector.solve (rl/solve.rs:73-101), from the env's current state."""
     acts = np.zeros(4096, dtype=np.int32)
     s, r, n = C.c_float(), C.c_float(), C.c_int32()
-    lib().orc_solve(C.byref(env._e), policy._h, int(bool(deterministic)), int(num_searches), int(seed), int(collect_id),
-                    int(id0), C.byref(s), C.byref(r), acts.ctypes.data, C.byref(n))
+    lib().orc_solve_mcts(C.byref(env._e), policy._h, int(bool(deterministic)), int(num_searches), int(num_mcts_searches),
+                         float(c_puct), int(max_expand_depth), int(seed), int(collect_id),
+                         int(id0), C.byref(s), C.byref(r), acts.ctypes.data, C.byref(n))
     return (float(s.value), float(r.value)), acts[: n.value].tolist()
 
 
@@ -356,11 +364,12 @@ def az_collect(spec: EnvSpec, policy: Policy, num_episodes, n_sims, c_puct, max_
 
 
 def evaluate(spec: EnvSpec, policy: Policy, num_episodes, deterministic, num_searches, seed=0, collect_id=0,
-             reset_base=0, search_base=0):
+             reset_base=0, search_base=0, num_mcts_searches=0, c_puct=1.41, max_expand_depth=1):
     """(success_rate, mean_reward, per-episode best success, per-episode best reward) (rl/evaluate.rs:22-89)."""
     bs = np.zeros(num_episodes, dtype=np.float32); bt = np.zeros(num_episodes, dtype=np.float32)
     s, r = C.c_float(), C.c_float()
-    lib().orc_evaluate(C.byref(spec), policy._h, int(num_episodes), int(bool(deterministic)), int(num_searches), int(seed),
-                       int(collect_id), int(reset_base), int(search_base), C.byref(s), C.byref(r), bs.ctypes.data,
-                       bt.ctypes.data)
+    lib().orc_evaluate_mcts(C.byref(spec), policy._h, int(num_episodes), int(bool(deterministic)), int(num_searches),
+                            int(num_mcts_searches), float(c_puct), int(max_expand_depth), int(seed),
+                            int(collect_id), int(reset_base), int(search_base), C.byref(s), C.byref(r), bs.ctypes.data,
+                            bt.ctypes.data)
     return float(s.value), float(r.value), bs, bt

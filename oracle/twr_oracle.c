@@ -646,6 +646,12 @@ void orc_collected_free(orc_collected* c) {
 
 void orc_single_solve(orc_env* env, const orc_policy* p, int32_t deterministic, uint64_t seed, uint32_t collect_id,
                       uint32_t stream_id, float* success, float* total, int32_t* actions, int32_t* n_actions) {
+    orc_single_solve_mcts(env, p, deterministic, 0, 0.0f, 0, seed, collect_id, stream_id, success, total, actions, n_actions);
+}
+
+void orc_single_solve_mcts(orc_env* env, const orc_policy* p, int32_t deterministic, int32_t n_mcts, float C,
+                           int32_t max_expand_depth, uint64_t seed, uint32_t collect_id, uint32_t stream_id,
+                           float* success, float* total, int32_t* actions, int32_t* n_actions) {
     /* rl/solve.rs:17-71 */
     const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     const int nc = orc_env_num_cells(env), na = orc_env_num_actions(env);
@@ -665,7 +671,10 @@ void orc_single_solve(orc_env* env, const orc_policy* p, int32_t deterministic, 
             orc_philox4x32_10(ctr, key, w);
             perm = (int)mulhi32(w[0], (uint32_t)p->n_perms);
         }
-        orc_policy_predict(p, obs, nc, masks, perm, probs, &value);
+        if (n_mcts > 0)   /* solve.rs:40-47: predict_probs_mcts on a clone of the env */
+            orc_mcts_probs(env, p, n_mcts, C, max_expand_depth, seed, collect_id, stream_id, t, probs, NULL);
+        else
+            orc_policy_predict(p, obs, nc, masks, perm, probs, &value);
         int act = 0;
         if (deterministic) {
             act = orc_argmax(probs, na);
@@ -702,6 +711,12 @@ void orc_single_solve(orc_env* env, const orc_policy* p, int32_t deterministic, 
 
 void orc_solve(const orc_env* env, const orc_policy* p, int32_t deterministic, int32_t num_searches, uint64_t seed,
                uint32_t collect_id, uint32_t id0, float* success, float* total, int32_t* actions, int32_t* n_actions) {
+    orc_solve_mcts(env, p, deterministic, num_searches, 0, 0.0f, 0, seed, collect_id, id0, success, total, actions, n_actions);
+}
+
+void orc_solve_mcts(const orc_env* env, const orc_policy* p, int32_t deterministic, int32_t num_searches, int32_t n_mcts,
+                    float C, int32_t max_expand_depth, uint64_t seed, uint32_t collect_id, uint32_t id0, float* success,
+                    float* total, int32_t* actions, int32_t* n_actions) {
     /* rl/solve.rs:73-101: best = ((0, -inf), []) ; strict tuple '>' keeps the first best */
     float bs = 0.0f, br = -INFINITY;
     int bn = 0;
@@ -709,7 +724,7 @@ void orc_solve(const orc_env* env, const orc_policy* p, int32_t deterministic, i
     for (int s = 0; s < num_searches; ++s) {
         orc_env e = *env;
         float s1, r1; int32_t n1 = 0;
-        orc_single_solve(&e, p, deterministic, seed, collect_id, id0 + (uint32_t)s, &s1, &r1, tmp, &n1);
+        orc_single_solve_mcts(&e, p, deterministic, n_mcts, C, max_expand_depth, seed, collect_id, id0 + (uint32_t)s, &s1, &r1, tmp, &n1);
         if (s1 > bs || (s1 == bs && r1 > br)) {
             bs = s1; br = r1; bn = n1;
             if (actions) memcpy(actions, tmp, sizeof(int32_t) * (size_t)n1);
@@ -722,6 +737,14 @@ void orc_solve(const orc_env* env, const orc_policy* p, int32_t deterministic, i
 void orc_evaluate(const orc_env_spec* spec, const orc_policy* p, int32_t num_episodes, int32_t deterministic,
                   int32_t num_searches, uint64_t seed, uint32_t collect_id, uint32_t reset_base, uint32_t search_base,
                   float* success_rate, float* mean_reward, float* best_success, float* best_total) {
+    orc_evaluate_mcts(spec, p, num_episodes, deterministic, num_searches, 0, 0.0f, 0, seed, collect_id, reset_base, search_base,
+                      success_rate, mean_reward, best_success, best_total);
+}
+
+void orc_evaluate_mcts(const orc_env_spec* spec, const orc_policy* p, int32_t num_episodes, int32_t deterministic,
+                       int32_t num_searches, int32_t n_mcts, float C, int32_t max_expand_depth, uint64_t seed,
+                       uint32_t collect_id, uint32_t reset_base, uint32_t search_base, float* success_rate,
+                       float* mean_reward, float* best_success, float* best_total) {
     /* rl/evaluate.rs:22-48 (the serial branch; the rayon branch reduces the same per-episode values) */
     float succ = 0.0f, rew = 0.0f;
     for (int ep = 0; ep < num_episodes; ++ep) {
@@ -729,7 +752,8 @@ void orc_evaluate(const orc_env_spec* spec, const orc_policy* p, int32_t num_epi
         orc_env_init(&env, spec);
         orc_env_reset(&env, seed, reset_base + (uint32_t)ep, collect_id);
         float s1, r1;
-        orc_solve(&env, p, deterministic, num_searches, seed, collect_id, search_base + (uint32_t)(ep * num_searches), &s1, &r1, NULL, NULL);
+        orc_solve_mcts(&env, p, deterministic, num_searches, n_mcts, C, max_expand_depth, seed, collect_id,
+                       search_base + (uint32_t)(ep * num_searches), &s1, &r1, NULL, NULL);
         succ += s1; rew += r1;
         if (best_success) best_success[ep] = s1;
         if (best_total) best_total[ep] = r1;

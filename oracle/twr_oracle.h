@@ -148,6 +148,19 @@ void orc_evaluate(const orc_env_spec* spec, const orc_policy* p, int32_t num_epi
                   int32_t num_searches, uint64_t seed, uint32_t collect_id, uint32_t reset_base, uint32_t search_base,
                   float* success_rate, float* mean_reward, float* best_success, float* best_total);
 
+/* the same three with num_mcts_searches > 0: the action distribution of every step is predict_probs_mcts of the
+ * current state (solve.rs:40-47) on Philox stream (stream_id, t) */
+void orc_single_solve_mcts(orc_env* env, const orc_policy* p, int32_t deterministic, int32_t n_mcts, float C,
+                           int32_t max_expand_depth, uint64_t seed, uint32_t collect_id, uint32_t stream_id,
+                           float* success, float* total, int32_t* actions, int32_t* n_actions);
+void orc_solve_mcts(const orc_env* env, const orc_policy* p, int32_t deterministic, int32_t num_searches, int32_t n_mcts,
+                    float C, int32_t max_expand_depth, uint64_t seed, uint32_t collect_id, uint32_t id0, float* success,
+                    float* total, int32_t* actions, int32_t* n_actions);
+void orc_evaluate_mcts(const orc_env_spec* spec, const orc_policy* p, int32_t num_episodes, int32_t deterministic,
+                       int32_t num_searches, int32_t n_mcts, float C, int32_t max_expand_depth, uint64_t seed,
+                       uint32_t collect_id, uint32_t reset_base, uint32_t search_base, float* success_rate,
+                       float* mean_reward, float* best_success, float* best_total);
+
 /* ---- AlphaZero path (rust/src/rl/search.rs, rust/src/rl/tree.rs, rust/src/collector/az.rs) ---- */
 /* predict_probs_mcts (search.rs:104-189) from `env`; the child draw of simulation `sim`, expansion round d uses
  * Philox (stream_id, (t*(n_sims+1)+sim)*max(1,max_expand_depth)+d, MCTS, collect_id).  visits may be NULL. */

@@ -20,13 +20,13 @@ def eng():
     return tw.default_engine()
 
 
-def _evaluate(eng, env, pol, n, det, searches, cid):
+def _evaluate(eng, env, pol, n, det, searches, cid, mcts=0, c_puct=1.41, depth=1):
     from twisterl_b200 import _lib
     import twisterl_b200 as tw
     spec = tw.env.spec_from_env(env)
     s, r = C.c_float(), C.c_float()
     eng.set_collect_id(cid)
-    _lib.check(_lib.load().twr_evaluate(eng._h, C.byref(spec), pol.device_handle(eng), n, int(det), searches,
+    _lib.check(_lib.load().twr_evaluate(eng._h, C.byref(spec), pol.device_handle(eng), n, int(det), searches, mcts, c_puct, depth,
                                         C.byref(s), C.byref(r)))
     return float(s.value), float(r.value)
 
@@ -57,8 +57,7 @@ def test_evaluate_edge_cases_and_api(eng):
     assert tw.collector.evaluate(env, pol, 16, False, 1, 0, 0, 1.4, 1, 32) == (1.0, 1.0)
     s, r = _evaluate(eng, env, pol, 8, False, 0, cid=1)       # zero searches: solve()'s initial best
     assert s == 0.0 and r == float("-inf")
-    with pytest.raises(NotImplementedError):
-        tw.collector.evaluate(env, pol, 4, False, 1, 3, 0, 1.4, 1, 1)
+    assert tw.collector.evaluate(env, pol, 4, False, 1, 3, 0, 1.4, 1, 1) == (1.0, 1.0)     # MCTS-guided, already solved
     # keyword form used by rl/algorithm.py:98
     out = tw.collector.evaluate(env, pol, num_episodes=4, deterministic=True, num_searches=2, num_mcts_searches=0, seed=1,
                                 C=1.4, max_expand_depth=1, num_cores=4)
@@ -127,3 +126,40 @@ def test_collect_torch_device_handoff(eng):
     assert np.array_equal(t["rets"].cpu().numpy(), ref.additional_array("rets"))
     assert np.array_equal(t["perms"].cpu().numpy(), ref.perms_array.astype(np.int64))
     assert t["stats"]["records"] == len(ref.values_array)
+
+
+@pytest.mark.parametrize("det,searches,sims", [(True, 1, 24), (False, 2, 10)])
+def test_evaluate_with_mcts_matches_oracle(eng, det, searches, sims):
+    """defaults.py's "mcts_100" evaluation: single_solve takes its action distribution from predict_probs_mcts
+    (rl/solve.rs:37-48).  Same Philox streams on both sides; a flipped UCB near-tie can change single rollouts."""
+    import twisterl_b200 as tw
+    from parity import make_policies
+    pol, opol = make_policies(synth_state_dict(8, 81, 512, 256, 4), 81)
+    ospec = orc.puzzle_spec(3, 3, 4, 2, 256)
+    env = tw.env.Puzzle(3, 3, 4, 2, 256)
+    n = 96
+    s, r = _evaluate(eng, env, pol, n, det, searches, cid=13, mcts=sims, c_puct=1.41, depth=1)
+    os_, or_, _, _ = orc.evaluate(ospec, opol, n, det, searches, seed=eng.seed, collect_id=13, num_mcts_searches=sims,
+                                  c_puct=1.41, max_expand_depth=1)
+    assert abs(s - os_) <= 4.0 / n and abs(r - or_) <= 0.06
+    # the search must help: MCTS-guided evaluation solves at least as often as the raw synthetic policy
+    s0, _ = _evaluate(eng, env, pol, n, det, searches, cid=13)
+    assert s >= s0 - 2.0 / n
+
+
+def test_solve_with_mcts(eng):
+    import twisterl_b200 as tw
+    from parity import make_policies
+    _, sd = trained15()
+    pol, opol = make_policies(sd, 256)
+    env = tw.env.Puzzle(4, 4, 1, 2, 256)
+    start = [1, 5, 2, 3, 4, 0, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15]         # two moves from solved
+    env.set_state(start)
+    (succ, rew), acts = tw.collector.solve(env, pol, True, 1, 16, 1.41, 1)
+    oenv = orc.Env(orc.puzzle_spec(4, 4, 1, 2, 256)); oenv.set_state(start)
+    (os_, or_), oacts = orc.solve(oenv, opol, True, 1, seed=eng.seed, num_mcts_searches=16, c_puct=1.41, max_expand_depth=1)
+    assert succ == 1.0 and os_ == 1.0
+    assert acts == oacts and abs(rew - or_) < 1e-6
+    for a in acts:
+        oenv.step(a)
+    assert oenv.success()

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/twisterl_b200.h but not exported"
     assert declared == set(_lib.SYMBOLS)
-    assert L.twr_abi_version() == 1
+    assert L.twr_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():

@@ -53,3 +53,23 @@ def test_az_collect_structure():                      # collector/az.rs:51-130
         want = np.array([np.float32(tot - q) for q in prefix], dtype=np.float32)   # az.rs:93
         assert np.array_equal(want, d["remaining_values"][off:off + n])
         off += n
+
+
+def test_solve_with_mcts_searches():
+    """rl/solve.rs:37-48 with num_mcts_searches > 0: the per-step distribution is the MCTS visit distribution."""
+    from helpers import trained15
+    _, sd = trained15()
+    pol = orc.Policy.from_torch_state_dict(sd)
+    env = orc.Env(orc.puzzle_spec(4, 4, 1, 2, 256))
+    start = [1, 5, 2, 3, 4, 0, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15]
+    env.set_state(start)
+    (s, r), acts = orc.solve(env, pol, True, 1, seed=3, num_mcts_searches=16)
+    assert s == 1.0 and len(acts) >= 2
+    for a in acts:
+        env.step(a)
+    assert env.success()
+    # evaluation of a scrambled batch: MCTS guidance never lowers the success rate of this trained policy
+    spec = orc.puzzle_spec(4, 4, 3, 2, 256)
+    s0, _, _, _ = orc.evaluate(spec, pol, 24, True, 1, seed=5)
+    s1, _, _, _ = orc.evaluate(spec, pol, 24, True, 1, seed=5, num_mcts_searches=12)
+    assert s1 >= s0 - 1e-6

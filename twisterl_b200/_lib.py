@@ -127,8 +127,9 @@ def load():
         L.twr_max_records.argtypes = [C.POINTER(EnvSpec), C.c_int64]; L.twr_max_records.restype = C.c_int64
         L.twr_ppo_collect_host.argtypes = [vp, C.POINTER(EnvSpec), vp, C.POINTER(PolicyDesc), C.c_int64, C.c_float,
                                            C.c_float, C.POINTER(HostBuffers), C.POINTER(Collected)]
-        L.twr_evaluate.argtypes = [vp, C.POINTER(EnvSpec), vp, C.c_int64, C.c_int32, C.c_int32, f32p, f32p]
-        L.twr_solve.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, f32p, f32p, vp, C.c_int32, i32p]
+        L.twr_evaluate.argtypes = [vp, C.POINTER(EnvSpec), vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32,
+                                   f32p, f32p]
+        L.twr_solve.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, f32p, f32p, vp, C.c_int32, i32p]
         L.twr_az_collect.argtypes = [vp, C.POINTER(EnvSpec), vp, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.POINTER(Collected)]
         L.twr_mcts_probs.argtypes = [vp, vp, vp, C.c_int32, C.c_float, C.c_int32, C.c_uint32, C.c_uint32, C.c_int32, vp, vp]
         L.twr_host_alloc.argtypes = [C.POINTER(vp), C.c_int64]

@@ -240,16 +240,9 @@ class AZCollector(PyBaseCollector):
         return data
 
 
-def _no_mcts(num_mcts_searches):
-    if int(num_mcts_searches) != 0:
-        raise NotImplementedError("MCTS-guided solve/evaluate (num_mcts_searches > 0) is not implemented on the device "
-                                  "path yet; there is no CPU fallback")
-
-
 def solve(env, policy, deterministic, num_searches, num_mcts_searches, C, max_expand_depth):
     """`collector.solve` (python_interface/env.rs:180-191; rl/solve.rs:73-101): best of `num_searches` rollouts
     from the env's CURRENT state -> ((success, reward), actions)."""
-    _no_mcts(num_mcts_searches)
     spec_from_env(env)                       # rejects envs without a device implementation
     eng = _lib.default_engine()
     import ctypes as ct
@@ -260,6 +253,7 @@ def solve(env, policy, deterministic, num_searches, num_mcts_searches, C, max_ex
     acts = np.zeros(cap, dtype=np.int32)
     succ, rew, n = ct.c_float(), ct.c_float(), ct.c_int32()
     _lib.check(_lib.load().twr_solve(eng._h, batch._h, policy.device_handle(eng), int(bool(deterministic)), int(num_searches),
+                                     int(num_mcts_searches), float(C), int(max_expand_depth),
                                      ct.byref(succ), ct.byref(rew), _lib.ptr(acts), cap, ct.byref(n)))
     return (float(succ.value), float(rew.value)), [int(a) for a in acts[: n.value]]
 
@@ -268,11 +262,11 @@ def evaluate(env, policy, num_episodes, deterministic, num_searches, num_mcts_se
              num_cores):
     """`collector.evaluate` (python_interface/env.rs:194-207; rl/evaluate.rs:22-89) -> (success rate, mean reward).
     `seed` is ignored like in the reference; `num_cores` is accepted for compatibility."""
-    _no_mcts(num_mcts_searches)
     spec = spec_from_env(env)
     eng = _lib.default_engine()
     import ctypes as ct
     s, r = ct.c_float(), ct.c_float()
     _lib.check(_lib.load().twr_evaluate(eng._h, ct.byref(spec), policy.device_handle(eng), int(num_episodes),
-                                        int(bool(deterministic)), int(num_searches), ct.byref(s), ct.byref(r)))
+                                        int(bool(deterministic)), int(num_searches), int(num_mcts_searches), float(C),
+                                        int(max_expand_depth), ct.byref(s), ct.byref(r)))
     return float(s.value), float(r.value)

@@ -1011,135 +1011,7 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
 }
 
 
-// ------------------------------------------------------------ evaluate / solve (f1) ---
-// Shared driver: B envs already initialised in (cells, meta); runs single_solve (rl/solve.rs:17-71) for all of
-// them in lockstep.  Fills total[B], success[B], n_steps[B] and (optionally) the per-step action record.
-static int run_solve(twr_engine* e, const EnvParams& env, const PolicyDev& dev, int64_t B, int T, EnvIds ids, uint32_t cid,
-                     int deterministic, uint4* cells, uint32_t* meta, float* total, uint8_t* success, int32_t* n_steps,
-                     uint8_t* act_rec) {
-    Staging<int32_t> live_a, live_b, n_live;
-    Staging<float4> logits; Staging<float> values;
-    int rc;
-    if ((rc = live_a.alloc((size_t)B)) || (rc = live_b.alloc((size_t)B)) || (rc = n_live.alloc((size_t)T + 2)) ||
-        (rc = logits.alloc((size_t)B)) || (rc = values.alloc((size_t)B))) return rc;
-    cudaStream_t st = e->stream;
-    std::vector<int32_t> iota((size_t)B);
-    for (int64_t i = 0; i < B; ++i) iota[(size_t)i] = (int32_t)i;
-    CU_TRY(cudaMemcpyAsync(live_a.d, iota.data(), sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemsetAsync(n_live.d, 0, sizeof(int32_t) * (size_t)(T + 2), st));
-    const int32_t b32 = (int32_t)B;
-    CU_TRY(cudaMemcpyAsync(n_live.d, &b32, sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemsetAsync(total, 0, sizeof(float) * (size_t)B, st));
-    CU_TRY(cudaMemsetAsync(success, 0, (size_t)B, st));
-    CU_TRY(cudaMemsetAsync(n_steps, 0, sizeof(int32_t) * (size_t)B, st));
-    ForwardArgs fa{};
-    fa.env = env; fa.seed = e->seed; fa.cid = cid; fa.ids = ids; fa.cells = cells; fa.n = B;
-    fa.logits = logits.d; fa.values = values.d;
-    SolveArgs sa{};
-    sa.env = env; sa.seed = e->seed; sa.cid = cid; sa.ids = ids; sa.A = dev.A; sa.deterministic = deterministic; sa.B = B;
-    sa.cells = cells; sa.meta = meta; sa.logits = logits.d; sa.n_live = n_live.d; sa.total = total; sa.success = success;
-    sa.act_rec = act_rec; sa.n_steps = n_steps;
-    for (int t = 0; t <= T; ++t) {          // at most T steps, then the terminal visit
-        int32_t* cur = (t & 1) ? live_b.d : live_a.d;
-        int32_t* nxt = (t & 1) ? live_a.d : live_b.d;
-        fa.t = t; fa.live = cur; fa.n_live_ptr = n_live.d + t;
-        launch_forward(e, dev, fa);
-        sa.t = t;
-        launch_solve_step(st, sa, cur, nxt);
-    }
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaStreamSynchronize(st));       // staging buffers are freed on return
-    return TWR_OK;
-}
-
-int twr_evaluate(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, int32_t deterministic,
-                 int32_t num_searches, float* success_rate, float* mean_reward) {
-    if (!success_rate || !mean_reward) return fail(TWR_ERR_INVALID, "NULL argument");
-    CollectPlan plan;
-    if (num_episodes <= 0) { *success_rate = NAN; *mean_reward = NAN; return TWR_OK; }   // 0/0 in rl/evaluate.rs:47
-    int rc = plan_collect(e, spec, p, num_episodes, &plan);
-    if (rc) return rc;
-    if (num_searches < 0) return fail(TWR_ERR_INVALID, "num_searches must be >= 0");
-    const int S = num_searches;
-    if (S == 0) { *success_rate = 0.0f; *mean_reward = -INFINITY; return TWR_OK; }       // solve() returns its initial best
-    const int64_t B = num_episodes * S;
-    if (B >= (1ll << 31)) return fail(TWR_ERR_INVALID, "num_episodes * num_searches too large");
-    CU_TRY(cudaSetDevice(e->device));
-    Staging<uint4> cells; Staging<uint32_t> meta; Staging<float> total; Staging<uint8_t> success; Staging<int32_t> n_steps;
-    if ((rc = cells.alloc((size_t)B)) || (rc = meta.alloc((size_t)B)) || (rc = total.alloc((size_t)B)) ||
-        (rc = success.alloc((size_t)B)) || (rc = n_steps.alloc((size_t)B))) return rc;
-    const uint32_t cid = e->collect_id++;
-    const uint32_t base = (uint32_t)((int64_t)e->rank * num_episodes);
-    // every search of an episode starts from the same reset state (evaluate.rs:29-31 resets once, solve clones)
-    EnvIds reset_ids{base, 0u, 0u, (uint32_t)S};
-    launch_envs_reset(e->stream, plan.env, cells.d, meta.d, B, e->seed, reset_ids, cid, nullptr, nullptr);
-    EnvIds ids{(uint32_t)((int64_t)e->rank * B), 0u, 0u, 0u};
-    if ((rc = run_solve(e, plan.env, plan.dev, B, plan.T, ids, cid, deterministic, cells.d, meta.d, total.d, success.d,
-                        n_steps.d, nullptr))) return rc;
-    std::vector<float> h_total((size_t)B); std::vector<uint8_t> h_succ((size_t)B);
-    CU_TRY(cudaMemcpy(h_total.data(), total.d, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(h_succ.data(), success.d, (size_t)B, cudaMemcpyDeviceToHost));
-    float succ = 0.0f, rew = 0.0f;
-    for (int64_t ep = 0; ep < num_episodes; ++ep) {
-        float bs = 0.0f, br = -INFINITY;                       // solve.rs:82: best = ((0.0, -inf), [])
-        for (int sidx = 0; sidx < S; ++sidx) {
-            const float s1 = h_succ[(size_t)(ep * S + sidx)] ? 1.0f : 0.0f, r1 = h_total[(size_t)(ep * S + sidx)];
-            if (s1 > bs || (s1 == bs && r1 > br)) { bs = s1; br = r1; }   // tuple '>' (lexicographic), solve.rs:94
-        }
-        succ += bs; rew += br;
-    }
-    *success_rate = succ / (float)num_episodes;
-    *mean_reward = rew / (float)num_episodes;
-    return TWR_OK;
-}
-
-int twr_solve(twr_engine* e, twr_envs* start, const twr_policy* p, int32_t deterministic, int32_t num_searches,
-              float* success, float* reward, int32_t* actions, int32_t max_actions, int32_t* n_actions) {
-    if (!e || !start || !p || !success || !reward || !n_actions) return fail(TWR_ERR_INVALID, "NULL argument");
-    if (start->eng != e || p->eng != e) return fail(TWR_ERR_INVALID, "envs/policy belong to another engine");
-    if (start->n != 1) return fail(TWR_ERR_INVALID, "twr_solve needs a batch of exactly one env holding the start state");
-    *success = 0.0f; *reward = -INFINITY; *n_actions = 0;
-    if (num_searches <= 0) return TWR_OK;
-    PolicyDev dev;
-    int rc = check_policy_env(p, start->p, &dev);
-    if (rc) return rc;
-    CU_TRY(cudaSetDevice(e->device));
-    int32_t depth = 0;
-    if ((rc = twr_envs_depth(start, &depth))) return rc;
-    const int T = depth;                                       // every step burns one unit of budget
-    const int64_t B = num_searches;
-    Staging<uint4> cells; Staging<uint32_t> meta; Staging<float> total; Staging<uint8_t> succ, act; Staging<int32_t> n_steps;
-    if ((rc = cells.alloc((size_t)B)) || (rc = meta.alloc((size_t)B)) || (rc = total.alloc((size_t)B)) ||
-        (rc = succ.alloc((size_t)B)) || (rc = n_steps.alloc((size_t)B)) || (rc = act.alloc((size_t)B * (size_t)(T + 1)))) return rc;
-    launch_envs_broadcast(e->stream, start->cells, start->meta, cells.d, meta.d, B);
-    const uint32_t cid = e->collect_id++;
-    EnvIds ids{0x50000000u, 0u, 0u, 0u};
-    if ((rc = run_solve(e, start->p, dev, B, T, ids, cid, deterministic, cells.d, meta.d, total.d, succ.d, n_steps.d, act.d))) return rc;
-    std::vector<float> h_total((size_t)B); std::vector<uint8_t> h_succ((size_t)B); std::vector<int32_t> h_n((size_t)B);
-    CU_TRY(cudaMemcpy(h_total.data(), total.d, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(h_succ.data(), succ.d, (size_t)B, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(h_n.data(), n_steps.d, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost));
-    float bs = 0.0f, br = -INFINITY; int best = -1;
-    for (int64_t i = 0; i < B; ++i) {
-        const float s1 = h_succ[(size_t)i] ? 1.0f : 0.0f, r1 = h_total[(size_t)i];
-        if (s1 > bs || (s1 == bs && r1 > br)) { bs = s1; br = r1; best = (int)i; }
-    }
-    *success = bs; *reward = br;
-    if (best >= 0) {
-        const int n = h_n[(size_t)best];
-        *n_actions = n;
-        if (actions) {
-            if (n > max_actions) return fail(TWR_ERR_INVALID, "actions buffer too small");
-            std::vector<uint8_t> col((size_t)(T + 1) * (size_t)B);
-            CU_TRY(cudaMemcpy(col.data(), act.d, col.size(), cudaMemcpyDeviceToHost));
-            for (int t = 0; t < n; ++t) actions[t] = col[(size_t)t * (size_t)B + (size_t)best];
-        }
-    }
-    return TWR_OK;
-}
-
-
-// ------------------------------------------------------------- AlphaZero (K6) ---
+// ------------------------------------------------ batched MCTS driver (K6; also used by solve/evaluate) ---
 struct MctsMem {
     Staging<uint4> cells; Staging<uint32_t> meta; Staging<int32_t> parent, first_child, n_nodes, fwd_list, fwd_env, fwd_count, cur_node;
     Staging<uint8_t> n_children, action, active; Staging<float> prior, value_sum, cur_value; Staging<uint32_t> visits;
@@ -1187,6 +1059,173 @@ static void enqueue_mcts(twr_engine* e, const PolicyDev& dev, MctsArgs& a, const
     }
 }
 
+
+// ------------------------------------------------------------ evaluate / solve (f1) ---
+// Shared driver: B envs already initialised in (cells, meta); runs single_solve (rl/solve.rs:17-71) for all of
+// them in lockstep.  Fills total[B], success[B], n_steps[B] and (optionally) the per-step action record.
+struct MctsOpt { int n_sims; float C; int max_expand_depth; };
+
+static int run_solve(twr_engine* e, const EnvParams& env, const PolicyDev& dev, int64_t B, int T, EnvIds ids, uint32_t cid,
+                     int deterministic, MctsOpt mo, uint4* cells, uint32_t* meta, float* total, uint8_t* success, int32_t* n_steps,
+                     uint8_t* act_rec) {
+    Staging<int32_t> live_a, live_b, n_live;
+    Staging<float4> logits; Staging<float> values;
+    int rc;
+    // num_mcts_searches > 0: every step's action distribution is predict_probs_mcts of the current state
+    MctsArgs ma{};
+    MctsMem mem;
+    Staging<float> mcts_probs; Staging<int32_t> mcts_vis;
+    if (mo.n_sims > 0) {
+        if (dev.n_perms > 0) return fail(TWR_ERR_UNSUPPORTED, "MCTS with twists (full_predict over all perms) is not implemented; the AZ trainer clears them (rl/az.py:24-26)");
+        const int P = mcts_pool_nodes(dev.A, mo.n_sims, mo.max_expand_depth);
+        if ((double)B * P >= 2147483647.0) return fail(TWR_ERR_INVALID, "MCTS node pool too large");
+        ma.pool.A = dev.A;
+        if ((rc = mem.alloc(B, P, &ma.pool, &ma)) || (rc = mcts_probs.alloc((size_t)B * dev.A)) || (rc = mcts_vis.alloc((size_t)B * dev.A))) return rc;
+    }
+    if ((rc = live_a.alloc((size_t)B)) || (rc = live_b.alloc((size_t)B)) || (rc = n_live.alloc((size_t)T + 2)) ||
+        (rc = logits.alloc((size_t)B)) || (rc = values.alloc((size_t)B))) return rc;
+    cudaStream_t st = e->stream;
+    std::vector<int32_t> iota((size_t)B);
+    for (int64_t i = 0; i < B; ++i) iota[(size_t)i] = (int32_t)i;
+    CU_TRY(cudaMemcpyAsync(live_a.d, iota.data(), sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(n_live.d, 0, sizeof(int32_t) * (size_t)(T + 2), st));
+    const int32_t b32 = (int32_t)B;
+    CU_TRY(cudaMemcpyAsync(n_live.d, &b32, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(total, 0, sizeof(float) * (size_t)B, st));
+    CU_TRY(cudaMemsetAsync(success, 0, (size_t)B, st));
+    CU_TRY(cudaMemsetAsync(n_steps, 0, sizeof(int32_t) * (size_t)B, st));
+    ForwardArgs fa{};
+    fa.env = env; fa.seed = e->seed; fa.cid = cid; fa.ids = ids; fa.cells = cells; fa.n = B;
+    fa.logits = logits.d; fa.values = values.d;
+    SolveArgs sa{};
+    sa.env = env; sa.seed = e->seed; sa.cid = cid; sa.ids = ids; sa.A = dev.A; sa.deterministic = deterministic; sa.B = B;
+    sa.cells = cells; sa.meta = meta; sa.logits = logits.d; sa.n_live = n_live.d; sa.total = total; sa.success = success;
+    sa.act_rec = act_rec; sa.n_steps = n_steps;
+    if (mo.n_sims > 0) {
+        ma.env = env; ma.seed = e->seed; ma.cid = cid; ma.ids = ids; ma.n_sims = mo.n_sims;
+        ma.max_expand_depth = mo.max_expand_depth; ma.C = mo.C;
+        ma.env_cells = cells; ma.env_meta = meta; ma.logits = logits.d; ma.values = values.d;
+        sa.mcts_probs = mcts_probs.d;
+    }
+    for (int t = 0; t <= T; ++t) {          // at most T steps, then the terminal visit
+        int32_t* cur = (t & 1) ? live_b.d : live_a.d;
+        int32_t* nxt = (t & 1) ? live_a.d : live_b.d;
+        if (mo.n_sims > 0) {
+            ma.t = t;
+            enqueue_mcts(e, dev, ma, cur, n_live.d + t, B);
+            launch_mcts_read(st, ma, B, mcts_probs.d, mcts_vis.d);
+        } else {
+            fa.t = t; fa.live = cur; fa.n_live_ptr = n_live.d + t;
+            launch_forward(e, dev, fa);
+        }
+        sa.t = t;
+        launch_solve_step(st, sa, cur, nxt);
+        if (mo.n_sims > 0 && (t & 3) == 3) {     // MCTS steps are expensive: stop once every rollout has ended
+            int32_t left = 0;
+            CU_TRY(cudaMemcpyAsync(&left, n_live.d + t + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            if (left == 0) break;
+        }
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));       // staging buffers are freed on return
+    return TWR_OK;
+}
+
+int twr_evaluate(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, int32_t deterministic,
+                 int32_t num_searches, int32_t num_mcts_searches, float C, int32_t max_expand_depth,
+                 float* success_rate, float* mean_reward) {
+    if (!success_rate || !mean_reward) return fail(TWR_ERR_INVALID, "NULL argument");
+    if (num_mcts_searches < 0 || max_expand_depth < 0) return fail(TWR_ERR_INVALID, "negative argument");
+    const MctsOpt mo{num_mcts_searches, C, max_expand_depth};
+    CollectPlan plan;
+    if (num_episodes <= 0) { *success_rate = NAN; *mean_reward = NAN; return TWR_OK; }   // 0/0 in rl/evaluate.rs:47
+    int rc = plan_collect(e, spec, p, num_episodes, &plan);
+    if (rc) return rc;
+    if (num_searches < 0) return fail(TWR_ERR_INVALID, "num_searches must be >= 0");
+    const int S = num_searches;
+    if (S == 0) { *success_rate = 0.0f; *mean_reward = -INFINITY; return TWR_OK; }       // solve() returns its initial best
+    const int64_t B = num_episodes * S;
+    if (B >= (1ll << 31)) return fail(TWR_ERR_INVALID, "num_episodes * num_searches too large");
+    CU_TRY(cudaSetDevice(e->device));
+    Staging<uint4> cells; Staging<uint32_t> meta; Staging<float> total; Staging<uint8_t> success; Staging<int32_t> n_steps;
+    if ((rc = cells.alloc((size_t)B)) || (rc = meta.alloc((size_t)B)) || (rc = total.alloc((size_t)B)) ||
+        (rc = success.alloc((size_t)B)) || (rc = n_steps.alloc((size_t)B))) return rc;
+    const uint32_t cid = e->collect_id++;
+    const uint32_t base = (uint32_t)((int64_t)e->rank * num_episodes);
+    // every search of an episode starts from the same reset state (evaluate.rs:29-31 resets once, solve clones)
+    EnvIds reset_ids{base, 0u, 0u, (uint32_t)S};
+    launch_envs_reset(e->stream, plan.env, cells.d, meta.d, B, e->seed, reset_ids, cid, nullptr, nullptr);
+    EnvIds ids{(uint32_t)((int64_t)e->rank * B), 0u, 0u, 0u};
+    if ((rc = run_solve(e, plan.env, plan.dev, B, plan.T, ids, cid, deterministic, mo, cells.d, meta.d, total.d, success.d,
+                        n_steps.d, nullptr))) return rc;
+    std::vector<float> h_total((size_t)B); std::vector<uint8_t> h_succ((size_t)B);
+    CU_TRY(cudaMemcpy(h_total.data(), total.d, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(h_succ.data(), success.d, (size_t)B, cudaMemcpyDeviceToHost));
+    float succ = 0.0f, rew = 0.0f;
+    for (int64_t ep = 0; ep < num_episodes; ++ep) {
+        float bs = 0.0f, br = -INFINITY;                       // solve.rs:82: best = ((0.0, -inf), [])
+        for (int sidx = 0; sidx < S; ++sidx) {
+            const float s1 = h_succ[(size_t)(ep * S + sidx)] ? 1.0f : 0.0f, r1 = h_total[(size_t)(ep * S + sidx)];
+            if (s1 > bs || (s1 == bs && r1 > br)) { bs = s1; br = r1; }   // tuple '>' (lexicographic), solve.rs:94
+        }
+        succ += bs; rew += br;
+    }
+    *success_rate = succ / (float)num_episodes;
+    *mean_reward = rew / (float)num_episodes;
+    return TWR_OK;
+}
+
+int twr_solve(twr_engine* e, twr_envs* start, const twr_policy* p, int32_t deterministic, int32_t num_searches,
+              int32_t num_mcts_searches, float C, int32_t max_expand_depth,
+              float* success, float* reward, int32_t* actions, int32_t max_actions, int32_t* n_actions) {
+    if (!e || !start || !p || !success || !reward || !n_actions) return fail(TWR_ERR_INVALID, "NULL argument");
+    if (num_mcts_searches < 0 || max_expand_depth < 0) return fail(TWR_ERR_INVALID, "negative argument");
+    const MctsOpt mo{num_mcts_searches, C, max_expand_depth};
+    if (start->eng != e || p->eng != e) return fail(TWR_ERR_INVALID, "envs/policy belong to another engine");
+    if (start->n != 1) return fail(TWR_ERR_INVALID, "twr_solve needs a batch of exactly one env holding the start state");
+    *success = 0.0f; *reward = -INFINITY; *n_actions = 0;
+    if (num_searches <= 0) return TWR_OK;
+    PolicyDev dev;
+    int rc = check_policy_env(p, start->p, &dev);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(e->device));
+    int32_t depth = 0;
+    if ((rc = twr_envs_depth(start, &depth))) return rc;
+    const int T = depth;                                       // every step burns one unit of budget
+    const int64_t B = num_searches;
+    Staging<uint4> cells; Staging<uint32_t> meta; Staging<float> total; Staging<uint8_t> succ, act; Staging<int32_t> n_steps;
+    if ((rc = cells.alloc((size_t)B)) || (rc = meta.alloc((size_t)B)) || (rc = total.alloc((size_t)B)) ||
+        (rc = succ.alloc((size_t)B)) || (rc = n_steps.alloc((size_t)B)) || (rc = act.alloc((size_t)B * (size_t)(T + 1)))) return rc;
+    launch_envs_broadcast(e->stream, start->cells, start->meta, cells.d, meta.d, B);
+    const uint32_t cid = e->collect_id++;
+    EnvIds ids{0x50000000u, 0u, 0u, 0u};
+    if ((rc = run_solve(e, start->p, dev, B, T, ids, cid, deterministic, mo, cells.d, meta.d, total.d, succ.d, n_steps.d, act.d))) return rc;
+    std::vector<float> h_total((size_t)B); std::vector<uint8_t> h_succ((size_t)B); std::vector<int32_t> h_n((size_t)B);
+    CU_TRY(cudaMemcpy(h_total.data(), total.d, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(h_succ.data(), succ.d, (size_t)B, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(h_n.data(), n_steps.d, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost));
+    float bs = 0.0f, br = -INFINITY; int best = -1;
+    for (int64_t i = 0; i < B; ++i) {
+        const float s1 = h_succ[(size_t)i] ? 1.0f : 0.0f, r1 = h_total[(size_t)i];
+        if (s1 > bs || (s1 == bs && r1 > br)) { bs = s1; br = r1; best = (int)i; }
+    }
+    *success = bs; *reward = br;
+    if (best >= 0) {
+        const int n = h_n[(size_t)best];
+        *n_actions = n;
+        if (actions) {
+            if (n > max_actions) return fail(TWR_ERR_INVALID, "actions buffer too small");
+            std::vector<uint8_t> col((size_t)(T + 1) * (size_t)B);
+            CU_TRY(cudaMemcpy(col.data(), act.d, col.size(), cudaMemcpyDeviceToHost));
+            for (int t = 0; t < n; ++t) actions[t] = col[(size_t)t * (size_t)B + (size_t)best];
+        }
+    }
+    return TWR_OK;
+}
+
+
+// ------------------------------------------------------------- AlphaZero (K6) ---
 int twr_mcts_probs(twr_engine* e, const twr_policy* p, twr_envs* v, int32_t n_sims, float C, int32_t max_expand_depth,
                    uint32_t env_id_base, uint32_t collect_id, int32_t t, float* probs, int32_t* visits) {
     if (!e || !p || !v || !probs || !visits) return fail(TWR_ERR_INVALID, "NULL argument");

@@ -458,14 +458,20 @@ __global__ void __launch_bounds__(256) k_solve_step(SolveArgs a, const int32_t* 
             a.success[e] = env_success(a.env, s) ? 1 : 0;
             a.n_steps[e] = a.t;
         } else {
-            const uint32_t m = env_masks(a.env, s);
-            const float4 raw = a.logits[pos];
-            const float l[4] = {raw.x, raw.y, raw.z, raw.w};
-            float pr[4], sum = 0.0f;
+            float pr[4];
+            if (a.mcts_probs) {                     // solve.rs:37-48: probs come from predict_probs_mcts on a clone
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { pr[i] = (i < a.A && ((m >> i) & 1u)) ? expf(l[i]) : 0.0f; sum += pr[i]; }
+                for (int i = 0; i < 4; ++i) pr[i] = i < a.A ? a.mcts_probs[(int64_t)e * a.A + i] : 0.0f;
+            } else {
+                const uint32_t m = env_masks(a.env, s);
+                const float4 raw = a.logits[pos];
+                const float l[4] = {raw.x, raw.y, raw.z, raw.w};
+                float sum = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) pr[i] = pr[i] / (sum + 0.000001f);
+                for (int i = 0; i < 4; ++i) { pr[i] = (i < a.A && ((m >> i) & 1u)) ? expf(l[i]) : 0.0f; sum += pr[i]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pr[i] = pr[i] / (sum + 0.000001f);
+            }
             int act = 0;
             if (a.deterministic) {
                 float bv = pr[0];

@@ -118,6 +118,7 @@ struct SolveArgs {
     uint4* cells; uint32_t* meta; const float4* logits; int32_t* n_live;   // n_live[t], n_live[t+1]
     float* total; uint8_t* success; uint8_t* act_rec;  // act_rec [T][B] or NULL
     int32_t* n_steps;   // [B] number of actions taken
+    const float* mcts_probs;   // [B][A] root visit distribution of predict_probs_mcts, or NULL -> Policy::predict of `logits`
 };
 void launch_solve_step(cudaStream_t s, const SolveArgs& a, const int32_t* live_cur, int32_t* live_next);
 void launch_envs_broadcast(cudaStream_t s, const uint4* src_cells, const uint32_t* src_meta, uint4* cells, uint32_t* meta, int64_t n);

@@ -44,7 +44,9 @@ typedef enum { TWR_ENV_PUZZLE = 0, TWR_ENV_GRIDWORLD = 1 } twr_env_kind;
 /* arithmetic of the policy forward (kernel K2) */
 typedef enum {
     TWR_PREC_FP32 = 0,  /* SIMT fp32 FMA; parity bar 1e-5 */
-    TWR_PREC_F16X2 = 1  /* tcgen05, operands split into fp16 hi+lo, fp32 TMEM accumulate; bar 1e-3 */
+    TWR_PREC_F16X2 = 1  /* tcgen05, operands split into fp16 hi+lo, fp32 TMEM accumulate; bar 1e-3 (1e-5 measured).
+                         * Policies whose shape does not fit the tensor-core kernel (obs_size > 256, e.g. GridWorld 5x5)
+                         * and multiset observations run the fp32 SIMT kernel on the same engine. */
 } twr_precision;
 
 typedef struct twr_engine twr_engine;

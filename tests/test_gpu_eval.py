@@ -64,9 +64,8 @@ def test_evaluate_edge_cases_and_api(eng):
     assert out == (1.0, 1.0)
     g = tw.env.GridWorld(5, 5, 64, 6)
     gp, _ = make_policies(synth_state_dict(5, 625, 512, 128, 4), 625)
-    if PRECISION == "fp32":
-        s, r = tw.collector.evaluate(g, gp, 64, False, 2, 0, 0, 1.4, 1, 1)
-        assert 0.0 <= s <= 1.0 and -40.0 < r <= 1.0
+    s, r = tw.collector.evaluate(g, gp, 64, False, 2, 0, 0, 1.4, 1, 1)    # 625-row table: fp32 kernel on either engine
+    assert 0.0 <= s <= 1.0 and -40.0 < r <= 1.0
 
 
 def test_solve_matches_oracle_and_replays(eng):

@@ -165,8 +165,6 @@ def test_forward_twists_match_reference_torch_golden(eng):
 
 @pytest.mark.parametrize("name,N,kind", [("puzzle8", 9, 0), ("gridworld", 25, 1)])
 def test_forward_other_config_shapes(eng, name, N, kind):
-    if PRECISION == "f16x2" and N * N > 256:
-        pytest.skip("tensor-core forward holds the one-hot operand in 64 KB of shared memory: obs_size <= 256")
     from parity import make_policies
     from twisterl_b200.env import EnvBatch
     from twisterl_b200.nn import forward_batch
@@ -296,8 +294,6 @@ CASES = [
 
 @pytest.mark.parametrize("name,ospec,obs_size,hidden,episodes,twists", CASES, ids=[c[0] for c in CASES])
 def test_collect_replays_through_oracle(eng, name, ospec, obs_size, hidden, episodes, twists):
-    if PRECISION == "f16x2" and obs_size > 256:
-        pytest.skip("tensor-core forward holds the one-hot operand in 64 KB of shared memory: obs_size <= 256")
     import twisterl_b200 as tw
     from parity import check_collect_against_oracle, make_policies
     if obs_size == 256:
@@ -520,3 +516,18 @@ def test_conv1d_policy_forward_and_collect(eng, conv_dim):
     l2, _ = forward_obs(eng, pol2, obs[:8], None)
     ref = np.array([opol2.raw_predict(o)[0] for o in obs[:8]])
     assert _close(l2, ref, TOL)
+
+
+def test_forward_obs_multiset_and_wide_tables_use_the_fp32_kernel(eng):
+    """EmbeddingBag sums repeated indices (layers.rs:58-62); the one-hot tensor-core operand cannot, so such calls --
+    and tables wider than 256 rows -- must run the fp32 kernel on an f16x2 engine instead of failing."""
+    from parity import make_policies
+    from twisterl_b200.nn import forward_obs
+    _, sd = trained15()
+    pol, opol = make_policies(sd, 256)
+    obs = np.array([[3, 3, 17, 40, 41, 42, 43, 44, 45, 46, 47, 48, 49, 50, 51, 255],
+                    [0, 17, 34, 51, 68, 85, 102, 119, 136, 153, 170, 187, 204, 221, 238, 255]], np.int32)
+    l, v = forward_obs(eng, pol, obs, None)
+    for k in range(2):
+        rl, rv = opol.raw_predict(obs[k].tolist())
+        assert _close(l[k], rl, TOL) and abs(v[k] - rv) <= TOL * max(1.0, abs(rv))

@@ -153,7 +153,7 @@ def ptr(a: np.ndarray):
 class Engine:
     """One engine per CUDA device (twr_engine)."""
 
-    def __init__(self, device: int = 0, precision: str | int = "fp32", seed: int = 0x5EED5EED, rank: int = 0,
+    def __init__(self, device: int = 0, precision: str | int = "f16x2", seed: int = 0x5EED5EED, rank: int = 0,
                  world: int = 1, stream: int | None = None):
         L = load()
         prec = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
@@ -207,7 +207,7 @@ def default_engine() -> Engine:
     global _default_engine
     if _default_engine is None:
         cfg = dict(device=int(os.environ.get("TWISTERL_B200_DEVICE", os.environ.get("LOCAL_RANK", "0"))),
-                   precision=os.environ.get("TWISTERL_B200_PRECISION", "fp32"),
+                   precision=os.environ.get("TWISTERL_B200_PRECISION", "f16x2"),
                    seed=int(os.environ.get("TWISTERL_B200_SEED", str(0x5EED5EED)), 0))
         cfg.update(_default_cfg)
         _default_engine = Engine(**cfg)

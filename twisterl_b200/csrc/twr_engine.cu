@@ -375,14 +375,19 @@ int twr_policy_create(twr_engine* e, const twr_policy_desc* d_in, twr_policy** o
     p->off_wv = off; off += H;
     p->off_bv = off; off += 1;
     p->blob_floats = off;
+    bool use_tc = false;
     {
         PolicyDev probe = p->dev;
         probe.n_obs = 1;
         EnvParams dummy{};
         const char* why = "";
-        const int ok = e->precision == TWR_PREC_F16X2 ? forward_tc_supported(probe, dummy, &why)
-                                                       : forward_fp32_supported(probe, dummy, &why);
-        if (!ok) { delete p; return fail(TWR_ERR_UNSUPPORTED, std::string("policy shape not supported on the device: ") + why); }
+        // TWR_PREC_F16X2 = tensor cores where the shape fits the tcgen05 kernel (obs_size <= 256, E % 128 == 0, H in
+        // {128, 256}); other shapes (GridWorld's 625-row table) run the fp32 SIMT kernel -- still on the device.
+        use_tc = e->precision == TWR_PREC_F16X2 && forward_tc_supported(probe, dummy, &why);
+        if (!use_tc && !forward_fp32_supported(probe, dummy, &why)) {
+            delete p;
+            return fail(TWR_ERR_UNSUPPORTED, std::string("policy shape not supported on the device: ") + why);
+        }
     }
     if ((rc = dev_alloc(&p->d_blob, (size_t)p->blob_floats))) { delete p; return rc; }
     if (d->n_perms > 0) {
@@ -394,7 +399,7 @@ int twr_policy_create(twr_engine* e, const twr_policy_desc* d_in, twr_policy** o
     p->dev.wa = p->d_blob + p->off_wa; p->dev.ba = p->d_blob + p->off_ba;
     p->dev.wv = p->d_blob + p->off_wv; p->dev.bv = p->d_blob + p->off_bv;
     p->dev.obs_perms = p->d_obs_perms; p->dev.act_perms = p->d_act_perms;
-    if (e->precision == TWR_PREC_F16X2) {
+    if (use_tc) {
         const size_t bytes = forward_tc_pack_bytes(p->dev);
         cudaError_t ce = cudaMalloc(&p->tc_pack, bytes);
         if (ce != cudaSuccess) { twr_policy_destroy(p); return fail(TWR_ERR_CUDA, cudaGetErrorString(ce)); }
@@ -552,7 +557,7 @@ static int check_policy_env(const twr_policy* p, const EnvParams& env, PolicyDev
 }
 
 static void launch_forward(twr_engine* e, const PolicyDev& dev, const ForwardArgs& a) {
-    if (e->precision == TWR_PREC_F16X2) launch_forward_tc(e->stream, dev, a);
+    if (dev.tc_pack) launch_forward_tc(e->stream, dev, a);     // policies whose shape fits the tensor-core kernel (f16x2 engines)
     else launch_forward_fp32(e->stream, dev, a);
 }
 
@@ -625,16 +630,17 @@ int twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* ob
     if (perm_idx)
         for (int64_t i = 0; i < n; ++i)
             if (perm_idx[i] < -1 || perm_idx[i] >= p->dev.n_perms) return fail(TWR_ERR_INVALID, "perm_idx out of range");
-    if (e->precision == TWR_PREC_F16X2) {   // the one-hot GEMM operand cannot express a repeated index
-        for (int64_t i = 0; i < n; ++i)
-            for (int a2 = 0; a2 < n_obs; ++a2)
+    bool multiset = false;                   // the one-hot GEMM operand cannot express a repeated index: fp32 kernel then
+    if (p->dev.tc_pack) {
+        for (int64_t i = 0; i < n && !multiset; ++i)
+            for (int a2 = 0; a2 < n_obs && !multiset; ++a2)
                 for (int b2 = a2 + 1; b2 < n_obs; ++b2)
-                    if (obs[i * n_obs + a2] == obs[i * n_obs + b2])
-                        return fail(TWR_ERR_UNSUPPORTED, "repeated observation index: use TWR_PREC_FP32 for multiset observations");
+                    if (obs[i * n_obs + a2] == obs[i * n_obs + b2]) { multiset = true; break; }
     }
     CU_TRY(cudaSetDevice(e->device));
     PolicyDev dev = p->dev;
     dev.n_obs = n_obs;
+    if (multiset) dev.tc_pack = nullptr;
     Staging<float4> d_logits; Staging<float> d_values; Staging<int32_t> d_perm, d_obs;
     int rc;
     if ((rc = d_logits.alloc((size_t)n)) || (rc = d_values.alloc((size_t)n)) || (rc = d_obs.alloc((size_t)n * n_obs))) return rc;
@@ -778,7 +784,7 @@ static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev&
     ForwardArgs fa{};
     fa.env = env; fa.seed = e->seed; fa.cid = cid; fa.ids = ids; fa.perm_idx = nullptr;
     fa.cells = b.cells; fa.n = B; fa.logits = b.logits; fa.values = b.values;
-    const bool fused = e->precision == TWR_PREC_F16X2 && forward_tc_can_fuse(dev);
+    const bool fused = dev.tc_pack && forward_tc_can_fuse(dev);
     int n_fwd = *n_fwd_out;
     if (fused) {
         // Persistent chunks: one launch covers `chunk` consecutive steps of every tile (envs stay with their

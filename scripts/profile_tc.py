@@ -23,7 +23,7 @@ for rep in range(3):
     _lib.check(_lib.load().twr_debug_forward_profile(eng._h, pol.device_handle(eng), b._h, _lib.ptr(craw), 164, flags))
 print("flags", flags)
 names = {0: "mma total", 1: "mma wait slot(TMA)", 2: "mma wait a1_full", 3: "mma wait a2_full", 4: "mma wait d2_empty",
-         5: "tiles", 6: "mma wait peer slot", 8: "producer wait empty", 9: "epi total", 10: "epi wait d1_full", 11: "epi wait d2_full", 12: "epi wait a1_empty", 13: "epi1 busy", 14: "build_a1 (incl wait)", 15: "epi2+step busy"}
+         5: "tiles", 6: "mma slot wait in G1", 7: "mma slot wait G1 kb0", 8: "producer wait empty", 9: "epi total", 10: "epi wait d1_full", 11: "epi wait d2_full", 12: "epi wait a1_empty", 13: "epi1 busy", 14: "build_a1 (incl wait)", 15: "epi2+step busy"}
 for k, v in names.items():
     col = c[:, k]
     print(f"{v:22s} cta0 {col[0]:9d}  mean {col.mean():11.1f}  min {col.min():9d}  max {col.max():9d}")

@@ -3,9 +3,8 @@
 // Same math and pipeline as twr_forward_tc.cu (one-hot GEMM1 -> TMEM -> bias/ReLU/fp16 split in place
 // -> GEMM2 with A from TMEM -> heads), but two CTAs of a cluster cooperate on a 256-env tile:
 // every tcgen05.mma is M=256 (rows 0..127 live in CTA 0's TMEM, 128..255 in CTA 1's) and the B operand
-// (weights) is split along N between the two CTAs' shared memory -- each SM therefore ingests only
-// HALF of the operand stream per env (the single-CTA kernel is bound by the ~25 B/clk/SM L2->SM
-// ingest rate, measured with the pipeline wait counters).
+// (weights) is split along N between the two CTAs' shared memory -- each SM therefore streams only
+// HALF of the operand bytes per env and issues M = 256 instructions (see DESIGN.md for what bounds it).
 //
 //   CTA 0 (leader): warp 1 issues all MMAs; its mbarriers collect the arrivals of both CTAs
 //   CTA 1 (peer)  : its TMA loads credit the leader's `full` barrier (2-SM TMA); epilogue warps
@@ -307,8 +306,12 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             auto push = [&](int row) {
                 const uint32_t slot = use % NSLOTS, round = use / NSLOTS;
                 mbar_wait_t(bar(B_EMPTY0 + slot), (round & 1u) ^ 1u, w_empty, timed);
-                if (crank == 0) mbar_expect_tx(bar(B_FULL0 + slot), 2 * TILE_BYTES);
-                tma_load_2sm(sbase + SM_RING + slot * TILE_BYTES, &tmap, 0, row, bar(B_FULL0 + slot));
+                if (a.dbg_flags & 2) {                      // ablation: no operand traffic, the slot is "full" at once
+                    if (crank == 0) mbar_arrive(bar(B_FULL0 + slot));
+                } else {
+                    if (crank == 0) mbar_expect_tx(bar(B_FULL0 + slot), 2 * TILE_BYTES);
+                    tma_load_2sm(sbase + SM_RING + slot * TILE_BYTES, &tmap, 0, row, bar(B_FULL0 + slot));
+                }
                 ++use;
             };
             auto push_g1 = [&](int c) { for (int i = 0; i < NKB1; ++i) push(g1_row0 + (c * NKB1 + i) * (TILE_BYTES / 128)); };
@@ -325,7 +328,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         if (lane == 0 && crank == 0) {
             // =========================== MMA issuer (leader CTA) ======================
             uint32_t use = 0, d1use = 0, a2use = 0;
-            long long w_slot = 0, w_a1 = 0, w_a2 = 0, w_d2 = 0;
+            long long w_slot = 0, w_a1 = 0, w_a2 = 0, w_d2 = 0, w_slot_g1 = 0, w_slot_first = 0;
             const long long t_begin = clock64();
             auto wait_slot = [&]() -> uint32_t {
                 const uint32_t slot = use % NSLOTS, round = use / NSLOTS;
@@ -343,7 +346,10 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     const uint32_t buf = d1use & 1u;
                     const uint32_t d = tmem + D1_COL + buf * 128u;
                     for (int kb = 0; kb < NKB1; ++kb) {
+                        const long long w0 = w_slot;
                         const uint32_t slot = wait_slot();
+                        w_slot_g1 += w_slot - w0;
+                        if (kb == 0) w_slot_first += w_slot - w0;
                         const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
                         const uint64_t bh = make_desc(sbase + SM_RING + slot * TILE_BYTES);
                         const uint64_t bl = make_desc(sbase + SM_RING + slot * TILE_BYTES + HALF_BYTES);
@@ -396,6 +402,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             if (a.dbg) {
                 long long* d = a.dbg + blockIdx.x * 16;
                 d[0] = clock64() - t_begin; d[1] = w_slot; d[2] = w_a1; d[3] = w_a2; d[4] = w_d2; d[5] = my_tiles;
+                d[6] = w_slot_g1; d[7] = w_slot_first;
             }
         }
         __syncwarp();

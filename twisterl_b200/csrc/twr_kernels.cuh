@@ -95,7 +95,7 @@ struct ForwardArgs {
     // balanced item schedule of the persistent pair kernel: groups beyond a whole number per CTA pair are cut along
     // TIME into pieces handed from pair to pair; bal_flags[g] counts the finished steps of such a group (zeroed per launch)
     int32_t* bal_flags; int bal_delta;   // bal_delta: extra item slots granted to each hand-off (0 = balancing off)
-    int dbg_flags;    // debug experiments (k_forward_tc2): 1 skip epilogue-1 TMEM traffic, 2 skip TMA copies, 4 skip GEMM2 MMAs, 8 skip GEMM1 MMAs
+    int dbg_flags;    // ablations (k_forward_tc2, timing only): 1 skip epilogue-1 TMEM traffic, 2 no operand TMA traffic, 4 skip GEMM2 MMAs, 8 skip GEMM1 MMAs
     long long* dbg;   // optional [gridDim][16] cycle counters written by k_forward_tc (debug/profiling)
 };
 int  forward_fp32_supported(const PolicyDev& p, const EnvParams& env, const char** why);

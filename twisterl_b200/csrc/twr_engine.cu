@@ -808,7 +808,34 @@ static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev&
                 fa.bal_flags = e->bal_flags; fa.bal_delta = bal_delta;
             }
             if (e->timing && 2 * n_fwd + 1 < (int)e->ev.size()) cudaEventRecord(e->ev[2 * n_fwd], st);
+            fa.dbg = nullptr;
+            static long long* trace_buf = nullptr;           // TWISTERL_B200_TRACE=<chunk index>: pipeline counters of that launch
+            static const char* trace_env = getenv("TWISTERL_B200_TRACE");
+            if (trace_env && ci == atoi(trace_env)) {
+                if (!trace_buf) cudaMalloc(reinterpret_cast<void**>(&trace_buf), sizeof(long long) * (148 * 16 + 256));
+                cudaMemsetAsync(trace_buf, 0, sizeof(long long) * (148 * 16 + 256), st);
+                fa.dbg = trace_buf;
+            }
             launch_forward(e, dev, fa);
+            if (fa.dbg) {
+                std::vector<long long> h(148 * 16 + 256);
+                cudaMemcpyAsync(h.data(), trace_buf, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st);
+                cudaStreamSynchronize(st);
+                static const char* names[16] = {"mma total", "mma wait slot", "mma wait a1_full", "mma wait a2_full", "mma wait d2_empty", "lanes",
+                                                "mma slot wait G1", "mma slot wait G1 first", "producer wait empty", "epi total", "epi wait d1_full",
+                                                "epi wait d2_full", "epi wait a1_empty", "epi1 busy", "build_a1", "epi2+step busy"};
+                fprintf(stderr, "[trace] chunk %d, %d steps, %lld live envs\n", ci, cnt, (long long)B);
+                for (int k = 0; k < 16; ++k) {
+                    double sum = 0; int n = 0; long long mx = 0;
+                    for (int c = 0; c < 148; ++c) { const long long v = h[(size_t)c * 16 + k]; if (v) { sum += (double)v; ++n; if (v > mx) mx = v; } }
+                    fprintf(stderr, "[trace] %-24s cta0 %10lld  mean(nonzero) %12.1f  max %10lld\n", names[k], h[k], n ? sum / n : 0.0, mx);
+                }
+                for (int item = 0; item < 8; ++item) {
+                    fprintf(stderr, "[trace] item %d:", item);
+                    for (int ev = 0; ev < 23; ++ev) if (h[148 * 16 + item * 32 + ev]) fprintf(stderr, " %d@%lld", ev, h[148 * 16 + item * 32 + ev] - h[148 * 16]);
+                    fprintf(stderr, "\n");
+                }
+            }
             if (e->timing && 2 * n_fwd + 1 < (int)e->ev.size()) cudaEventRecord(e->ev[2 * n_fwd + 1], st);
             ++n_fwd;
             if (cnt > 1) launch_compact_live(st, cur, b.n_live + ci, b.ep_len, B, nxt, b.n_live + ci + 1);

@@ -31,7 +31,6 @@ constexpr int TM = 128;               // envs per CTA (the pair covers 256)
 constexpr int NTHREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int NEPI = 256;
 constexpr int TILE_BYTES = 16384;
-constexpr int HALF_BYTES = 8192;
 constexpr int NSLOTS = 8;
 constexpr int MAX_KB1 = 4;
 constexpr int MAX_OBS = 32;
@@ -106,22 +105,6 @@ __device__ __forceinline__ void tc2_mma(uint32_t d_tmem, uint64_t a_desc, uint64
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// A-operand reuse: `fill` keeps the A tile in the tensor core's collector buffer, `lastuse` consumes it without
-// re-reading shared memory (GEMM1 multiplies the same one-hot A by the hi and the lo half of the table)
-__device__ __forceinline__ void tc2_mma_fill(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc2_mma_lastuse(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void tc2_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -129,7 +112,6 @@ __device__ __forceinline__ void tc2_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-constexpr uint32_t IDESC_256x128 = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 constexpr uint32_t IDESC_256x256 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
 
 struct Tc2Params { int NC, NKB1, E, H; };
@@ -138,7 +120,9 @@ __host__ __device__ inline size_t slots_g2(const Tc2Params& t) { return (size_t)
 __host__ __device__ inline size_t slots_per_rank(const Tc2Params& t) { return slots_g1(t) + slots_g2(t); }
 
 // Operand image per CTA rank r (rank 0 image, then rank 1 image), in streaming order, 16 KB per ring slot:
-//   G1 slot (c,kb)      : [hi half-tile 8 KB][lo half-tile 8 KB], rows n = feature c*128 + r*64 + (0..63), k = obs row
+//   G1 slot (s,kb,part) : [128 rows x 64 k] of the hi (part 0) or lo (part 1) table, rows n = feature (2s+r)*128 + (0..127),
+//                         k = obs row kb*64 + kk -- GEMM1 runs as N = 256 MMAs over a PAIR of 128-feature chunks (both D1
+//                         buffers at once; rank r's half of B is chunk 2s+r): N = 128 MMAs issue at half rate
 //   G2 slot (j,kb,part) : [128 rows x 64 k], rows n = output r*128 + (0..127), k = feature j*128 + kb*64 + kk
 __global__ void __launch_bounds__(256) k_tc2_pack(PolicyDev p, Tc2Params t, __half* __restrict__ pack) {
     const size_t spr = slots_per_rank(t), n1 = slots_g1(t);
@@ -152,13 +136,12 @@ __global__ void __launch_bounds__(256) k_tc2_pack(PolicyDev p, Tc2Params t, __ha
         int lo_part;
         uint32_t off;
         if (slot < n1) {
-            const int c = (int)(slot / t.NKB1), kb = (int)(slot % t.NKB1);
-            lo_part = within >= (HALF_BYTES / 2);
-            const uint32_t w2 = within % (HALF_BYTES / 2);
-            const uint32_t row = w2 >> 6, kk = w2 & 63u;
-            const int f = c * 128 + r * 64 + (int)row, k = kb * 64 + (int)kk;
+            const int sc = (int)(slot / (2 * t.NKB1)), kb = (int)((slot % (2 * t.NKB1)) / 2);
+            lo_part = (int)(slot % 2);
+            const uint32_t row = within >> 6, kk = within & 63u;
+            const int f = (2 * sc + r) * 128 + (int)row, k = kb * 64 + (int)kk;
             if (k < p.obs_size) x = p.emb[(size_t)k * p.E + f];
-            off = (lo_part ? HALF_BYTES : 0) + tile_off(row, kk);
+            off = tile_off(row, kk);
         } else {
             const size_t q = slot - n1;
             const int j = (int)(q / 4), kb = (int)((q % 4) / 2);
@@ -314,13 +297,10 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 }
                 ++use;
             };
-            auto push_g1 = [&](int c) { for (int i = 0; i < NKB1; ++i) push(g1_row0 + (c * NKB1 + i) * (TILE_BYTES / 128)); };
+            auto push_g1 = [&](int sc) { for (int i = 0; i < 2 * NKB1; ++i) push(g1_row0 + (sc * 2 * NKB1 + i) * (TILE_BYTES / 128)); };
             auto push_g2 = [&](int j) { for (int i = 0; i < 4; ++i) push(g2_row0 + (j * 4 + i) * (TILE_BYTES / 128)); };
-            for (int it = 0; it < n_items; ++it) {
-                push_g1(0);
-                for (int c = 1; c < NC; ++c) { push_g1(c); push_g2(c - 1); }
-                push_g2(NC - 1);
-            }
+            for (int it = 0; it < n_items; ++it)
+                for (int sc = 0; sc < NC / 2; ++sc) { push_g1(sc); push_g2(2 * sc); push_g2(2 * sc + 1); }
             if (a.dbg) a.dbg[blockIdx.x * 16 + 8] = w_empty;
         }
         __syncwarp();
@@ -341,30 +321,31 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 mbar_wait_cluster_t(bar(B_A1_FULL), it & 1, w_a1, timed);
                 tc_fence_after();
                 stamp(it, 0);
-                auto g1 = [&](int c) {
-                    stamp(it, 1 + c);
-                    const uint32_t buf = d1use & 1u;
-                    const uint32_t d = tmem + D1_COL + buf * 128u;
+                // GEMM1 of the chunk pair (2sc, 2sc+1): N = 256 MMAs write both D1 buffers (columns [256,384) = chunk 2sc from
+                // rank 0's half of B, [384,512) = chunk 2sc+1 from rank 1's half)
+                auto g1 = [&](int sc) {
+                    stamp(it, 1 + 2 * sc);
+                    const uint32_t d = tmem + D1_COL;
                     for (int kb = 0; kb < NKB1; ++kb) {
-                        const long long w0 = w_slot;
-                        const uint32_t slot = wait_slot();
-                        w_slot_g1 += w_slot - w0;
-                        if (kb == 0) w_slot_first += w_slot - w0;
                         const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
-                        const uint64_t bh = make_desc(sbase + SM_RING + slot * TILE_BYTES);
-                        const uint64_t bl = make_desc(sbase + SM_RING + slot * TILE_BYTES + HALF_BYTES);
-                        if (!(a.dbg_flags & 8)) {
+                        for (int part = 0; part < 2; ++part) {
+                            const long long w0 = w_slot;
+                            const uint32_t slot = wait_slot();
+                            w_slot_g1 += w_slot - w0;
+                            if (kb == 0 && part == 0) w_slot_first += w_slot - w0;
+                            const uint64_t bd = make_desc(sbase + SM_RING + slot * TILE_BYTES);
+                            if (!(a.dbg_flags & 8)) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                tc2_mma_fill(d, ad + 2u * ks, bh + 2u * ks, IDESC_256x128, (kb | ks) != 0);
-                                tc2_mma_lastuse(d, ad + 2u * ks, bl + 2u * ks, IDESC_256x128, 1u);
+                                for (int ks = 0; ks < 4; ++ks)
+                                    tc2_mma(d, ad + 2u * ks, bd + 2u * ks, IDESC_256x256, (kb | part | ks) != 0);
                             }
+                            tc2_commit(bar(B_EMPTY0 + slot));
                         }
-                        tc2_commit(bar(B_EMPTY0 + slot));
                     }
-                    tc2_commit(bar(B_D1_FULL0 + buf));
-                    if (c == NC - 1) tc2_commit(bar(B_A1_EMPTY));
-                    ++d1use;
+                    tc2_commit(bar(B_D1_FULL0));
+                    tc2_commit(bar(B_D1_FULL1));
+                    if (sc == NC / 2 - 1) tc2_commit(bar(B_A1_EMPTY));
+                    d1use += 2;
                 };
                 auto g2 = [&](int j) {
                     const uint32_t buf = a2use & 1u;
@@ -394,9 +375,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     ++a2use;
                     if (j == NC - 1) tc2_commit(bar(B_D2_FULL));
                 };
-                g1(0);
-                for (int c = 1; c < NC; ++c) { g1(c); g2(c - 1); }
-                g2(NC - 1);
+                for (int sc = 0; sc < NC / 2; ++sc) { g1(sc); g2(2 * sc); g2(2 * sc + 1); }
                 stamp(it, 9);
             }
             if (a.dbg) {
@@ -512,46 +491,91 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         // them); with a single tile per pair the next item is the same envs one step later, whose state
         // only exists after this item's fused env step
         const bool build_early = my_tiles > 1 || t_count == 1;
+        // ---- epilogue 1 of chunk c: this thread's 64 columns of the D1 chunk, rewritten in place as the fp16 A operand
+        auto epi1 = [&](int it, int c) {
+            const uint32_t buf = d1use & 1u;
+            mbar_wait_t(bar(B_D1_FULL0 + buf), (d1use >> 1) & 1u, w_d1, timed);
+            tc_fence_after();
+            if (threadIdx.x == 64) stamp(it, 10 + c);
+            const long long t_e1 = timed ? clock64() : 0;
+            if (!(a.dbg_flags & 1)) {
+                uint32_t v0[32], v1[32];
+                const uint32_t taddr = tmem + lane_addr + D1_COL + buf * 128u + (uint32_t)chalf * 64u;
+                tc_ld32(taddr, v0);
+                tc_ld32(taddr + 32u, v1);
+                tc_wait_ld();
+                const float* bias = embb + c * 128 + chalf * 64;
+                uint32_t w[32];
+#pragma unroll
+                for (int e2 = 0; e2 < 16; ++e2)
+                    split2(__uint_as_float(v0[2 * e2]) + bias[2 * e2], __uint_as_float(v0[2 * e2 + 1]) + bias[2 * e2 + 1], w[e2], w[16 + e2]);
+                tc_st32(taddr, w);
+#pragma unroll
+                for (int e2 = 0; e2 < 16; ++e2)
+                    split2(__uint_as_float(v1[2 * e2]) + bias[32 + 2 * e2], __uint_as_float(v1[2 * e2 + 1]) + bias[32 + 2 * e2 + 1], w[e2], w[16 + e2]);
+                tc_st32(taddr + 32u, w);
+                tc_wait_st();
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(buf ? l_a2_full1 : l_a2_full0);
+            if (timed) c_epi1 += clock64() - t_e1;
+            if (threadIdx.x == 64) stamp(it, 14 + c);
+            ++d1use;
+        };
+        // ---- the collect step of one item (lower-half threads): record, sample, env step, hand-off signal
+        struct Saved { float out[4]; float value; int perm; int64_t pos; int step, group, extra; bool valid; };
+        auto run_step = [&](const Saved& v) {
+            const bool active = v.pos < n;
+            if (a.fused) {
+                const int e = active ? (a.live ? a.live[v.pos] : (int)v.pos) : 0;
+                StepArgs sa = a.step;
+                sa.t = a.t + v.step;
+                // inside a multi-step chunk an env that already recorded its terminal state idles
+                const bool alive = active && (t_count == 1 || a.cb.ep_len[e] == 0);
+                collect_step_body(sa, a.cb, alive, e, make_float4(v.out[0], v.out[1], v.out[2], v.out[3]), v.value, v.perm,
+                                  a.live_next);
+            } else if (active) {
+                a.logits[v.pos] = make_float4(v.out[0], v.out[1], v.out[2], v.out[3]);
+                a.values[v.pos] = v.value;
+            }
+            if (v.extra) {
+                // a time-split group: publish this CTA's finished step to the pair that runs the next piece
+                asm volatile("bar.sync 4, %0;" ::"n"(NEPI / 2) : "memory");
+                if (threadIdx.x == 64) { __threadfence(); atomicAdd(a.bal_flags + (v.group - sch.lanes * sch.P), 1); }
+            }
+        };
+        // Deferred step: the fused collect step of item `it` (global loads, Philox, record stores: ~5k cycles) would sit
+        // between this item's heads and the next item's first epilogue-1, right where GEMM2 of the next item waits for its
+        // A operand; it runs instead after epilogue-1 of the next item's first chunk pair, hidden behind that GEMM2.
+        const bool defer = build_early && a.fused && t_count > 1;
+        Saved sv;
+        sv.valid = false; sv.pos = 0; sv.step = 0; sv.group = 0; sv.extra = 0; sv.perm = -1; sv.value = 0.f;
+        sv.out[0] = sv.out[1] = sv.out[2] = sv.out[3] = 0.f;
+
         if (chalf == 1) perm_next = build_a1(0, prefetch(0));          // the upper-half warps own the one-hot operand
         for (int it = 0; it < n_items; ++it) {
             Pre pre_next; pre_next.pos = 0; pre_next.e = 0; pre_next.c = make_uint4(0, 0, 0, 0); pre_next.step = 0;
-            if (build_early && chalf == 1 && it + 1 < n_items) {
+            int c_done = 0;
+            if (defer) {
+                for (; c_done < 2 && c_done < NC; ++c_done) epi1(it, c_done);
+                if (chalf == 0 && sv.valid) {                          // step of item it-1
+                    run_step(sv);
+                    sv.valid = false;
+                    if (it + 1 < n_items) asm volatile("bar.arrive 3, %0;" ::"n"(NEPI) : "memory");
+                }
+                if (chalf == 1 && it + 1 < n_items) {
+                    // item it+1's env state was last written by the step of an item <= it-1 (same-group items are >= 2
+                    // apart), which the lower-half threads have just finished: barrier 3 orders it before these loads
+                    if (it >= 1) asm volatile("bar.sync 3, %0;" ::"n"(NEPI) : "memory");
+                    pre_next = prefetch(it + 1);
+                }
+            } else if (build_early && chalf == 1 && it + 1 < n_items) {
                 // with >= 2 tiles per pair, item it+1's env state was last written by the fused step of item
                 // it+1-my_tiles <= it-1 (lower-half threads); barrier 3 orders that step before these loads
                 if (t_count > 1 && it >= 1) asm volatile("bar.sync 3, %0;" ::"n"(NEPI) : "memory");
                 pre_next = prefetch(it + 1);
             }
-            // ---- epilogue 1: this thread's 64 columns of the D1 chunk, rewritten in place as the fp16 A operand
-            for (int c = 0; c < NC; ++c) {
-                const uint32_t buf = d1use & 1u;
-                mbar_wait_t(bar(B_D1_FULL0 + buf), (d1use >> 1) & 1u, w_d1, timed);
-                tc_fence_after();
-                if (threadIdx.x == 64) stamp(it, 10 + c);
-                const long long t_e1 = timed ? clock64() : 0;
-                if (!(a.dbg_flags & 1)) {
-                    uint32_t v0[32], v1[32];
-                    const uint32_t taddr = tmem + lane_addr + D1_COL + buf * 128u + (uint32_t)chalf * 64u;
-                    tc_ld32(taddr, v0);
-                    tc_ld32(taddr + 32u, v1);
-                    tc_wait_ld();
-                    const float* bias = embb + c * 128 + chalf * 64;
-                    uint32_t w[32];
-#pragma unroll
-                    for (int e2 = 0; e2 < 16; ++e2)
-                        split2(__uint_as_float(v0[2 * e2]) + bias[2 * e2], __uint_as_float(v0[2 * e2 + 1]) + bias[2 * e2 + 1], w[e2], w[16 + e2]);
-                    tc_st32(taddr, w);
-#pragma unroll
-                    for (int e2 = 0; e2 < 16; ++e2)
-                        split2(__uint_as_float(v1[2 * e2]) + bias[32 + 2 * e2], __uint_as_float(v1[2 * e2 + 1]) + bias[32 + 2 * e2 + 1], w[e2], w[16 + e2]);
-                    tc_st32(taddr + 32u, w);
-                    tc_wait_st();
-                }
-                tc_fence_before();
-                mbar_arrive_cluster(buf ? l_a2_full1 : l_a2_full0);
-                if (timed) c_epi1 += clock64() - t_e1;
-                if (threadIdx.x == 64) stamp(it, 14 + c);
-                ++d1use;
-            }
+            for (; c_done < NC; ++c_done) epi1(it, c_done);
             // ---- next tile's one-hot operand, so its GEMM1 overlaps this tile's heads
             {
                 const long long t_b = timed ? clock64() : 0;
@@ -592,52 +616,41 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 ps[4] = acc[4];
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");     // the 8 epilogue warps only
-            int group_cur, step_cur, extra_cur;
-            sched_item(sch, pair_id, it, group_cur, step_cur, extra_cur);
-            const int64_t pos = ((int64_t)group_cur * 2 + crank) * TM + row;
             if (chalf == 0) {                                          // warp-uniform: whole warps take this branch
-                const bool active = pos < n;
-                float out[4] = {0.f, 0.f, 0.f, 0.f};
-                float value = 0.f;
+                Saved cur;
+                sched_item(sch, pair_id, it, cur.group, cur.step, cur.extra);
+                cur.pos = ((int64_t)cur.group * 2 + crank) * TM + row;
+                cur.valid = true;
+                cur.out[0] = cur.out[1] = cur.out[2] = cur.out[3] = 0.f;
+                cur.value = 0.f;
                 perm_cur = perm_s[(it & 3) * TM + row];             // written by the partner thread when it built this tile
-                if (active) {
+                cur.perm = perm_cur;
+                if (cur.pos < n) {
                     const float4 o4 = *reinterpret_cast<const float4*>(ps);
                     acc[0] += o4.x; acc[1] += o4.y; acc[2] += o4.z; acc[3] += o4.w; acc[4] += ps[4];
                     float l[4];
 #pragma unroll
                     for (int o = 0; o < 4; ++o) l[o] = o < p.A ? acc[o] + p.ba[o] : 0.0f;
 #pragma unroll
-                    for (int o = 0; o < 4; ++o) out[o] = l[o];
+                    for (int o = 0; o < 4; ++o) cur.out[o] = l[o];
                     if (perm_cur >= 0) {                               // twist-out, nn/policy.rs:95-97
 #pragma unroll
                         for (int o = 0; o < 4; ++o) {
                             if (o < p.A) {
                                 const int src = p.act_perms[perm_cur * p.A + o];
-                                out[o] = src == 0 ? l[0] : src == 1 ? l[1] : src == 2 ? l[2] : l[3];
+                                cur.out[o] = src == 0 ? l[0] : src == 1 ? l[1] : src == 2 ? l[2] : l[3];
                             }
                         }
                     }
-                    value = acc[4] + p.bv[0];
+                    cur.value = acc[4] + p.bv[0];
                 }
-                if (a.fused) {
-                    const int e = active ? (a.live ? a.live[pos] : (int)pos) : 0;
-                    StepArgs sa = a.step;
-                    sa.t = a.t + step_cur;
-                    // inside a multi-step chunk an env that already recorded its terminal state idles
-                    const bool alive = active && (t_count == 1 || a.cb.ep_len[e] == 0);
-                    collect_step_body(sa, a.cb, alive, e, make_float4(out[0], out[1], out[2], out[3]), value, perm_cur,
-                                      a.live_next);
-                } else if (active) {
-                    a.logits[pos] = make_float4(out[0], out[1], out[2], out[3]);
-                    a.values[pos] = value;
+                if (defer && it + 1 < n_items) {
+                    sv = cur;                                          // runs inside the next iteration
+                } else {
+                    run_step(cur);
+                    // publish "step of item `it` done" to the upper-half threads (matched by their bar.sync 3 at item it+1)
+                    if (!defer && build_early && t_count > 1 && it + 2 < n_items) asm volatile("bar.arrive 3, %0;" ::"n"(NEPI) : "memory");
                 }
-                if (extra_cur) {
-                    // a time-split group: publish this CTA's finished step to the pair that runs the next piece
-                    asm volatile("bar.sync 4, %0;" ::"n"(NEPI / 2) : "memory");
-                    if (threadIdx.x == 64) { __threadfence(); atomicAdd(a.bal_flags + (group_cur - sch.lanes * sch.P), 1); }
-                }
-                // publish "step of item `it` done" to the upper-half threads (matched by their bar.sync 3 at item it+1)
-                if (build_early && t_count > 1 && it + 2 < n_items) asm volatile("bar.arrive 3, %0;" ::"n"(NEPI) : "memory");
             }
             if (!build_early && it + 1 < n_items) {                    // single tile per pair: the next item is these envs one step later
                 asm volatile("bar.sync 2, %0;" ::"n"(NEPI) : "memory");  // their fused env step (lower-half threads) is done
@@ -698,7 +711,7 @@ bool get_tmap(const void* pack, size_t bytes, CUtensorMap* out) {
 
 }  // namespace
 
-int forward_tc2_supported(const PolicyDev& p) { return p.H == 256; }
+int forward_tc2_supported(const PolicyDev& p) { return p.H == 256 && p.E % 256 == 0; }   // GEMM1 works on chunk pairs
 
 size_t forward_tc2_pack_bytes(const PolicyDev& p) {
     if (!forward_tc2_supported(p)) return 0;

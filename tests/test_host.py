@@ -165,3 +165,37 @@ def test_max_records_and_spec_validation():
     big = _lib.EnvSpec(0, 5, 5, 1, 1, 1)
     assert L.twr_max_records(C.byref(big), 1) == -1
     assert b"16 cells" in L.twr_last_error()
+
+
+def test_reference_python_half_builds_on_this_module():
+    """Drop-in check that needs the reference checkout (present in the build container only, skipped elsewhere):
+    with twisterl_b200 installed as `twisterl.twisterl`, the reference's own unmodified Python half
+    (twisterl.utils.load_config / prepare_algorithm, BasicPolicy.to_rust) builds PPO and AlphaZero from its own
+    JSON configs and hands our nn.Policy / collectors the layouts they expect.  No device is touched."""
+    import subprocess
+    import sys
+    ref = Path("/root/reference")
+    if not (ref / "src" / "twisterl").is_dir():
+        pytest.skip("reference checkout not available")
+    code = r'''
+import sys, json
+sys.path.insert(0, %r)
+import twisterl_b200
+twisterl_b200.install_as_twisterl()
+sys.path.insert(0, "/root/reference/src")
+from twisterl.utils import load_config, prepare_algorithm
+out = {}
+for name in ("ppo_puzzle8_v1", "ppo_puzzle15_v1"):
+    algo = prepare_algorithm(load_config("/root/reference/examples/%%s.json" %% name))
+    pol = algo.policy.to_rust()
+    out[name] = [type(algo).__name__, type(algo.env).__module__, type(algo.collector).__module__, type(pol).__module__,
+                 int(pol.embeddings.vectors.shape[0]), int(pol.embeddings.bias.size), int(pol.num_actions),
+                 algo.env.obs_shape(), algo.env.num_actions()]
+print(json.dumps(out))
+''' % str(ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd="/tmp")
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["ppo_puzzle8_v1"] == ["PPO", "twisterl_b200.env", "twisterl_b200.collector", "twisterl_b200.nn", 81, 512, 4, [9, 9], 4]
+    assert out["ppo_puzzle15_v1"] == ["PPO", "twisterl_b200.env", "twisterl_b200.collector", "twisterl_b200.nn", 256, 512, 4, [16, 16], 4]

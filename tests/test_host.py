@@ -191,6 +191,20 @@ for name in ("ppo_puzzle8_v1", "ppo_puzzle15_v1"):
     out[name] = [type(algo).__name__, type(algo.env).__module__, type(algo.collector).__module__, type(pol).__module__,
                  int(pol.embeddings.vectors.shape[0]), int(pol.embeddings.bias.size), int(pol.num_actions),
                  algo.env.obs_shape(), algo.env.num_actions()]
+# the reference trainer's own data_to_torch / train_step (rl/ppo.py:25-106) on a CollectedData of this module
+import numpy as np
+from twisterl_b200.collector import CollectedData
+R = 6
+rng = np.random.default_rng(0)
+obs = np.arange(16)[None, :] * 16 + rng.integers(0, 16, size=(R, 16))
+d = CollectedData(obs.astype(np.uint16), rng.standard_normal((R, 4)).astype(np.float32), np.zeros(R, np.float32),
+                  np.zeros(R, np.float32), rng.integers(0, 4, R).astype(np.uint8), np.full(R, -1, np.int8))
+d.set_additional_data_item("advs", rng.standard_normal(R).astype(np.float32))
+d.set_additional_data_item("rets", rng.standard_normal(R).astype(np.float32))
+td = algo.data_to_torch(d)
+td = td[0] if isinstance(td[0], tuple) else td
+out["torch_shapes"] = [list(t.shape) for t in td]
+algo.train_step(td)
 print(json.dumps(out))
 ''' % str(ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd="/tmp")
@@ -199,3 +213,4 @@ print(json.dumps(out))
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["ppo_puzzle8_v1"] == ["PPO", "twisterl_b200.env", "twisterl_b200.collector", "twisterl_b200.nn", 81, 512, 4, [9, 9], 4]
     assert out["ppo_puzzle15_v1"] == ["PPO", "twisterl_b200.env", "twisterl_b200.collector", "twisterl_b200.nn", 256, 512, 4, [16, 16], 4]
+    assert out["torch_shapes"] == [[6, 256], [6], [6], [6], [6], [6]]

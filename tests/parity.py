@@ -31,7 +31,7 @@ def make_conv1d_policies(sd, obs_shape, conv_dim, obs_perms=(), act_perms=()):
 
 
 def check_collect_against_oracle(data, spec, opol, seed, collect_id, gamma, lam, tol, env_id_base=0,
-                                 max_episodes=None, near_tie=1e-4):
+                                 max_episodes=None, near_tie=1e-4, stride=1):
     """Replay check (north_star: 'bit-exact under forced or replayed action sequences').
 
     For every episode (reference merge order): the oracle env, reset from the same Philox stream and
@@ -56,7 +56,7 @@ def check_collect_against_oracle(data, spec, opol, seed, collect_id, gamma, lam,
     skipped = checked = 0
     for slot, ep in enumerate(order):
         n = int(ep_len[ep])
-        if max_episodes is not None and slot >= max_episodes:
+        if (max_episodes is not None and slot >= max_episodes * stride) or slot % stride:   # stride: sample every k-th episode
             off += n
             continue
         env.reset(seed=seed, env_id=env_id_base + int(ep), collect_id=collect_id)

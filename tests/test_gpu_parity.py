@@ -409,10 +409,14 @@ def test_collect_full_size_properties(eng):
     adv, ret = d.additional_array("advs"), d.additional_array("rets")
     assert np.abs((ret - adv) - d.values_array).max() <= 1e-5
     assert np.array_equal(ret[ends], rew[ends])
-    # and the full replay check on the first 24 episodes in merge order
+    # and the full replay check on the first 24 episodes in merge order, then on 40 episodes spread over all tiles
+    # (own and time-split groups of the balanced schedule alike)
     rep = check_collect_against_oracle(d, ospec, opol, seed=eng.seed, collect_id=5, gamma=0.995, lam=0.995, tol=TOL,
                                        max_episodes=24)
     assert rep["records"] > 24
+    rep = check_collect_against_oracle(d, ospec, opol, seed=eng.seed, collect_id=5, gamma=0.995, lam=0.995, tol=TOL,
+                                       max_episodes=40, stride=1637)
+    assert rep["records"] > 40
 
 
 def test_collect_host_pipelined_matches_plain(eng, monkeypatch):
@@ -531,3 +535,20 @@ def test_forward_obs_multiset_and_wide_tables_use_the_fp32_kernel(eng):
     for k in range(2):
         rl, rv = opol.raw_predict(obs[k].tolist())
         assert _close(l[k], rl, TOL) and abs(v[k] - rv) <= TOL * max(1.0, abs(rv))
+
+
+@pytest.mark.parametrize("E", [30000, 20000])
+def test_collect_mid_size_sampled_replay(eng, E):
+    """Between one and two tiles per CTA pair (two with the deferred fused step, and pairs with one and two tiles in
+    the same launch): every 211th episode, spread over all tiles, is replayed record by record through the oracle."""
+    import twisterl_b200 as tw
+    from parity import check_collect_against_oracle, make_policies
+    _, sd = trained15()
+    pol, opol = make_policies(sd, 256, *transpose_twists(4))
+    ospec = orc.puzzle_spec(4, 4, 18, 2, 256)
+    env = tw.env.Puzzle(4, 4, 18, 2, 256)
+    col = tw.collector.PPOCollector(E, 0.995, 0.995, 32, engine=eng)
+    eng.set_collect_id(17)
+    d = col.collect(env, pol)
+    rep = check_collect_against_oracle(d, ospec, opol, seed=eng.seed, collect_id=17, gamma=0.995, lam=0.995, tol=TOL, stride=211)
+    assert rep["records"] > 200

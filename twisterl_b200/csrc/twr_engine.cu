@@ -1046,19 +1046,19 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
 
 // ------------------------------------------------ batched MCTS driver (K6; also used by solve/evaluate) ---
 struct MctsMem {
-    Staging<uint4> cells; Staging<uint32_t> meta; Staging<int32_t> parent, first_child, n_nodes, fwd_list, fwd_env, fwd_count, cur_node;
-    Staging<uint8_t> n_children, action, active; Staging<float> prior, value_sum, cur_value; Staging<uint32_t> visits;
+    Staging<uint4> cells, node; Staging<uint32_t> meta; Staging<int32_t> parent, n_nodes, fwd_list, fwd_env, fwd_count, cur_node, path, path_len;
+    Staging<uint8_t> active; Staging<float> cur_value;
     int alloc(int64_t B, int P, MctsPool* pool, MctsArgs* a) {
         const size_t n = (size_t)B * (size_t)P;
         int rc;
-        if ((rc = cells.alloc(n)) || (rc = meta.alloc(n)) || (rc = parent.alloc(n)) || (rc = first_child.alloc(n)) ||
-            (rc = n_children.alloc(n)) || (rc = action.alloc(n)) || (rc = prior.alloc(n)) || (rc = visits.alloc(n)) ||
-            (rc = value_sum.alloc(n)) || (rc = n_nodes.alloc((size_t)B)) || (rc = fwd_list.alloc((size_t)B)) ||
+        if (P >= (1 << 20)) return fail(TWR_ERR_INVALID, "MCTS tree too large (num_mcts_searches * max_expand_depth must stay below 2^18)");
+        if ((rc = cells.alloc(n)) || (rc = meta.alloc(n)) || (rc = parent.alloc(n)) || (rc = node.alloc(n)) ||
+            (rc = n_nodes.alloc((size_t)B)) || (rc = fwd_list.alloc((size_t)B)) ||
             (rc = fwd_env.alloc((size_t)B)) || (rc = fwd_count.alloc(2)) || (rc = cur_node.alloc((size_t)B)) ||
-            (rc = cur_value.alloc((size_t)B)) || (rc = active.alloc((size_t)B))) return rc;
+            (rc = cur_value.alloc((size_t)B)) || (rc = active.alloc((size_t)B)) ||
+            (rc = path.alloc((size_t)B * TWR_MCTS_PATH)) || (rc = path_len.alloc((size_t)B))) return rc;
         pool->B = B; pool->P = P; pool->cells = cells.d; pool->meta = meta.d; pool->parent = parent.d;
-        pool->first_child = first_child.d; pool->n_children = n_children.d; pool->action = action.d; pool->prior = prior.d;
-        pool->visits = visits.d; pool->value_sum = value_sum.d; pool->n_nodes = n_nodes.d;
+        pool->node = node.d; pool->n_nodes = n_nodes.d; pool->path = path.d; pool->path_len = path_len.d;
         a->fwd_list = fwd_list.d; a->fwd_env = fwd_env.d; a->fwd_count = fwd_count.d; a->cur_node = cur_node.d;
         a->cur_value = cur_value.d; a->active = active.d;
         return TWR_OK;

@@ -124,12 +124,14 @@ void launch_solve_step(cudaStream_t s, const SolveArgs& a, const int32_t* live_c
 void launch_envs_broadcast(cudaStream_t s, const uint4* src_cells, const uint32_t* src_meta, uint4* cells, uint32_t* meta, int64_t n);
 
 // K6: batched MCTS (twr_mcts.cu)
+#define TWR_MCTS_PATH 96                       // recorded descent path entries per env (deeper paths fall back to the parent walk)
 struct MctsPool {
     int64_t B; int P; int A;                   // node (e, i) lives at e*P + i, root at i = 0
     uint4* cells; uint32_t* meta;              // the node's env (MCTSNode.state)
-    int32_t* parent; int32_t* first_child; uint8_t* n_children; uint8_t* action;
-    float* prior; uint32_t* visits; float* value_sum;
+    int32_t* parent;
+    uint4* node;                               // {visit_count, value_sum, prior, first_child | n_children << 20 | action << 24}
     int32_t* n_nodes;                          // [B]
+    int32_t* path; int32_t* path_len;          // [TWR_MCTS_PATH][B] node indices of the current descent, [B] its length (-1: overflow)
 };
 struct MctsArgs {
     EnvParams env; uint64_t seed; uint32_t cid; EnvIds ids;

@@ -1,11 +1,13 @@
 // twr_mcts.cu -- K6: batched Monte-Carlo tree search for the AlphaZero collector
 // (rust/src/rl/search.rs:20-189, rust/src/rl/tree.rs, rust/src/collector/az.rs:51-109).
 //
-// One tree per env in a pre-sized node pool (structure of arrays, node (e, i) at index e*P + i, root at i = 0;
+// One tree per env in a pre-sized node pool (node (e, i) at index e*P + i, root at i = 0;
 // P = 1 + A*(n_sims*max(1,max_expand_depth) + 1) nodes is the reference's worst case).  A node stores what the
-// reference's MCTSNode stores -- the cloned+stepped env (16-byte cells + meta), action_taken, prior,
-// visit_count, value_sum -- plus parent / first_child / n_children links.  All envs advance in lockstep, one
-// simulation at a time:
+// reference's MCTSNode stores -- the cloned+stepped env (16-byte cells + meta) and ONE 16-byte record
+// {visit_count, value_sum, prior, first_child | n_children | action_taken} -- plus a parent link.  The children of a
+// node are contiguous, so the UCB descent reads one 64-byte line per tree level (statistics AND the links of the
+// child it moves to), and the descent records its path so that the backup is a set of independent updates instead
+// of a parent-pointer walk.  All envs advance in lockstep, one simulation at a time:
 //   k_mcts_select : UCB descent to a leaf (search.rs:134-137, ucb :29-39, next :77-91); terminal leaves back up
 //                   their reward at once, the others are compacted (warp ballot) into the leaf batch
 //   forward       : the SAME policy forward kernel as the PPO path evaluates the whole leaf batch (K2)
@@ -28,11 +30,45 @@ __device__ __forceinline__ EnvState node_state(const MctsPool& m, int64_t g) {
     return env_load(m.cells, m.meta, g);
 }
 
-// MCTSTree::backpropagate (search.rs:45-53): add the value and one visit on the path to the root
-__device__ __forceinline__ void backprop(const MctsPool& m, int64_t base, int node, float v) {
-    for (int b = node; b >= 0; b = m.parent[base + b]) {
-        m.value_sum[base + b] += v;
-        m.visits[base + b] += 1u;
+// node record: x = visit_count, y = value_sum (f32 bits), z = prior (f32 bits), w = first_child | n_children << 20 | action << 24
+__device__ __forceinline__ uint32_t link_pack(int first, int nch, int action) {
+    return ((uint32_t)first & 0xFFFFFu) | ((uint32_t)nch << 20) | (((uint32_t)action & 0xFFu) << 24);
+}
+__device__ __forceinline__ int link_first(uint32_t w) { return (int)(w & 0xFFFFFu); }
+__device__ __forceinline__ int link_nch(uint32_t w) { return (int)((w >> 20) & 0xFu); }
+__device__ __forceinline__ int link_action(uint32_t w) { return (int)(w >> 24); }
+
+// one node of MCTSTree::backpropagate (search.rs:45-53): value_sum += v, visit_count += 1
+__device__ __forceinline__ void bump(const MctsPool& m, int64_t g, float v) {
+    uint2* q = reinterpret_cast<uint2*>(m.node + g);
+    uint2 r = *q;
+    r.x += 1u;
+    r.y = __float_as_uint(__uint_as_float(r.y) + v);
+    *q = r;
+}
+// MCTSTree::backpropagate over the recorded path (root .. node); falls back to the parent walk when the path
+// outgrew its buffer
+__device__ __forceinline__ void backprop(const MctsPool& m, int e, int64_t base, int node, int len, float v) {
+    if (len < 0) {
+        for (int b = node; b >= 0; b = m.parent[base + b]) bump(m, base + b, v);
+        return;
+    }
+    // the nodes of a path are distinct: all loads of a block of 8 are issued before the first store
+    for (int k0 = 0; k0 < len; k0 += 8) {
+        int idx[8];
+        uint2 r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) idx[j] = k0 + j < len ? m.path[(int64_t)(k0 + j) * m.B + e] : -1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (idx[j] >= 0) r[j] = *reinterpret_cast<const uint2*>(m.node + base + idx[j]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (idx[j] >= 0) {
+                r[j].x += 1u;
+                r[j].y = __float_as_uint(__uint_as_float(r[j].y) + v);
+                *reinterpret_cast<uint2*>(m.node + base + idx[j]) = r[j];
+            }
+        }
     }
 }
 
@@ -46,26 +82,32 @@ __device__ __forceinline__ void masked_probs(const float4 raw, uint32_t mask, in
     for (int i = 0; i < 4; ++i) pr[i] = pr[i] / (sum + 0.000001f);
 }
 
-// MCTSTree::expand (search.rs:56-75): one child per action with prior > 0, in action order
-__device__ __forceinline__ void expand(const MctsPool& m, const EnvParams& env, int e, int64_t base, int node, const float pr[4]) {
+// MCTSTree::expand (search.rs:56-75): one child per action with prior > 0, in action order.  Returns the first
+// child index and fills cp[] with the children's priors (cnt entries).
+__device__ __forceinline__ int expand(const MctsPool& m, const EnvParams& env, int e, int64_t base, int node, const float pr[4],
+                                      float cp[4], int& cnt) {
     const EnvState s = node_state(m, base + node);
     int n = m.n_nodes[e];
     const int first = n;
-    int cnt = 0;
+    cnt = 0;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
+        cp[a] = 0.0f;
         if (a < m.A && pr[a] > 0.0f && n < m.P) {
             EnvState c = s;
             env_step(env, c, a);
             env_store(m.cells, m.meta, base + n, c);
-            m.parent[base + n] = node; m.first_child[base + n] = -1; m.n_children[base + n] = 0;
-            m.action[base + n] = (uint8_t)a; m.prior[base + n] = pr[a]; m.visits[base + n] = 0u; m.value_sum[base + n] = 0.0f;
+            m.parent[base + n] = node;
+            m.node[base + n] = make_uint4(0u, __float_as_uint(0.0f), __float_as_uint(pr[a]), link_pack(0, 0, a));
+            // cp[] is indexed by child order; cnt <= a, so this never overwrites an entry still to be read
+            if (cnt == 0) cp[0] = pr[a]; else if (cnt == 1) cp[1] = pr[a]; else if (cnt == 2) cp[2] = pr[a]; else cp[3] = pr[a];
             ++n; ++cnt;
         }
     }
-    m.first_child[base + node] = first;
-    m.n_children[base + node] = (uint8_t)cnt;
+    uint32_t* link = &m.node[base + node].w;
+    *link = link_pack(first, cnt, link_action(*link));
     m.n_nodes[e] = n;
+    return first;
 }
 
 // rand's WeightedIndex as used by nn/policy.rs:153-167
@@ -109,9 +151,10 @@ __global__ void __launch_bounds__(128) k_mcts_begin(MctsArgs a, const int32_t* _
     const MctsPool& m = a.pool;
     const int64_t base = (int64_t)e * m.P;
     m.cells[base] = a.env_cells[e]; m.meta[base] = a.env_meta[e];
-    m.parent[base] = -1; m.first_child[base] = -1; m.n_children[base] = 0; m.action[base] = 0xFF;
-    m.prior[base] = 0.0f; m.visits[base] = 1u; m.value_sum[base] = 0.0f;      // search.rs:119-125: root visit_count = 1
+    m.parent[base] = -1;
+    m.node[base] = make_uint4(1u, __float_as_uint(0.0f), __float_as_uint(0.0f), link_pack(0, 0, 0xFF));   // search.rs:119-125: root visit_count = 1
     m.n_nodes[e] = 1;
+    m.path[e] = 0; m.path_len[e] = 1;                                          // path[0][e] = root
     a.fwd_list[pos] = (int32_t)base;
     a.fwd_env[pos] = e;
 }
@@ -127,20 +170,24 @@ __global__ void __launch_bounds__(128) k_mcts_expand(MctsArgs a, int mode, int s
     const EnvState s = node_state(m, base + node);
     float pr[4];
     masked_probs(a.logits[pos], env_masks(a.env, s), m.A, pr);
-    expand(m, a.env, e, base, node, pr);
+    float cp[4];
+    int nch;
+    const int first = expand(m, a.env, e, base, node, pr, cp, nch);
     if (mode == 0) return;
     // next_sample (search.rs:94-100): child drawn proportionally to the priors
-    const int nch = m.n_children[base + node], first = m.first_child[base + node];
-    float cp[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < nch; ++k) cp[k] = m.prior[base + first + k];
     uint32_t w[4];
     const int med = a.max_expand_depth > 1 ? a.max_expand_depth : 1;
     philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)((a.t * (a.n_sims + 1) + sim) * med + d), TWR_RNG_MCTS, a.cid,
                   (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w);
     const int child = nch > 0 ? first + weighted_index(cp, nch, u32_to_unit_f32(w[0])) : node;
     const float v = a.values[pos];
+    int len = m.path_len[e];
+    if (child != node && len >= 0) {                     // the drawn child joins the recorded path
+        if (len < TWR_MCTS_PATH) { m.path[(int64_t)len * m.B + e] = child; ++len; } else len = -1;
+        m.path_len[e] = len;
+    }
     if (d + 1 >= a.max_expand_depth) {
-        backprop(m, base, child, v);
+        backprop(m, e, base, child, len, v);
         a.active[e] = 0;
     } else {
         a.cur_node[e] = child;
@@ -161,29 +208,41 @@ __global__ void __launch_bounds__(128) k_mcts_select(MctsArgs a, const int32_t* 
         e = live[pos];
         const MctsPool& m = a.pool;
         const int64_t base = (int64_t)e * m.P;
-        int node = 0;
-        while (m.n_children[base + node] > 0) {                               // next(): argmax UCB, strict '>'
-            const int first = m.first_child[base + node], nch = m.n_children[base + node];
-            const float sq = sqrtf((float)m.visits[base + node]);
+        int node = 0, len = 1;
+        uint4 cur = m.node[base];                                              // root record (its path entry is permanent)
+        while (link_nch(cur.w) > 0) {                                          // next(): argmax UCB, strict '>'
+            const int first = link_first(cur.w), nch = link_nch(cur.w);
+            const float sq = sqrtf((float)cur.x);
+            uint4 ch[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (k < nch) ch[k] = m.node[base + first + k];   // one 64-byte line
             int best = -1;
             float best_ucb = -INFINITY;
-            for (int k = 0; k < nch; ++k) {
-                const uint32_t n = m.visits[base + first + k];
-                const float q = n == 0u ? 0.0f : __fdiv_rn(m.value_sum[base + first + k], (float)n);
-                const float ucb = __fadd_rn(q, __fmul_rn(__fmul_rn(a.C, __fdiv_rn(sq, __fadd_rn((float)n, 1.0f))), m.prior[base + first + k]));
-                if (ucb > best_ucb) { best = first + k; best_ucb = ucb; }
+            uint4 best_rec = cur;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k < nch) {
+                    const uint32_t n = ch[k].x;
+                    const float q = n == 0u ? 0.0f : __fdiv_rn(__uint_as_float(ch[k].y), (float)n);
+                    const float ucb = __fadd_rn(q, __fmul_rn(__fmul_rn(a.C, __fdiv_rn(sq, __fadd_rn((float)n, 1.0f))), __uint_as_float(ch[k].z)));
+                    if (ucb > best_ucb) { best = first + k; best_ucb = ucb; best_rec = ch[k]; }
+                }
             }
             if (best < 0) break;
-            node = best;
+            node = best; cur = best_rec;
+            if (len >= 0) {
+                if (len < TWR_MCTS_PATH) { m.path[(int64_t)len * m.B + e] = node; ++len; } else len = -1;
+            }
         }
+        m.path_len[e] = len;
         a.cur_node[e] = node;
         if (a.max_expand_depth <= 0) {
-            backprop(m, base, node, 0.0f);                                     // the rollout loop never runs: value stays 0
+            backprop(m, e, base, node, len, 0.0f);                             // the rollout loop never runs: value stays 0
             a.active[e] = 0;
         } else {
             const EnvState s = node_state(m, base + node);
             if (env_is_final(a.env, s) || m.n_nodes[e] + m.A > m.P) {
-                backprop(m, base, node, env_reward(a.env, s));
+                backprop(m, e, base, node, len, env_reward(a.env, s));
                 a.active[e] = 0;
             } else {
                 a.active[e] = 1;
@@ -211,7 +270,7 @@ __global__ void __launch_bounds__(128) k_mcts_pre(MctsArgs a, const int32_t* __r
             const int node = a.cur_node[e];
             const EnvState s = node_state(m, base + node);
             if (env_is_final(a.env, s) || m.n_nodes[e] + m.A > m.P) {
-                backprop(m, base, node, env_reward(a.env, s));
+                backprop(m, e, base, node, m.path_len[e], env_reward(a.env, s));
                 a.active[e] = 0;
             } else {
                 want = true;
@@ -226,10 +285,12 @@ __global__ void __launch_bounds__(128) k_mcts_pre(MctsArgs a, const int32_t* __r
 __device__ __forceinline__ void root_probs(const MctsPool& m, int64_t base, float pr[4], int32_t vis[4]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { pr[i] = 0.0f; vis[i] = 0; }
-    const int first = m.first_child[base], nch = m.n_children[base];
+    const uint32_t link = m.node[base].w;
+    const int first = link_first(link), nch = link_nch(link);
     for (int k = 0; k < nch; ++k) {
-        const int act = m.action[base + first + k];
-        const uint32_t n = m.visits[base + first + k];
+        const uint4 rec = m.node[base + first + k];
+        const int act = link_action(rec.w);
+        const uint32_t n = rec.x;
         const float f = (float)n;
         if (act == 0) { pr[0] = f; vis[0] = (int32_t)n; } else if (act == 1) { pr[1] = f; vis[1] = (int32_t)n; }
         else if (act == 2) { pr[2] = f; vis[2] = (int32_t)n; } else { pr[3] = f; vis[3] = (int32_t)n; }

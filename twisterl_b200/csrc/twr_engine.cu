@@ -1046,7 +1046,7 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
 
 // ------------------------------------------------ batched MCTS driver (K6; also used by solve/evaluate) ---
 struct MctsMem {
-    Staging<uint4> cells, node; Staging<uint32_t> meta; Staging<int32_t> parent, n_nodes, fwd_list, fwd_env, fwd_count, cur_node, path, path_len;
+    Staging<uint4> cells, node; Staging<uint32_t> meta; Staging<int32_t> parent, n_nodes, fwd_list, fwd_env, fwd_count, cur_node, path, path_len, leaf_pos;
     Staging<uint8_t> active; Staging<float> cur_value;
     int alloc(int64_t B, int P, MctsPool* pool, MctsArgs* a) {
         const size_t n = (size_t)B * (size_t)P;
@@ -1056,11 +1056,11 @@ struct MctsMem {
             (rc = n_nodes.alloc((size_t)B)) || (rc = fwd_list.alloc((size_t)B)) ||
             (rc = fwd_env.alloc((size_t)B)) || (rc = fwd_count.alloc(2)) || (rc = cur_node.alloc((size_t)B)) ||
             (rc = cur_value.alloc((size_t)B)) || (rc = active.alloc((size_t)B)) ||
-            (rc = path.alloc((size_t)B * TWR_MCTS_PATH)) || (rc = path_len.alloc((size_t)B))) return rc;
+            (rc = path.alloc((size_t)B * TWR_MCTS_PATH)) || (rc = path_len.alloc((size_t)B)) || (rc = leaf_pos.alloc((size_t)B))) return rc;
         pool->B = B; pool->P = P; pool->cells = cells.d; pool->meta = meta.d; pool->parent = parent.d;
         pool->node = node.d; pool->n_nodes = n_nodes.d; pool->path = path.d; pool->path_len = path_len.d;
         a->fwd_list = fwd_list.d; a->fwd_env = fwd_env.d; a->fwd_count = fwd_count.d; a->cur_node = cur_node.d;
-        a->cur_value = cur_value.d; a->active = active.d;
+        a->cur_value = cur_value.d; a->active = active.d; a->leaf_pos = leaf_pos.d;
         return TWR_OK;
     }
 };
@@ -1078,6 +1078,18 @@ static void enqueue_mcts(twr_engine* e, const PolicyDev& dev, MctsArgs& a, const
     fa.n_live_ptr = a.fwd_count;
     launch_forward(e, dev, fa);
     launch_mcts_expand(st, a, 0, 0, 0, 0, B);
+    if (a.max_expand_depth == 1 && a.n_sims > 0) {
+        // one expansion round per simulation: expand/backup of simulation s and the descent of s+1 share a launch
+        int which = 1;
+        launch_mcts_select(st, a, live, n_live, 0, which, B);
+        for (int sim = 0; sim < a.n_sims; ++sim) {
+            fa.n_live_ptr = a.fwd_count + which;
+            launch_forward(e, dev, fa);
+            if (sim + 1 < a.n_sims) { launch_mcts_expand_select(st, a, live, n_live, sim, which, B); which ^= 1; }
+            else launch_mcts_expand(st, a, 1, sim, 0, which, B);
+        }
+        return;
+    }
     int round = 1;
     for (int sim = 0; sim < a.n_sims; ++sim) {
         int which = round & 1;

@@ -139,12 +139,14 @@ struct MctsArgs {
     MctsPool pool;
     const uint4* env_cells; const uint32_t* env_meta;    // the envs being searched from
     int32_t* fwd_list; int32_t* fwd_env; int32_t* fwd_count;   // leaf batch: node indices, env ids, two counters
+    int32_t* leaf_pos;                                          // [B] leaf-batch slot of env e in the current simulation
     const float4* logits; const float* values;           // forward outputs, indexed by leaf-batch position
     int32_t* cur_node; float* cur_value; uint8_t* active; // per env, current simulation
 };
 void launch_mcts_begin(cudaStream_t s, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int64_t max_n);
 void launch_mcts_expand(cudaStream_t s, const MctsArgs& a, int mode, int sim, int d, int which, int64_t max_n);
 void launch_mcts_select(cudaStream_t s, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int sim, int which, int64_t max_n);
+void launch_mcts_expand_select(cudaStream_t s, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int sim, int which, int64_t max_n);
 void launch_mcts_pre(cudaStream_t s, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int which, int64_t max_n);
 void launch_mcts_read(cudaStream_t s, const MctsArgs& a, int64_t n, float* probs, int32_t* visits);
 void launch_az_finish(cudaStream_t s, const MctsArgs& a, const CollectBuffers& b, const int32_t* live, int32_t* live_next);

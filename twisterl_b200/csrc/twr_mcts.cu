@@ -139,6 +139,7 @@ __device__ __forceinline__ void push_leaf(const MctsArgs& a, bool want, int64_t 
         const int slot = base + __popc(bal & ((1u << lane) - 1u));
         a.fwd_list[slot] = (int32_t)gnode;
         a.fwd_env[slot] = e;
+        a.leaf_pos[e] = slot;
     }
 }
 
@@ -160,10 +161,7 @@ __global__ void __launch_bounds__(128) k_mcts_begin(MctsArgs a, const int32_t* _
 }
 
 // mode 0: root expansion (search.rs:112-128); mode 1: simulation expansion round d (search.rs:142-160)
-__global__ void __launch_bounds__(128) k_mcts_expand(MctsArgs a, int mode, int sim, int d, int which) {
-    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos >= a.fwd_count[which]) return;
-    const int e = a.fwd_env[pos];
+__device__ __forceinline__ void expand_body(const MctsArgs& a, int e, int pos, int mode, int sim, int d) {
     const MctsPool& m = a.pool;
     const int64_t base = (int64_t)e * m.P;
     const int node = mode == 0 ? 0 : a.cur_node[e];
@@ -194,18 +192,16 @@ __global__ void __launch_bounds__(128) k_mcts_expand(MctsArgs a, int mode, int s
         a.cur_value[e] = v;
     }
 }
-
-// descent + first rollout round (search.rs:132-146)
-__global__ void __launch_bounds__(128) k_mcts_select(MctsArgs a, const int32_t* __restrict__ live, const int32_t* __restrict__ n_live,
-                                                     int sim, int which) {
+__global__ void __launch_bounds__(128) k_mcts_expand(MctsArgs a, int mode, int sim, int d, int which) {
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pos == 0) a.fwd_count[which ^ 1] = 0;          // the other counter is idle until the next round
-    const bool valid = pos < *n_live;
+    if (pos >= a.fwd_count[which]) return;
+    expand_body(a, a.fwd_env[pos], pos, mode, sim, d);
+}
+
+// descent + first rollout round (search.rs:132-146) of one env; returns whether its leaf needs a policy evaluation
+__device__ __forceinline__ bool select_body(const MctsArgs& a, int e, int64_t& gnode) {
     bool want = false;
-    int e = 0;
-    int64_t gnode = 0;
-    if (valid) {
-        e = live[pos];
+    {
         const MctsPool& m = a.pool;
         const int64_t base = (int64_t)e * m.P;
         int node = 0, len = 1;
@@ -251,7 +247,38 @@ __global__ void __launch_bounds__(128) k_mcts_select(MctsArgs a, const int32_t* 
             }
         }
     }
+    return want;
+}
+__global__ void __launch_bounds__(128) k_mcts_select(MctsArgs a, const int32_t* __restrict__ live, const int32_t* __restrict__ n_live,
+                                                     int sim, int which) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos == 0) a.fwd_count[which ^ 1] = 0;          // the other counter is idle until the next round
+    const bool valid = pos < *n_live;
+    bool want = false;
+    int e = 0;
+    int64_t gnode = 0;
+    if (valid) {
+        e = live[pos];
+        want = select_body(a, e, gnode);
+    }
     push_leaf(a, want, gnode, e, a.fwd_count + which);
+}
+// max_expand_depth == 1: expansion + backup of simulation `sim` and the descent of simulation sim+1 in one launch
+// (one thread per live env; the leaf batch of sim was compacted into counter `which`, the next goes into which^1)
+__global__ void __launch_bounds__(128) k_mcts_expand_select(MctsArgs a, const int32_t* __restrict__ live,
+                                                            const int32_t* __restrict__ n_live, int sim, int which) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos == 0) a.fwd_count[which] = 0;              // consumed by the forward before this launch; the next launch fills it
+    const bool valid = pos < *n_live;
+    bool want = false;
+    int e = 0;
+    int64_t gnode = 0;
+    if (valid) {
+        e = live[pos];
+        if (a.active[e]) expand_body(a, e, a.leaf_pos[e], 1, sim, 0);
+        want = select_body(a, e, gnode);
+    }
+    push_leaf(a, want, gnode, e, a.fwd_count + (which ^ 1));
 }
 
 // rollout rounds d > 0 (search.rs:142-146 for the child sampled in the previous round)
@@ -379,6 +406,10 @@ void launch_mcts_expand(cudaStream_t st, const MctsArgs& a, int mode, int sim, i
 }
 void launch_mcts_select(cudaStream_t st, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int sim, int which, int64_t max_n) {
     k_mcts_select<<<grid_for(max_n, 128), 128, 0, st>>>(a, live, n_live, sim, which);
+    TWR_COUNT_LAUNCH();
+}
+void launch_mcts_expand_select(cudaStream_t st, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int sim, int which, int64_t max_n) {
+    k_mcts_expand_select<<<grid_for(max_n, 128), 128, 0, st>>>(a, live, n_live, sim, which);
     TWR_COUNT_LAUNCH();
 }
 void launch_mcts_pre(cudaStream_t st, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int which, int64_t max_n) {

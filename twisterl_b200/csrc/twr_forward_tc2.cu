@@ -112,6 +112,7 @@ __device__ __forceinline__ void tc2_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+constexpr uint32_t IDESC_256x128 = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 constexpr uint32_t IDESC_256x256 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
 
 struct Tc2Params { int NC, NKB1, E, H; };
@@ -139,7 +140,10 @@ __global__ void __launch_bounds__(256) k_tc2_pack(PolicyDev p, Tc2Params t, __ha
             const int sc = (int)(slot / (2 * t.NKB1)), kb = (int)((slot % (2 * t.NKB1)) / 2);
             lo_part = (int)(slot % 2);
             const uint32_t row = within >> 6, kk = within & 63u;
-            const int f = (2 * sc + r) * 128 + (int)row, k = kb * 64 + (int)kk;
+            // rows of rank r: chunk 2sc+r for the N = 256 MMAs; in the LAST k-block the two chunks are finished one after
+            // the other with N = 128 MMAs (rows 0..63 = rank r's half of chunk 2sc, rows 64..127 = its half of chunk 2sc+1)
+            const int f = kb == t.NKB1 - 1 ? (2 * sc + (int)(row >> 6)) * 128 + r * 64 + (int)(row & 63u) : (2 * sc + r) * 128 + (int)row;
+            const int k = kb * 64 + (int)kk;
             if (k < p.obs_size) x = p.emb[(size_t)k * p.E + f];
             off = tile_off(row, kk);
         } else {
@@ -326,7 +330,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 auto g1 = [&](int sc) {
                     stamp(it, 1 + 2 * sc);
                     const uint32_t d = tmem + D1_COL;
-                    for (int kb = 0; kb < NKB1; ++kb) {
+                    for (int kb = 0; kb < NKB1 - 1; ++kb) {
                         const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
                         for (int part = 0; part < 2; ++part) {
                             const long long w0 = w_slot;
@@ -342,8 +346,38 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                             tc2_commit(bar(B_EMPTY0 + slot));
                         }
                     }
-                    tc2_commit(bar(B_D1_FULL0));
-                    tc2_commit(bar(B_D1_FULL1));
+                    // last k-block: chunk 2sc is completed first (N = 128 MMAs on rows 0..63 of the hi and the lo slot) and
+                    // published, so that its epilogue-1 runs while chunk 2sc+1 (rows 64..127 of the same two slots) finishes --
+                    // otherwise GEMM2 would wait a whole epilogue-1 after the pair
+                    {
+                        const int kb = NKB1 - 1;
+                        const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
+                        const long long w0 = w_slot;
+                        const uint32_t slot_h = wait_slot();
+                        const uint32_t slot_l = wait_slot();
+                        w_slot_g1 += w_slot - w0;
+                        const uint64_t bh = make_desc(sbase + SM_RING + slot_h * TILE_BYTES);
+                        const uint64_t bl = make_desc(sbase + SM_RING + slot_l * TILE_BYTES);
+                        const uint64_t half = (uint64_t)((64 * 128) >> 4);          // 64 rows further into the slot (descriptor address units of 16 B)
+                        if (!(a.dbg_flags & 8)) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                tc2_mma(d, ad + 2u * ks, bh + 2u * ks, IDESC_256x128, (kb | ks) != 0);
+                                tc2_mma(d, ad + 2u * ks, bl + 2u * ks, IDESC_256x128, 1u);
+                            }
+                        }
+                        tc2_commit(bar(B_D1_FULL0));
+                        if (!(a.dbg_flags & 8)) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                tc2_mma(d + 128u, ad + 2u * ks, bh + half + 2u * ks, IDESC_256x128, (kb | ks) != 0);
+                                tc2_mma(d + 128u, ad + 2u * ks, bl + half + 2u * ks, IDESC_256x128, 1u);
+                            }
+                        }
+                        tc2_commit(bar(B_EMPTY0 + slot_h));
+                        tc2_commit(bar(B_EMPTY0 + slot_l));
+                        tc2_commit(bar(B_D1_FULL1));
+                    }
                     if (sc == NC / 2 - 1) tc2_commit(bar(B_A1_EMPTY));
                     d1use += 2;
                 };

@@ -9,9 +9,16 @@
 //   CTA 0 (leader): warp 1 issues all MMAs; its mbarriers collect the arrivals of both CTAs
 //   CTA 1 (peer)  : its TMA loads credit the leader's `full` barrier (2-SM TMA); epilogue warps
 //                   arrive remotely (mapa + mbarrier.arrive on the shared::cluster address) on the leader's barriers
-//   both          : warp 0 streams this CTA's half tiles with cp.async.bulk into its own ring;
-//                   warps 2..5 are the epilogue of this CTA's 128 envs; tcgen05.commit.cta_group::2
-//                   (multicast) publishes accumulators / frees ring slots in both CTAs.
+//   both          : warp 0 streams this CTA's half tiles with 2-SM tensor-map TMA into its own 8-slot ring;
+//                   warps 2..9 are the epilogue of this CTA's 128 envs (two warps per TMEM lane quarter: epilogue-1
+//                   conversion, heads, and -- lower column half -- the fused collect step, upper half -- the one-hot
+//                   operand of the next item); tcgen05.commit.cta_group::2 (multicast) publishes accumulators / frees
+//                   ring slots in both CTAs.
+//
+// Per 256-env item: GEMM1 runs over PAIRS of 128-feature chunks as N = 256 MMAs (N = 128 issues at half rate), the
+// last k-block finishing the two chunks one after the other; GEMM2 (3 split passes, A from TMEM) follows per chunk.
+// A launch is persistent over up to 32 time steps of the tiles a pair owns (struct Sched balances left-over tiles
+// along time between pairs); the fused collect step of an item is deferred behind the next item's first epilogue-1.
 #include "twr_kernels.cuh"
 #include "twr_tc_ptx.cuh"
 #include "twr_step.cuh"

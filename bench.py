@@ -56,27 +56,34 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._halt = threading.Event()
-
-    def run(self):
-        try:
+        self._nv = self._h = None
+        try:                                   # NVML is initialised here, outside the timed region
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
-                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
-                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
-            while not self._halt.is_set():
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        except Exception as exc:               # NVML missing: report it rather than fail the bench
+            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+
+    def run(self):
+        nv, h = self._nv, self._h
+        if nv is None:
+            return
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        try:
+            while not self._halt.is_set():     # the timed region can be as short as ~80 ms: sample every 5 ms
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                self._halt.wait(0.1)
-        except Exception as exc:  # NVML missing: report it rather than fail the bench
-            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+                self._halt.wait(0.005)
+        except Exception as exc:
+            self.reasons.add(f"nvml_error:{type(exc).__name__}")
 
     def stop(self):
         self._halt.set()

@@ -233,8 +233,8 @@ def run_ours(args, rank, local_rank, world):
     desc = pol.desc()
     spec = tw.env.spec_from_env(env)
     out = _lib.Collected()
-    e2e_steps = max(1, min(args.steps, 3))
-    for _ in range(1):
+    e2e_steps = max(1, min(args.steps, 10))
+    for _ in range(2 if args.warmup >= 2 else 1):
         _lib.check(L.twr_ppo_collect_host(eng._h, C.byref(spec), hpol, C.byref(desc), args.episodes, 0.995, 0.995,
                                           C.byref(hb), C.byref(out)))
     barrier()

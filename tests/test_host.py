@@ -214,3 +214,24 @@ print(json.dumps(out))
     assert out["ppo_puzzle8_v1"] == ["PPO", "twisterl_b200.env", "twisterl_b200.collector", "twisterl_b200.nn", 81, 512, 4, [9, 9], 4]
     assert out["ppo_puzzle15_v1"] == ["PPO", "twisterl_b200.env", "twisterl_b200.collector", "twisterl_b200.nn", 256, 512, 4, [16, 16], 4]
     assert out["torch_shapes"] == [[6, 256], [6], [6], [6], [6], [6]]
+
+
+def test_balanced_schedule_host_model():
+    """scripts/sim_balance.py restates `struct Sched` of twr_forward_tc2.cu on the host: every (group, step) item is
+    issued exactly once, a pair never issues the same group twice within two items, hand-offs cannot deadlock, and the
+    benchmark shape (256 groups, 74 pairs, 32 steps) costs 111 item slots instead of 128."""
+    import importlib.util
+    import random
+    spec = importlib.util.spec_from_file_location("sim_balance", ROOT / "scripts" / "sim_balance.py")
+    sb = importlib.util.module_from_spec(spec)
+    argv = sys.argv
+    sys.argv = ["sim_balance.py"]
+    try:
+        spec.loader.exec_module(sb)
+    finally:
+        sys.argv = argv
+    assert sb.check(256, 74, 32, 2) == (111.0, 111)
+    assert sb.check(256, 74, 32, 0) == (128.0, 128)
+    rng = random.Random(3)
+    for _ in range(300):
+        sb.check(rng.randint(1, 700), rng.choice([2, 7, 66, 74]), rng.randint(1, 40), 2)

@@ -235,3 +235,23 @@ def test_balanced_schedule_host_model():
     rng = random.Random(3)
     for _ in range(300):
         sb.check(rng.randint(1, 700), rng.choice([2, 7, 66, 74]), rng.randint(1, 40), 2)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/twisterl_b200.h must be usable from C (the drop-in boundary is a C ABI): compile a C99 translation unit
+    against it with -pedantic, link the shared library and call an entry point that needs no device."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "twisterl_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { twr_env_spec s = {0, 4, 4, 1, 2, 256}; printf("%d %lld\\n", twr_abi_version(), '
+                   '(long long)twr_max_records(&s, 10)); return twr_abi_version() == TWR_ABI_VERSION ? 0 : 1; }\n')
+    libdir = ROOT / "twisterl_b200" / "lib"
+    exe = tmp_path / "abi"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(src),
+                        f"-L{libdir}", "-ltwisterl_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split() == ["2", "30"], (r.stdout, r.stderr)   # 10 episodes x (2*1 + 1) records

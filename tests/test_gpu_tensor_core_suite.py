@@ -17,7 +17,7 @@ def test_gpu_suites_on_the_tensor_core_path():
         pytest.skip("already running on the f16x2 path")
     env = dict(os.environ, TWISTERL_B200_PRECISION="f16x2")
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_parity.py",
-                        "tests/test_gpu_eval.py", "tests/test_gpu_az.py"], cwd=ROOT, env=env, capture_output=True, text=True,
+                        "tests/test_gpu_eval.py", "tests/test_gpu_az.py", "tests/test_cpp_host.py"], cwd=ROOT, env=env, capture_output=True, text=True,
                        timeout=1500)
     assert r.returncode == 0, (r.stdout[-4000:] + r.stderr[-2000:])
     assert " passed" in r.stdout

@@ -250,6 +250,41 @@ public:
     }
 };
 
+// A batch of envs of one spec on the device (the parity API of the C header): reset / set_state / step / queries
+class Envs {
+public:
+    Envs(Engine& eng, const twr_env_spec& spec, int64_t n) : n_(n), cells_(spec.width * spec.height) { check(twr_envs_create(eng.handle(), &spec, n, &h_)); }
+    ~Envs() { if (h_) twr_envs_destroy(h_); }
+    Envs(const Envs&) = delete;
+    Envs& operator=(const Envs&) = delete;
+    twr_envs* handle() const { return h_; }
+    void set_state(const std::vector<int64_t>& states) { check(twr_envs_set_state(h_, states.data())); }        // [n][cells]
+    void reset(uint32_t env_id_base = 0, uint32_t collect_id = 0) { check(twr_envs_reset(h_, env_id_base, collect_id)); }
+    void step(const std::vector<int32_t>& actions) { check(twr_envs_step(h_, actions.data())); }
+    std::vector<int64_t> get_state() { std::vector<int64_t> s((size_t)(n_ * cells_)); check(twr_envs_get_state(h_, s.data())); return s; }
+    std::vector<int32_t> observe() { std::vector<int32_t> o((size_t)(n_ * cells_)); check(twr_envs_observe(h_, o.data())); return o; }
+    std::vector<float> reward() { std::vector<float> r((size_t)n_); check(twr_envs_reward(h_, r.data())); return r; }
+    std::vector<uint8_t> is_final() { std::vector<uint8_t> f((size_t)n_); check(twr_envs_is_final(h_, f.data())); return f; }
+
+private:
+    twr_envs* h_ = nullptr;
+    int64_t n_;
+    int cells_;
+};
+
+// rl/solve.rs:73-101: best of num_searches rollouts from the state held by the one-env batch `start`
+// -> ((success, reward), actions)
+inline std::pair<std::pair<float, float>, std::vector<size_t>> solve(Envs& start, Policy& policy, bool deterministic, size_t num_searches,
+                                                                     size_t num_mcts_searches = 0, float C = 1.41f,
+                                                                     size_t max_expand_depth = 1, size_t max_actions = 4096) {
+    float s = 0.f, r = 0.f;
+    int32_t n = 0;
+    std::vector<int32_t> acts(max_actions);
+    check(twr_solve(policy.engine().handle(), start.handle(), policy.handle(), deterministic ? 1 : 0, (int32_t)num_searches,
+                    (int32_t)num_mcts_searches, C, (int32_t)max_expand_depth, &s, &r, acts.data(), (int32_t)max_actions, &n));
+    return {{s, r}, std::vector<size_t>(acts.begin(), acts.begin() + n)};
+}
+
 // rl/evaluate.rs:22-89 -> (success rate, mean reward); `seed` and `num_cores` of the reference signature have no effect here
 inline std::pair<float, float> evaluate(const twr_env_spec& env, Policy& policy, size_t num_episodes, bool deterministic,
                                         size_t num_searches, size_t num_mcts_searches = 0, float C = 1.41f, size_t max_expand_depth = 1) {

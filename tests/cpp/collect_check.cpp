@@ -33,6 +33,15 @@ int main(int argc, char** argv) {
         eng.set_collect_id(99);
         const auto ev = twisterl::evaluate(env, policy, 64, true, 1);
 
+        // solve from a board two moves away from solved (rl/solve.rs:73-101): the action list must solve it
+        twisterl::Envs start(eng, twisterl::Puzzle(4, 4, 1, 2, 256), 1);
+        start.set_state({1, 5, 2, 3, 4, 0, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15});
+        const auto sol = twisterl::solve(start, policy, false, 64);
+        if (sol.first.first == 1.0f) {
+            for (size_t act : sol.second) start.step({(int32_t)act});
+            if (!start.is_final()[0] || start.reward()[0] != 1.0f) return 5;
+        }
+
         std::FILE* o = std::fopen(argv[2], "wb");
         if (!o) return 2;
         const int64_t R = (int64_t)d.values.size();

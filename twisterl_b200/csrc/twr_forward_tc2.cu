@@ -723,12 +723,13 @@ Tc2Params make_params2(const PolicyDev& p) {
 
 int g_sms = 0;
 std::mutex g_tmap_mu;
-std::map<const void*, CUtensorMap> g_tmaps;
+std::map<std::pair<const void*, size_t>, CUtensorMap> g_tmaps;   // keyed by (image address, bytes): a freed image's address can be reused by a larger one
 
 // Tensor map over the packed operand image viewed as [rows][128 bytes]; one 128 x 128 box = one ring slot.
 bool get_tmap(const void* pack, size_t bytes, CUtensorMap* out) {
     std::lock_guard<std::mutex> lk(g_tmap_mu);
-    auto it = g_tmaps.find(pack);
+    const std::pair<const void*, size_t> key(pack, bytes);
+    auto it = g_tmaps.find(key);
     if (it != g_tmaps.end()) { *out = it->second; return true; }
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -745,7 +746,7 @@ bool get_tmap(const void* pack, size_t bytes, CUtensorMap* out) {
                                                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
-    g_tmaps[pack] = m;
+    g_tmaps[key] = m;
     *out = m;
     return true;
 }

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,11 @@ struct twr_engine {
     int32_t* ep_len_id = nullptr; int64_t cap_E = 0;
     int64_t cap_B = 0; int cap_T = 0; int64_t cap_R = 0; int cap_cells = 0;
     cudaStream_t copy_stream = nullptr;
+    std::map<uint64_t, float> survive_half;   // (env, batch) shape -> fraction of envs alive past half the horizon, last collect
+    uint64_t hint_key = 0; int64_t hint_B = 0;
+    void note_survival() {                    // call after h_stats of an enqueue_collect has landed
+        if (hint_B > 0) survive_half[hint_key] = (float)((double)(h_stats[3] & 0xFFFFFFFFull) / (double)hint_B);
+    }
     int32_t* bal_flags = nullptr;   // hand-off counters of the balanced pair-kernel schedule (one per CTA pair)
     int bal_delta = 2;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
@@ -768,6 +774,13 @@ static int ensure_collect_buffers(twr_engine* e, int64_t B, int T, int cells, in
 
 // Enqueue one (sub-)collect of B local episodes on the engine stream: reset -> T x (forward [+ step]) -> GAE ->
 // offsets -> compaction into output set `which`.  No host synchronisation.
+static uint64_t hint_key_of(const EnvParams& p, int64_t B) {
+    uint64_t k = 1469598103934665603ull;
+    const int64_t f[] = {p.kind, p.W, p.H, p.difficulty, p.depth_slope, p.max_depth, B};
+    for (int64_t v : f) { k ^= (uint64_t)v; k *= 1099511628211ull; }
+    return k;
+}
+
 static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev& dev, int64_t B, EnvIds ids, uint32_t cid,
                            float gamma, float lambda, int which, int* n_fwd_out) {
     CollectBuffers& b = e->buf;
@@ -790,7 +803,16 @@ static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev&
         // Persistent chunks: one launch covers `chunk` consecutive steps of every tile (envs stay with their
         // CTA pair, finished envs idle), then the live list is re-compacted.  Short episodes use chunk 1.
         int chunk = T / 8 < 1 ? 1 : (T / 8 > 32 ? 32 : T / 8);
+        // Adaptive: when the previous collect of this (env, batch) shape kept >= 90 % of its envs alive past half of the
+        // horizon, compacting every T/8 steps buys nothing and the launches are made 4x longer (results are identical
+        // for any chunking; a policy that starts to finish early flips the hint back after one collect)
+        e->hint_key = hint_key_of(env, B);
+        {
+            auto it = e->survive_half.find(e->hint_key);
+            if (it != e->survive_half.end() && it->second >= 0.9f) chunk = T / 2 < 1 ? 1 : (T / 2 > 128 ? 128 : T / 2);
+        }
         if (const char* c = getenv("TWISTERL_B200_CHUNK")) { const int v = atoi(c); if (v >= 1) chunk = v; }
+        int ci_half = -1;
         int bal_delta = e->bal_delta;
         if (const char* c = getenv("TWISTERL_B200_BALANCE")) bal_delta = atoi(c);   // 0 switches the time-split schedule off
         CU_TRY(cudaMemsetAsync(b.ep_len, 0, sizeof(int32_t) * (size_t)B, st));
@@ -798,6 +820,7 @@ static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev&
         int32_t* nxt = b.live_b;
         for (int t0 = 0, ci = 0; t0 < T; t0 += chunk, ++ci) {
             const int cnt = T - t0 < chunk ? T - t0 : chunk;
+            if (ci_half < 0 && 2 * t0 >= T) ci_half = ci;          // first compaction boundary in the second half of the horizon
             fa.t = t0; fa.t_count = cnt; fa.live = cur; fa.n_live_ptr = b.n_live + ci;
             sa.t = t0;
             fa.fused = 1; fa.step = sa; fa.cb = b; fa.live_next = cnt == 1 ? nxt : nullptr;
@@ -841,7 +864,11 @@ static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev&
             if (cnt > 1) launch_compact_live(st, cur, b.n_live + ci, b.ep_len, B, nxt, b.n_live + ci + 1);
             int32_t* tmp = cur; cur = nxt; nxt = tmp;
         }
+        // envs still alive at that boundary -> stats[3] (read back with the other statistics; feeds the chunk hint)
+        if (ci_half >= 0) CU_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(b.stats) + 24, b.n_live + ci_half, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        e->hint_B = ci_half >= 0 ? B : 0;
     } else {
+        e->hint_B = 0;
         for (int t = 0; t < T; ++t) {
             int32_t* cur = (t & 1) ? b.live_b : b.live_a;
             int32_t* nxt = (t & 1) ? b.live_a : b.live_b;
@@ -912,6 +939,7 @@ int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p
     if (e->timing) cudaEventRecord(e->ev_t1, st);
     CU_TRY(cudaMemcpyAsync(e->h_stats, e->buf.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    e->note_survival();
     finish_timing(e, n_fwd);
     CollectBuffers& b = e->buf;
     twr_collected& c = e->last;
@@ -1021,6 +1049,7 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
         CU_TRY(cudaMemcpyAsync(e->h_stats, e->buf.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, e->stream));
         CU_TRY(cudaEventRecord(e->ev_done[which], e->stream));
         CU_TRY(cudaStreamSynchronize(e->stream));       // record count of this sub-batch -> host offsets
+        e->note_survival();
         const size_t R = (size_t)e->h_stats[1];
         successes += (int64_t)e->h_stats[0];
         double rs; memcpy(&rs, &e->h_stats[2], sizeof(double)); reward_sum += rs;

@@ -232,6 +232,7 @@ def test_balanced_schedule_host_model():
         sys.argv = argv
     assert sb.check(256, 74, 32, 2) == (111.0, 111)
     assert sb.check(256, 74, 32, 0) == (128.0, 128)
+    assert sb.check(256, 74, 128, 2)[1] == 3 * 128 + 59          # the adaptive 128-step launches: ceil(34 * 128 / 74) extra slots
     rng = random.Random(3)
     for _ in range(300):
         sb.check(rng.randint(1, 700), rng.choice([2, 7, 66, 74]), rng.randint(1, 40), 2)

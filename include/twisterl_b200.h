@@ -106,6 +106,8 @@ typedef struct {
      * v = emb_size / obs_shape[1 - conv_dim], emb_bias stays [emb_size]; the observation indices then range over
      * obs_shape[0] * obs_shape[1]. */
     int32_t obs_shape[2], obs_shape_len, conv_dim;
+    /* the three Sequentials (rust/src/nn/modules.rs:16-34): 0..4 common Linears, 1..4 per head; the shape
+     * "one common Linear+ReLU, single-Linear heads" runs the tcgen05 / fp32 tile kernels, any other the generic fp32 kernel */
     const twr_linear_desc* common;     int32_t n_common;
     const twr_linear_desc* action_net; int32_t n_action;
     const twr_linear_desc* value_net;  int32_t n_value;

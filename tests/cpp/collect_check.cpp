@@ -58,10 +58,14 @@ int main(int argc, char** argv) {
         std::fclose(o);
         std::printf("records %lld successes %lld eval %.4f %.4f\n", (long long)R, (long long)d.successes, ev.first, ev.second);
 
-        // error behaviour: a policy with two common layers is not implemented on the device -> twisterl::Error
+        // error behaviour: a value head that does not end in one output is rejected -> twisterl::Error
+        twisterl::PolicyWeights bad = w;
+        bad.value_net[0] = twisterl::Linear{std::vector<float>(256 * 2, 0.f), std::vector<float>(2, 0.f), false};
+        try { twisterl::Policy p2(eng, bad); return 3; } catch (const twisterl::Error& e) { if (e.status != TWR_ERR_UNSUPPORTED) return 4; }
+        // a second common layer is fine (general layer stacks)
         twisterl::PolicyWeights deep = w;
         deep.common.push_back(twisterl::Linear{std::vector<float>(256 * 256, 0.f), std::vector<float>(256, 0.f), true});
-        try { twisterl::Policy p2(eng, deep); return 3; } catch (const twisterl::Error& e) { if (e.status != TWR_ERR_UNSUPPORTED) return 4; }
+        twisterl::Policy p3(eng, deep);
         return 0;
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());

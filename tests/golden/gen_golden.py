@@ -14,6 +14,8 @@ Outputs (tests/golden/):
                            without twists and with the {identity, transpose} twist set
   policy_synth.npz      -- same for seeded synthetic weights on the puzzle8 / grid_world shapes
                            (weights are regenerated from the seed at test time, only I/O is stored)
+  policy_deep.npz       -- the reference's torch BasicPolicy with deeper stacks (common_layers=(256,128),
+                           policy_layers=(64,), value_layers=(32,)), with and without twists, seeded synthetic weights
   policy_conv1d.npz     -- the reference's torch Conv1dPolicy (both conv_dim values, with and without twists) on
                            seeded synthetic weights, puzzle15 shape
 """
@@ -44,7 +46,7 @@ twisterl.twisterl = stub
 from twisterl.nn.policy import BasicPolicy, Conv1dPolicy  # noqa: E402
 
 sys.path.insert(0, str(OUT.parent))
-from helpers import scramble_states, synth_conv_state_dict, synth_state_dict, transpose_twists  # noqa: E402
+from helpers import scramble_states, synth_conv_state_dict, synth_deep_state_dict, synth_state_dict, transpose_twists  # noqa: E402
 
 
 def parse_boards(text, names):
@@ -182,6 +184,25 @@ def main():
             out[f"dim{conv_dim}.{tag}.values"] = v.numpy().astype(np.float32).reshape(-1)
         out[f"dim{conv_dim}.seed"] = np.int64(seed)
     np.savez(OUT / "policy_conv1d.npz", **out)
+
+    # ---- deeper layer stacks: BasicPolicy(common_layers=(256,128), policy_layers=(64,), value_layers=(32,))
+    out = {}
+    rng = np.random.default_rng(152)
+    st = scramble_states(rng, 192, 4, 4, 64)
+    x = one_hot(st)
+    perm_idx = rng.integers(0, 2, size=len(st)).astype(np.int64)
+    dsd = synth_deep_state_dict(1520, 256, 512, (256, 128), (64,), (32,), 4)
+    out["states"] = st; out["twist_perm_idx"] = perm_idx.astype(np.int32); out["seed"] = np.int64(1520)
+    for tag, perms in (("plain", ((), ())), ("twist", (obs_perms, act_perms))):
+        pol = BasicPolicy([16, 16], 4, 512, common_layers=(256, 128), policy_layers=(64,), value_layers=(32,),
+                          obs_perms=perms[0], act_perms=perms[1], device="cpu")
+        pol.load_state_dict({k: torch.as_tensor(v) for k, v in dsd.items()})
+        pol.eval()
+        with torch.no_grad():
+            l, v = pol(x) if tag == "plain" else pol(x, perm_indices=torch.as_tensor(perm_idx))
+        out[f"{tag}.logits"] = l.numpy().astype(np.float32)
+        out[f"{tag}.values"] = v.numpy().astype(np.float32).reshape(-1)
+    np.savez(OUT / "policy_deep.npz", **out)
     print("golden fixtures written to", OUT)
 
 

@@ -32,6 +32,25 @@ def synth_conv_state_dict(seed, n_in, v, emb, hidden, n_act):
             "value.0.weight": f(0.05, 1, hidden), "value.0.bias": b(1)}
 
 
+def synth_deep_state_dict(seed, obs_size, emb, common, policy, value, n_act):
+    """Seeded weights of a BasicPolicy with deeper stacks (common_layers=common, policy_layers=policy,
+    value_layers=value): torch Sequential indices 0, 2, 4, .. (a ReLU sits between the Linears)."""
+    g = np.random.default_rng(seed)
+    f = lambda *s: (g.standard_normal(s) * 0.08).astype(np.float32)
+    b = lambda n: g.uniform(-0.05, 0.05, size=n).astype(np.float32)
+    sd = {"embeddings.weight": f(emb, obs_size), "embeddings.bias": b(emb)}
+    width = emb
+    for k, w in enumerate(common):
+        sd[f"common.{2 * k}.weight"], sd[f"common.{2 * k}.bias"] = f(w, width), b(w)
+        width = w
+    for name, layers, last in (("action", policy, n_act), ("value", value, 1)):
+        wd = width
+        for k, w in enumerate(tuple(layers) + (last,)):
+            sd[f"{name}.{2 * k}.weight"], sd[f"{name}.{2 * k}.bias"] = f(w, wd), b(w)
+            wd = w
+    return sd
+
+
 def transpose_twists(w):
     """{identity, main-diagonal transpose} twist set for a square w x w puzzle."""
     N = w * w

@@ -18,6 +18,22 @@ def make_policies(sd, obs_size, obs_perms=(), act_perms=()):
     return pol, orc.Policy.from_torch_state_dict(sd, obs_perms, act_perms)
 
 
+def make_policies_general(sd, obs_size, obs_perms=(), act_perms=()):
+    """(device policy, oracle policy) from ANY BasicPolicy state dict (deeper common / head stacks included), the way
+    sequential_to_rust exports them (nn/utils.py:17-44): a Linear carries ReLU when a ReLU follows it in the Sequential,
+    i.e. every common layer and every head layer but the last."""
+    from twisterl_b200 import nn as twn
+
+    def stack(name, relu_last):
+        idxs = sorted({int(k.split(".")[1]) for k in sd if k.startswith(name + ".")})
+        return twn.Sequential([twn.Linear(sd[f"{name}.{i}.weight"].T.flatten(), sd[f"{name}.{i}.bias"], relu_last or n + 1 < len(idxs))
+                               for n, i in enumerate(idxs)])
+    pol = twn.Policy(twn.EmbeddingBag(sd["embeddings.weight"].T, sd["embeddings.bias"], True, [obs_size], 0),
+                     stack("common", True), stack("action", False), stack("value", False),
+                     [list(p) for p in obs_perms], [list(p) for p in act_perms])
+    return pol, orc.Policy.from_torch_state_dict(sd, obs_perms, act_perms)
+
+
 def make_conv1d_policies(sd, obs_shape, conv_dim, obs_perms=(), act_perms=()):
     """(device policy, oracle policy) of a Conv1dPolicy, via Conv1dPolicy.to_rust()'s layouts (nn/policy.py:259-266)."""
     from twisterl_b200 import nn as twn

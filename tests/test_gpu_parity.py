@@ -213,7 +213,7 @@ def test_policy_scalar_api_and_unsupported_shapes(eng):
     ml, v = pol.forward(o, masks)
     assert ml[1] == -1e10 and len(ml) == 4
     deep = tw.nn.Policy(pol.embeddings, tw.nn.Sequential(pol.common.layers * 2), pol.action_net, pol.value_net, [], [])
-    with pytest.raises(RuntimeError, match="one common"):
+    with pytest.raises(RuntimeError, match="do not chain"):                   # Linear(512,256) twice: sizes do not chain
         deep.device_handle(eng)
     conv = tw.nn.Policy(tw.nn.EmbeddingBag(np.zeros((15, 32)), np.zeros(512), True, [16, 16], 0), pol.common,
                         pol.action_net, pol.value_net, [], [])
@@ -555,3 +555,41 @@ def test_collect_mid_size_sampled_replay(eng, E):
     d = col.collect(env, pol)
     rep = check_collect_against_oracle(d, ospec, opol, seed=eng.seed, collect_id=17, gamma=0.995, lam=0.995, tol=TOL, stride=211)
     assert rep["records"] > 200
+
+
+def test_deep_stack_policy_forward_and_collect(eng):
+    """SURVEY 8f row f4, second half: general layer stacks run k_forward_generic -- forward against the reference's own
+    torch BasicPolicy with deeper stacks (golden fixture), +/- twists, a collect replayed through the oracle, evaluate,
+    a head-only policy (no common layer), and the in-place weight refresh."""
+    import twisterl_b200 as tw
+    from helpers import synth_deep_state_dict
+    from parity import check_collect_against_oracle, make_policies_general
+    from twisterl_b200.nn import forward_obs
+    g = np.load(GOLDEN / "policy_deep.npz")
+    sd = synth_deep_state_dict(int(g["seed"]), 256, 512, (256, 128), (64,), (32,), 4)
+    obs = obs_from_states(g["states"])
+    pol, opol = make_policies_general(sd, 256)
+    l, v = forward_obs(eng, pol, obs, None)
+    assert _close(l, g["plain.logits"], 1e-5) and _close(v, g["plain.values"], 1e-5)       # fp32 kernel on either engine
+    tpol, topol = make_policies_general(sd, 256, *transpose_twists(4))
+    l, v = forward_obs(eng, tpol, obs, g["twist_perm_idx"])
+    assert _close(l, g["twist.logits"], 1e-5) and _close(v, g["twist.values"], 1e-5)
+    ospec = orc.puzzle_spec(4, 4, 6, 2, 256)
+    env = tw.env.Puzzle(4, 4, 6, 2, 256)
+    eng.set_collect_id(41)
+    data = tw.collector.PPOCollector(150, 0.995, 0.995, 1, engine=eng).collect(env, tpol)
+    rep = check_collect_against_oracle(data, ospec, topol, seed=eng.seed, collect_id=41, gamma=0.995, lam=0.995, tol=1e-5)
+    assert rep["records"] == len(data.values_array)
+    s, r = tw.collector.evaluate(env, pol, 32, True, 1, 0, 0, 1.4, 1, 1) if eng is tw.default_engine() else (0.0, 0.0)
+    assert 0.0 <= s <= 1.0
+    # no common layer at all: heads read the embedding directly
+    hsd = synth_deep_state_dict(9, 256, 128, (), (), (), 4)
+    hpol, hopol = make_policies_general(hsd, 256)
+    l, v = forward_obs(eng, hpol, obs[:16], None)
+    ref = [hopol.raw_predict(o) for o in obs[:16]]
+    assert _close(l, np.array([x[0] for x in ref]), 1e-5) and _close(v, np.array([x[1] for x in ref]), 1e-5)
+    # twr_policy_update keeps the layer layout
+    sd2 = synth_deep_state_dict(77, 256, 512, (256, 128), (64,), (32,), 4)
+    pol2, opol2 = make_policies_general(sd2, 256)
+    l2, _ = forward_obs(eng, pol2, obs[:8], None)
+    assert _close(l2, np.array([opol2.raw_predict(o)[0] for o in obs[:8]]), 1e-5)

@@ -118,7 +118,8 @@ struct twr_policy {
     int32_t* d_obs_perms = nullptr;
     int32_t* d_act_perms = nullptr;
     void* tc_pack = nullptr;
-    int64_t off_emb_b = 0, off_w1 = 0, off_b1 = 0, off_wa = 0, off_ba = 0, off_wv = 0, off_bv = 0;
+    int64_t off_emb_b = 0;
+    std::vector<int64_t> off_w, off_b;   // blob offsets of every Linear (common..., action_net..., value_net...)
 };
 
 struct twr_envs {
@@ -276,21 +277,50 @@ int twr_engine_last_timing(const twr_engine* e, float* forward_ms, float* total_
 }
 
 // ----------------------------------------------------------------------- policy ---
+// every Linear of the three stacks, in blob order (common..., action_net..., value_net...)
+static std::vector<const twr_linear_desc*> all_linears(const twr_policy_desc* d) {
+    std::vector<const twr_linear_desc*> v;
+    for (int i = 0; i < d->n_common; ++i) v.push_back(d->common + i);
+    for (int i = 0; i < d->n_action; ++i) v.push_back(d->action_net + i);
+    for (int i = 0; i < d->n_value; ++i) v.push_back(d->value_net + i);
+    return v;
+}
+// the shape the tile kernels (tcgen05 / fp32) implement: embedding+ReLU -> one common Linear+ReLU -> single-Linear heads
+static bool is_standard_shape(const twr_policy_desc* d) {
+    return d->emb_apply_relu && d->n_common == 1 && d->n_action == 1 && d->n_value == 1 && d->common[0].apply_relu;
+}
+
 static int validate_desc(const twr_policy_desc* d) {
     if (!d || !d->emb_vectors || !d->emb_bias) return fail(TWR_ERR_INVALID, "policy desc / embedding is NULL");
     if (d->obs_shape_len != 1)
         return fail(TWR_ERR_UNSUPPORTED, "EmbeddingBag obs_shape must have 1 (BasicPolicy) or 2 (Conv1dPolicy) dimensions");
-    if (!d->emb_apply_relu) return fail(TWR_ERR_UNSUPPORTED, "EmbeddingBag without ReLU is not implemented");
-    if (d->n_common != 1 || !d->common) return fail(TWR_ERR_UNSUPPORTED, "exactly one common Linear layer is implemented");
-    if (d->n_action != 1 || !d->action_net || d->n_value != 1 || !d->value_net)
-        return fail(TWR_ERR_UNSUPPORTED, "single-Linear action and value heads are implemented");
-    const twr_linear_desc& c = d->common[0];
-    const twr_linear_desc& a = d->action_net[0];
-    const twr_linear_desc& v = d->value_net[0];
-    if (c.in != d->emb_size || !c.apply_relu) return fail(TWR_ERR_UNSUPPORTED, "common layer must be Linear(E,H)+ReLU");
-    if (a.in != c.out || a.apply_relu || a.out < 1 || a.out > TWR_MAX_ACTIONS)
-        return fail(TWR_ERR_UNSUPPORTED, "action head must be Linear(H,A) without ReLU, A <= 4");
-    if (v.in != c.out || v.apply_relu || v.out != 1) return fail(TWR_ERR_UNSUPPORTED, "value head must be Linear(H,1)");
+    if (d->n_common < 0 || d->n_common > TWR_MAX_STACK || d->n_action < 1 || d->n_action > TWR_MAX_STACK || d->n_value < 1 ||
+        d->n_value > TWR_MAX_STACK)
+        return fail(TWR_ERR_UNSUPPORTED, "layer stacks: 0..4 common Linears and 1..4 Linears per head are implemented");
+    if ((d->n_common > 0 && !d->common) || !d->action_net || !d->value_net) return fail(TWR_ERR_INVALID, "layer array is NULL");
+    if (d->emb_size < 1) return fail(TWR_ERR_INVALID, "empty embedding");
+    int width = d->emb_size;                                     // Sequential::forward chains the layers (nn/modules.rs:28-34)
+    for (int i = 0; i < d->n_common; ++i) {
+        const twr_linear_desc& l = d->common[i];
+        if (!l.weights || !l.bias || l.in != width || l.out < 1) return fail(TWR_ERR_INVALID, "common layer sizes do not chain");
+        width = l.out;
+    }
+    const int trunk = width;
+    for (int i = 0; i < d->n_action; ++i) {
+        const twr_linear_desc& l = d->action_net[i];
+        if (!l.weights || !l.bias || l.in != width || l.out < 1) return fail(TWR_ERR_INVALID, "action_net layer sizes do not chain");
+        width = l.out;
+    }
+    const twr_linear_desc& a = d->action_net[d->n_action - 1];
+    if (a.apply_relu || a.out > TWR_MAX_ACTIONS) return fail(TWR_ERR_UNSUPPORTED, "action head must end in a Linear without ReLU, at most 4 actions");
+    width = trunk;
+    for (int i = 0; i < d->n_value; ++i) {
+        const twr_linear_desc& l = d->value_net[i];
+        if (!l.weights || !l.bias || l.in != width || l.out < 1) return fail(TWR_ERR_INVALID, "value_net layer sizes do not chain");
+        width = l.out;
+    }
+    const twr_linear_desc& v = d->value_net[d->n_value - 1];
+    if (v.apply_relu || v.out != 1) return fail(TWR_ERR_UNSUPPORTED, "value head must end in a Linear(.., 1) without ReLU");
     if (d->n_perms < 0 || d->n_perms > 127) return fail(TWR_ERR_INVALID, "n_perms must be in 0..127");
     if (d->n_perms > 0 && (!d->obs_perms || !d->act_perms)) return fail(TWR_ERR_INVALID, "perm arrays are NULL");
     if (d->obs_size < 1 || d->obs_size >= 65536) return fail(TWR_ERR_UNSUPPORTED, "obs_size must be in 1..65535");
@@ -334,19 +364,22 @@ static int expand_conv1d(const twr_policy_desc* d, twr_policy_desc* out, std::ve
 
 static int upload_policy(twr_policy* p, const twr_policy_desc* d) {
     twr_engine* e = p->eng;
-    const int E = d->emb_size, H = d->common[0].out, A = d->action_net[0].out;
-    if (d->obs_size != p->dev.obs_size || E != p->dev.E || H != p->dev.H || A != p->dev.A || d->n_perms != p->dev.n_perms)
-        return fail(TWR_ERR_INVALID, "twr_policy_update: shapes differ from the ones the policy was created with");
+    const int E = d->emb_size, A = d->action_net[d->n_action - 1].out;
+    const std::vector<const twr_linear_desc*> lins = all_linears(d);
+    bool same = d->obs_size == p->dev.obs_size && E == p->dev.E && A == p->dev.A && d->n_perms == p->dev.n_perms &&
+                d->n_common == p->dev.n_common && d->n_action == p->dev.n_action && d->n_value == p->dev.n_value &&
+                (d->emb_apply_relu != 0) == (p->dev.emb_relu != 0) && is_standard_shape(d) == !p->dev.generic;
+    for (size_t i = 0; same && i < lins.size(); ++i)
+        same = lins[i]->in == p->dev.lin[i].in && lins[i]->out == p->dev.lin[i].out && (lins[i]->apply_relu != 0) == (p->dev.lin[i].relu != 0);
+    if (!same) return fail(TWR_ERR_INVALID, "twr_policy_update: shapes differ from the ones the policy was created with");
     cudaStream_t st = e->stream;
     float* b = p->d_blob;
     CU_TRY(cudaMemcpyAsync(b, d->emb_vectors, sizeof(float) * (size_t)d->obs_size * E, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(b + p->off_emb_b, d->emb_bias, sizeof(float) * E, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(b + p->off_w1, d->common[0].weights, sizeof(float) * (size_t)E * H, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(b + p->off_b1, d->common[0].bias, sizeof(float) * H, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(b + p->off_wa, d->action_net[0].weights, sizeof(float) * (size_t)H * A, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(b + p->off_ba, d->action_net[0].bias, sizeof(float) * A, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(b + p->off_wv, d->value_net[0].weights, sizeof(float) * H, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(b + p->off_bv, d->value_net[0].bias, sizeof(float), cudaMemcpyHostToDevice, st));
+    for (size_t i = 0; i < lins.size(); ++i) {
+        CU_TRY(cudaMemcpyAsync(b + p->off_w[i], lins[i]->weights, sizeof(float) * (size_t)lins[i]->in * lins[i]->out, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(b + p->off_b[i], lins[i]->bias, sizeof(float) * (size_t)lins[i]->out, cudaMemcpyHostToDevice, st));
+    }
     if (d->n_perms > 0) {
         CU_TRY(cudaMemcpyAsync(p->d_obs_perms, d->obs_perms, sizeof(int32_t) * (size_t)d->n_perms * d->obs_size, cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemcpyAsync(p->d_act_perms, d->act_perms, sizeof(int32_t) * (size_t)d->n_perms * A, cudaMemcpyHostToDevice, st));
@@ -367,22 +400,29 @@ int twr_policy_create(twr_engine* e, const twr_policy_desc* d_in, twr_policy** o
     const twr_policy_desc* d = &flat;
     if ((rc = validate_desc(d))) return rc;
     CU_TRY(cudaSetDevice(e->device));
-    const int E = d->emb_size, H = d->common[0].out, A = d->action_net[0].out;
+    const std::vector<const twr_linear_desc*> lins = all_linears(d);
+    const bool standard = is_standard_shape(d);
+    const int E = d->emb_size, A = d->action_net[d->n_action - 1].out;
+    const int H = d->n_common > 0 ? d->common[d->n_common - 1].out : E;     // trunk width
     twr_policy* p = new twr_policy();
     p->eng = e;
     p->dev.obs_size = d->obs_size; p->dev.E = E; p->dev.H = H; p->dev.A = A; p->dev.n_perms = d->n_perms;
     p->dev.n_obs = 0;
+    p->dev.generic = standard ? 0 : 1;
+    p->dev.emb_relu = d->emb_apply_relu ? 1 : 0;
+    p->dev.n_common = d->n_common; p->dev.n_action = d->n_action; p->dev.n_value = d->n_value;
     int64_t off = (int64_t)d->obs_size * E;
     p->off_emb_b = off; off += E;
-    p->off_w1 = off; off += (int64_t)E * H;
-    p->off_b1 = off; off += H;
-    p->off_wa = off; off += (int64_t)H * A;
-    p->off_ba = off; off += A;
-    p->off_wv = off; off += H;
-    p->off_bv = off; off += 1;
+    int max_width = E;
+    for (const twr_linear_desc* l : lins) {
+        p->off_w.push_back(off); off += (int64_t)l->in * l->out;
+        p->off_b.push_back(off); off += l->out;
+        if (l->out > max_width) max_width = l->out;
+    }
+    p->dev.max_width = max_width;
     p->blob_floats = off;
     bool use_tc = false;
-    {
+    if (standard) {
         PolicyDev probe = p->dev;
         probe.n_obs = 1;
         EnvParams dummy{};
@@ -394,6 +434,9 @@ int twr_policy_create(twr_engine* e, const twr_policy_desc* d_in, twr_policy** o
             delete p;
             return fail(TWR_ERR_UNSUPPORTED, std::string("policy shape not supported on the device: ") + why);
         }
+    } else if (max_width > 1024) {
+        delete p;
+        return fail(TWR_ERR_UNSUPPORTED, "general layer stacks are implemented for layer widths up to 1024");
     }
     if ((rc = dev_alloc(&p->d_blob, (size_t)p->blob_floats))) { delete p; return rc; }
     if (d->n_perms > 0) {
@@ -401,9 +444,13 @@ int twr_policy_create(twr_engine* e, const twr_policy_desc* d_in, twr_policy** o
             (rc = dev_alloc(&p->d_act_perms, (size_t)d->n_perms * A))) { twr_policy_destroy(p); return rc; }
     }
     p->dev.emb = p->d_blob; p->dev.emb_b = p->d_blob + p->off_emb_b;
-    p->dev.w1 = p->d_blob + p->off_w1; p->dev.b1 = p->d_blob + p->off_b1;
-    p->dev.wa = p->d_blob + p->off_wa; p->dev.ba = p->d_blob + p->off_ba;
-    p->dev.wv = p->d_blob + p->off_wv; p->dev.bv = p->d_blob + p->off_bv;
+    for (size_t i = 0; i < lins.size(); ++i)
+        p->dev.lin[i] = PolicyDev::Lin{p->d_blob + p->off_w[i], p->d_blob + p->off_b[i], lins[i]->in, lins[i]->out, lins[i]->apply_relu ? 1 : 0};
+    if (standard) {          // the tile kernels' named views of the same blob
+        p->dev.w1 = p->dev.lin[0].w; p->dev.b1 = p->dev.lin[0].b;
+        p->dev.wa = p->dev.lin[1].w; p->dev.ba = p->dev.lin[1].b;
+        p->dev.wv = p->dev.lin[2].w; p->dev.bv = p->dev.lin[2].b;
+    }
     p->dev.obs_perms = p->d_obs_perms; p->dev.act_perms = p->d_act_perms;
     if (use_tc) {
         const size_t bytes = forward_tc_pack_bytes(p->dev);
@@ -563,7 +610,8 @@ static int check_policy_env(const twr_policy* p, const EnvParams& env, PolicyDev
 }
 
 static void launch_forward(twr_engine* e, const PolicyDev& dev, const ForwardArgs& a) {
-    if (dev.tc_pack) launch_forward_tc(e->stream, dev, a);     // policies whose shape fits the tensor-core kernel (f16x2 engines)
+    if (dev.generic) launch_forward_generic(e->stream, dev, a);   // general layer stacks (f4)
+    else if (dev.tc_pack) launch_forward_tc(e->stream, dev, a);   // policies whose shape fits the tensor-core kernel (f16x2 engines)
     else launch_forward_fp32(e->stream, dev, a);
 }
 

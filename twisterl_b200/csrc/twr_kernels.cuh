@@ -19,7 +19,17 @@ struct PolicyDev {
     const int32_t* act_perms;  // [n_perms][A]
     // tensor-core operands (fp16 hi/lo split, UMMA canonical K-major tiles), see twr_forward_tc.cu
     const void* tc_pack;
+    // General layer stacks: any policy that is not "embedding+ReLU -> one common Linear+ReLU ->
+    // single-Linear heads" runs k_forward_generic (twr_forward_generic.cu) from this description instead.
+    int generic;                              // 1: the fields above (w1..bv, H) are unused
+    int emb_relu;
+    int n_common, n_action, n_value;          // Linear counts; lin[] holds common..., action_net..., value_net... in order
+    int max_width;                            // widest activation vector (embedding or any Linear output)
+    struct Lin { const float* w; const float* b; int in, out, relu; } lin[12];
 };
+#define TWR_MAX_STACK 4                       // Linears per stack
+size_t forward_generic_smem(const PolicyDev& p);
+void   launch_forward_generic(cudaStream_t s, const PolicyDev& p, const struct ForwardArgs& a);
 
 struct CollectBuffers {
     int64_t B;      // envs (episodes) in this collect

@@ -2,7 +2,7 @@
 every (group, step) is issued exactly once, that a pair never issues the same group twice within two items, and
 estimates the makespan (in item times) with the cross-pair hand-offs."""
 import sys
-MINBASE = int(sys.argv[1]) if len(sys.argv) > 1 else 3   # the kernel requires >= 3 own groups per pair
+MINBASE = int(sys.argv[1]) if len(sys.argv) > 1 else 2   # the kernel requires >= 2 own groups per pair
 
 
 def make_sched(G, P, T, pair, delta):
@@ -17,6 +17,9 @@ def make_sched(G, P, T, pair, delta):
             s["gA"], s["sA0"] = x0 // T, x0 % T
             s["nA"] = min(nX, T - s["sA0"]); s["nB"] = nX - s["nA"]
             dA = delta * (pair - (s["gA"] * T) // Lp) if s["sA0"] > 0 else 0
+            # the piece must end inside the pair's sequence (base * T + nX items): with few own groups the slack granted
+            # to late hand-offs is clamped (a shorter slack can only make the consumer wait, never deadlock)
+            dA = max(0, min(dA, base * T + nX - 1 - 2 * (s["sA0"] + s["nA"] - 1)))
             s["pA0"] = 2 * s["sA0"] + dA
         s["n_items"] = base * T + nX
     else:

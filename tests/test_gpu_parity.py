@@ -462,7 +462,8 @@ def test_collect_host_pipelined_matches_plain(eng, monkeypatch):
         assert np.array_equal(arr["rets"][:R], ref.additional_array("rets"))
 
 
-@pytest.mark.parametrize("E,difficulty,chunk,trained", [(65536, 128, None, False), (60000, 6, "8", True), (57100, 20, "5", False)])
+@pytest.mark.parametrize("E,difficulty,chunk,trained", [(65536, 128, None, False), (60000, 6, "8", True), (57100, 20, "5", False),
+                                                        (45000, 40, None, False), (38400, 24, "6", True)])     # the last two: two own groups per pair
 def test_collect_balanced_schedule_matches_plain(eng, monkeypatch, E, difficulty, chunk, trained):
     """The persistent pair kernel cuts left-over tile groups along time and hands them from CTA pair to CTA pair
     (Sched in twr_forward_tc2.cu).  Scheduling must not change a single byte: the same collect with the balanced

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) k_tc2_pack(PolicyDev p, Tc2Params t, __ha
 }
 
 // Item schedule of one CTA pair for a launch of T steps over G groups (256-env tiles pairs) on P pairs.
-// Plain: the pair owns groups pair, pair+P, ... and walks them step-major.  Balanced (T >= 4, >= 3 own groups per
+// Plain: the pair owns groups pair, pair+P, ... and walks them step-major.  Balanced (T >= 4, >= 2 own groups per
 // pair, G % P != 0): the G % P left-over groups are cut along time into pieces of <= Lp steps; piece k of a group
 // runs on the pair after the one that ran piece k-1, at item slots 2*step (+ bal_delta per hand-off), so no pair
 // does more than floor(G/P)*T + Lp items instead of (floor(G/P)+1)*T.  scripts/sim_balance.py is the host model.
@@ -182,7 +182,7 @@ __device__ __forceinline__ Sched make_sched(int G, int P, int T, int pair, int d
     Sched s;
     s.T = T; s.P = P; s.nA = 0; s.nB = 0; s.sA0 = 0; s.pA0 = 0; s.gA = 0;
     const int base = G / P, rem = G % P;
-    if (delta > 0 && T >= 4 && base >= 3 && rem > 0) {
+    if (delta > 0 && T >= 4 && base >= 2 && rem > 0) {
         s.lanes = base;
         const int X = rem * T;
         int Lp = (X + P - 1) / P;
@@ -191,7 +191,10 @@ __device__ __forceinline__ Sched make_sched(int G, int P, int T, int pair, int d
         if (nX > 0) {
             s.gA = x0 / T; s.sA0 = x0 % T;
             s.nA = min(nX, T - s.sA0); s.nB = nX - s.nA;
-            const int dA = s.sA0 > 0 ? delta * (pair - (s.gA * T) / Lp) : 0;
+            int dA = s.sA0 > 0 ? delta * (pair - (s.gA * T) / Lp) : 0;
+            // the piece must end inside this pair's sequence (base*T + nX items): with only two own groups the slack of
+            // late hand-offs is clamped -- a shorter slack can make the consumer wait, never deadlock
+            dA = max(0, min(dA, base * T + nX - 1 - 2 * (s.sA0 + s.nA - 1)));
             s.pA0 = 2 * s.sA0 + dA;
         }
         s.n_items = base * T + nX;

@@ -279,8 +279,11 @@ def run_ours(args, rank, local_rank, world):
             "roofline": {"bound": "tensor", "kernel": "k_forward_fp32" if args.precision == "fp32" else "k_forward_tc2",
                          "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s",
                          "frac": (achieved / pk["bf16"]) if achieved else None,
-                         # dram read+write bytes of one k_forward_tc2 launch (32 steps x 65536 envs), profiles/r1d_tc2_summary.md
-                         "traffic": 37_861_888 if (args.precision == "f16x2" and args.episodes == 65536) else None,
+                         # dram read+write bytes of one 32-step k_forward_tc2 launch over 65536 envs (profiles/r1f_tc2_summary.md;
+                         # the records it writes -- 88 MB algorithmic, the rest still sits in L2 when the launch ends);
+                         # steady-state launches cover 128 steps and move 4x as much
+                         "traffic": 44_504_576 if (args.precision == "f16x2" and args.episodes == 65536) else None,
+                         "traffic_launch_steps": 32,
                          "peak_source": pk["src"] + " bf16_tflops_sustained",
                          "forward_ms_per_launch": fwd_ms / max(fwd_launches, 1), "forward_share_of_step": fwd_ms / ms,
                          "algorithmic_flop_per_env_step": FLOP_PER_STEP["puzzle15"]},

@@ -594,3 +594,26 @@ def test_deep_stack_policy_forward_and_collect(eng):
     pol2, opol2 = make_policies_general(sd2, 256)
     l2, _ = forward_obs(eng, pol2, obs[:8], None)
     assert _close(l2, np.array([opol2.raw_predict(o)[0] for o in obs[:8]]), 1e-5)
+
+
+def test_collect_schedule_sweep_matches_plain(eng, monkeypatch):
+    """Batch sizes around every regime boundary of the persistent kernel's schedule (one / two / three tiles per CTA pair,
+    whole and ragged tile counts, left-over groups from 1 to P-1): balanced == plain, byte for byte."""
+    if PRECISION != "f16x2":
+        pytest.skip("the fused persistent kernel is the f16x2 path")
+    import twisterl_b200 as tw
+    from parity import make_policies
+    pol, _ = make_policies(synth_state_dict(5, 256, 512, 256, 4), 256)
+    env = tw.env.Puzzle(4, 4, 16, 2, 256)                      # horizon 33 -> 4-step launches (the shortest balanced ones)
+    for E in (1, 255, 257, 18944, 18945, 37887, 37889, 38000, 47000, 56831, 56833, 57088, 65535, 70001, 75776):
+        col = tw.collector.PPOCollector(E, 0.995, 0.995, 32, engine=eng)
+        out = []
+        for bal in ("0", "2"):
+            monkeypatch.setenv("TWISTERL_B200_BALANCE", bal)
+            eng.set_collect_id(3)
+            out.append(col.collect(env, pol))
+        a, b = out
+        assert np.array_equal(a.ep_len, b.ep_len) and a.stats == b.stats, E
+        assert np.array_equal(a.obs_array, b.obs_array) and np.array_equal(a.actions_array, b.actions_array), E
+        assert np.array_equal(a.logits_array, b.logits_array) and np.array_equal(a.values_array, b.values_array), E
+        assert np.array_equal(a.additional_array("rets"), b.additional_array("rets")), E

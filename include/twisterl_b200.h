@@ -124,6 +124,13 @@ int  twr_policy_create(twr_engine* e, const twr_policy_desc* desc, twr_policy** 
 /* In-place refresh with the same shapes (replaces rebuilding nn.Policy every iteration,
  * src/twisterl/rl/algorithm.py:91-93). */
 int  twr_policy_update(twr_policy* p, const twr_policy_desc* desc);
+/* Builds the policy straight from a safetensors checkpoint of the reference's BasicPolicy / Conv1dPolicy state dict
+ * (src/twisterl/utils.py:131-190: tensors embeddings.weight/bias or conv_layer.weight, common.{0,2,..}, action.{..},
+ * value.{..}; F32), putting the tensors into the layouts `to_rust()` produces (src/twisterl/nn/utils.py:17-75).
+ * obs_shape / conv_dim are only read for a Conv1d checkpoint; obs_perms / act_perms as in twr_policy_desc. */
+int  twr_policy_create_from_safetensors(twr_engine* e, const char* path, const int32_t* obs_shape, int32_t obs_shape_len,
+                                        int32_t conv_dim, const int32_t* obs_perms, const int32_t* act_perms,
+                                        int32_t n_perms, twr_policy** out);
 /* Flat fp32 parameter blob: [emb_vectors][emb_bias][common w][common b][action w][action b]
  * [value w][value b], each in the layout above.  update_from_device takes a DEVICE pointer
  * (e.g. the buffer an NCCL broadcast just filled). */

@@ -88,6 +88,19 @@ struct PolicyWeights {               // nn.Policy(embeddings, common, action_net
 class Policy {
 public:
     Policy(Engine& eng, const PolicyWeights& w) : eng_(&eng) { with_desc(w, [&](const twr_policy_desc& d) { check(twr_policy_create(eng.handle(), &d, &h_)); }); }
+    // straight from a safetensors checkpoint of the reference's BasicPolicy / Conv1dPolicy state dict (native reader)
+    static std::unique_ptr<Policy> from_safetensors(Engine& eng, const std::string& path, const std::vector<int32_t>& obs_shape = {},
+                                                    int conv_dim = 0, const std::vector<std::vector<int32_t>>& obs_perms = {},
+                                                    const std::vector<std::vector<int32_t>>& act_perms = {}) {
+        std::vector<int32_t> op, ap;
+        for (const auto& p : obs_perms) op.insert(op.end(), p.begin(), p.end());
+        for (const auto& p : act_perms) ap.insert(ap.end(), p.begin(), p.end());
+        std::unique_ptr<Policy> pol(new Policy(eng));
+        check(twr_policy_create_from_safetensors(eng.handle(), path.c_str(), obs_shape.empty() ? nullptr : obs_shape.data(),
+                                                 (int32_t)obs_shape.size(), conv_dim, op.empty() ? nullptr : op.data(),
+                                                 ap.empty() ? nullptr : ap.data(), (int32_t)obs_perms.size(), &pol->h_));
+        return pol;
+    }
     ~Policy() { if (h_) twr_policy_destroy(h_); }
     Policy(const Policy&) = delete;
     Policy& operator=(const Policy&) = delete;
@@ -97,6 +110,7 @@ public:
     Engine& engine() const { return *eng_; }
 
 private:
+    explicit Policy(Engine& eng) : eng_(&eng) {}
     template <class F>
     static void with_desc(const PolicyWeights& w, F&& f) {
         const EmbeddingBag& e = w.embeddings;

@@ -617,3 +617,41 @@ def test_collect_schedule_sweep_matches_plain(eng, monkeypatch):
         assert np.array_equal(a.obs_array, b.obs_array) and np.array_equal(a.actions_array, b.actions_array), E
         assert np.array_equal(a.logits_array, b.logits_array) and np.array_equal(a.values_array, b.values_array), E
         assert np.array_equal(a.additional_array("rets"), b.additional_array("rets")), E
+
+
+def test_native_safetensors_reader(eng, tmp_path):
+    """twr_policy_create_from_safetensors: checkpoints of the reference's state dicts (BasicPolicy with the shipped trained
+    weights, a deeper-stack BasicPolicy, a Conv1dPolicy) loaded natively give the same logits as the to_rust() route."""
+    st = pytest.importorskip("safetensors.numpy")
+    import twisterl_b200 as tw
+    from helpers import synth_conv_state_dict, synth_deep_state_dict
+    from parity import make_conv1d_policies, make_policies, make_policies_general
+    from twisterl_b200.nn import forward_obs
+    z, sd = trained15()
+    obs = obs_from_states(z["states"][:64])
+    twists = transpose_twists(4)
+    cases = [("basic", sd, make_policies(sd, 256, *twists)[0], dict(obs_perms=twists[0], act_perms=twists[1]))]
+    dsd = synth_deep_state_dict(5, 256, 512, (256, 128), (64,), (32,), 4)
+    cases.append(("deep", dsd, make_policies_general(dsd, 256)[0], {}))
+    csd = synth_conv_state_dict(6, 16, 32, 512, 256, 4)
+    cases.append(("conv", csd, make_conv1d_policies(csd, [16, 16], 1)[0], dict(obs_shape=[16, 16], conv_dim=1)))
+    for name, state, ref_pol, kw in cases:
+        path = tmp_path / f"{name}.safetensors"
+        st.save_file({k: np.ascontiguousarray(v, dtype=np.float32) for k, v in state.items()}, str(path), metadata={"format": "pt"})
+        pol = tw.nn.Policy.from_safetensors(path, engine=eng, **kw)
+        perm = (np.arange(len(obs)) % 2).astype(np.int32) if "obs_perms" in kw else None
+        l, v = forward_obs(eng, pol, obs, perm)
+        rl, rv = forward_obs(eng, ref_pol, obs, perm)
+        assert np.array_equal(l, rl) and np.array_equal(v, rv), name
+        pol.release()
+    # a collect runs on the natively loaded policy like on any other
+    path = tmp_path / "basic.safetensors"
+    pol = tw.nn.Policy.from_safetensors(path, engine=eng)
+    d = tw.collector.PPOCollector(64, 0.995, 0.995, 1, engine=eng).collect(tw.env.Puzzle(4, 4, 5, 2, 256), pol)
+    assert len(d.values_array) >= 64
+    bad = tmp_path / "bad.safetensors"
+    bad.write_bytes(b"\\x10\\x00\\x00\\x00\\x00\\x00\\x00\\x00{not json at all}")
+    with pytest.raises(RuntimeError, match="safetensors"):
+        tw.nn.Policy.from_safetensors(bad, engine=eng)
+    with pytest.raises(RuntimeError, match="cannot open"):
+        tw.nn.Policy.from_safetensors(tmp_path / "missing.safetensors", engine=eng)

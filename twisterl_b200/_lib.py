@@ -66,7 +66,7 @@ class HostBuffers(C.Structure):
 SYMBOLS = [
     "twr_abi_version", "twr_last_error", "twr_device_count", "twr_engine_create", "twr_engine_destroy",
     "twr_engine_synchronize", "twr_engine_launch_count", "twr_policy_create", "twr_policy_update",
-    "twr_policy_blob_floats", "twr_policy_update_from_device", "twr_policy_blob_device_ptr", "twr_policy_destroy",
+    "twr_policy_create_from_safetensors", "twr_policy_blob_floats", "twr_policy_update_from_device", "twr_policy_blob_device_ptr", "twr_policy_destroy",
     "twr_envs_create", "twr_envs_destroy", "twr_envs_set_difficulty", "twr_envs_set_state", "twr_envs_reset",
     "twr_envs_step", "twr_envs_get_state", "twr_envs_observe", "twr_envs_masks", "twr_envs_reward",
     "twr_envs_is_final", "twr_envs_success", "twr_envs_depth", "twr_policy_forward", "twr_policy_forward_obs", "twr_debug_forward_profile", "twr_sample", "twr_gae",
@@ -106,6 +106,7 @@ def load():
         L.twr_engine_last_timing.argtypes = [vp, f32p, f32p, i64p]
         L.twr_policy_create.argtypes = [vp, C.POINTER(PolicyDesc), C.POINTER(vp)]
         L.twr_policy_update.argtypes = [vp, C.POINTER(PolicyDesc)]
+        L.twr_policy_create_from_safetensors.argtypes = [vp, C.c_char_p, i32p, C.c_int32, C.c_int32, i32p, i32p, C.c_int32, C.POINTER(vp)]
         L.twr_policy_blob_floats.argtypes = [vp]; L.twr_policy_blob_floats.restype = C.c_int64
         L.twr_policy_update_from_device.argtypes = [vp, vp]
         L.twr_policy_blob_device_ptr.argtypes = [vp, C.POINTER(vp)]

@@ -15,7 +15,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libtwisterl_b200.so"
-SOURCES = ["twr_engine.cu", "twr_kernels.cu", "twr_forward_fp32.cu", "twr_forward_tc.cu", "twr_forward_tc2.cu", "twr_forward_generic.cu", "twr_mcts.cu"]
+SOURCES = ["twr_engine.cu", "twr_kernels.cu", "twr_forward_fp32.cu", "twr_forward_tc.cu", "twr_forward_tc2.cu", "twr_forward_generic.cu", "twr_mcts.cu", "twr_safetensors.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
 
@@ -31,7 +31,7 @@ def is_stale() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "twisterl_b200.h"]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.cpp")) + [PKG.parent / "include" / "twisterl_b200.h"]
     return any(d.stat().st_mtime > t for d in deps)
 
 

@@ -24,6 +24,10 @@ int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+}  // namespace
+// error hook for the other translation units of the library (twr_safetensors.cpp)
+extern "C" int twr_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+namespace {
 
 #define CU_TRY(expr)                                                                              \
     do {                                                                                          \

@@ -103,10 +103,16 @@ class Policy:
 
     @property
     def num_actions(self) -> int:
+        if getattr(self, "_native", False):
+            return self._native_actions
         return int(self.action_net.layers[-1].out)
 
     def device_handle(self, engine: _lib.Engine | None = None):
         engine = engine or _lib.default_engine()
+        if getattr(self, "_native", False):
+            if self._dev is None or self._dev[0] is not engine:
+                raise RuntimeError("a policy loaded with from_safetensors lives on the engine it was loaded on")
+            return self._dev[1]
         if self._dev is None or self._dev[0] is not engine:
             self.release()
             h = C.c_void_p()
@@ -121,6 +127,28 @@ class Policy:
             if getattr(eng, "_h", None):
                 _lib.load().twr_policy_destroy(h)
             self._dev = None
+
+    @classmethod
+    def from_safetensors(cls, path, obs_shape=None, conv_dim: int = 0, obs_perms=(), act_perms=(), engine: _lib.Engine | None = None):
+        """Device policy built by the library's native safetensors reader (twr_policy_create_from_safetensors) from a
+        checkpoint of the reference's BasicPolicy / Conv1dPolicy state dict -- no torch, no to_rust() round trip.
+        The result only lives on `engine` (no host copy of the weights; `predict` / `desc` are not available)."""
+        engine = engine or _lib.default_engine()
+        self = cls.__new__(cls)
+        two_d = lambda a: (np.ascontiguousarray(a, dtype=np.int32).reshape(len(a), -1) if len(a) else np.zeros((0, 0), np.int32))
+        self.obs_perms, self.act_perms = two_d(obs_perms), two_d(act_perms)
+        self._keep = None
+        self._native_actions = int(self.act_perms.shape[1]) if len(act_perms) else 4
+        shape = np.ascontiguousarray(obs_shape if obs_shape is not None else [], dtype=np.int32)
+        h = C.c_void_p()
+        n_perms = int(len(obs_perms))
+        _lib.check(_lib.load().twr_policy_create_from_safetensors(
+            engine._h, str(path).encode(), shape.ctypes.data_as(_lib.i32p) if shape.size else None, int(shape.size), int(conv_dim),
+            self.obs_perms.ctypes.data_as(_lib.i32p) if n_perms else None, self.act_perms.ctypes.data_as(_lib.i32p) if n_perms else None,
+            n_perms, C.byref(h)))
+        self._dev = (engine, h)
+        self._native = True
+        return self
 
     def __del__(self):
         try:

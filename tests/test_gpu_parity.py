@@ -479,7 +479,7 @@ def test_collect_balanced_schedule_matches_plain(eng, monkeypatch, E, difficulty
     if chunk:
         monkeypatch.setenv("TWISTERL_B200_CHUNK", chunk)
     out = []
-    for bal in ("0", "2", "6"):
+    for bal in ("0", "2", "3", "6"):
         monkeypatch.setenv("TWISTERL_B200_BALANCE", bal)
         eng.set_collect_id(9)
         d = col.collect(env, pol)

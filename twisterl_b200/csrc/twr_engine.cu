@@ -102,7 +102,7 @@ struct twr_engine {
         if (hint_B > 0) survive_half[hint_key] = (float)((double)(h_stats[3] & 0xFFFFFFFFull) / (double)hint_B);
     }
     int32_t* bal_flags = nullptr;   // hand-off counters of the balanced pair-kernel schedule (one per CTA pair)
-    int bal_delta = 2;
+    int bal_delta = 3;
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     unsigned long long* h_stats = nullptr;   // pinned
     bool has_last = false;

@@ -344,29 +344,19 @@ void launch_episode_offsets(cudaStream_t st, const CollectBuffers& b, const EnvI
 // axis of the time-major records, stores are coalesced along time inside each episode's
 // contiguous output range.  The 16-byte state is expanded to the sparse one-hot indices the
 // reference returns from Env::observe (obs[i] = i*N + board[i]).
-template <typename T>
-__device__ __forceinline__ void transpose_field(const T* __restrict__ src, T* __restrict__ dst, T (*tile)[33],
-                                                const CollectBuffers& b, int64_t e0, int t0, const int* lens,
-                                                const long long* offs) {
-    for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
-        const int t = t0 + ty;
-        const int64_t e = e0 + threadIdx.x;
-        if (t < b.Tmax && e < b.B && t < lens[threadIdx.x]) tile[ty][threadIdx.x] = src[(int64_t)t * b.B + e];
-    }
-    __syncthreads();
-    for (int ey = threadIdx.y; ey < 32; ey += blockDim.y) {
-        const int t = t0 + threadIdx.x;
-        if (e0 + ey < b.B && t < lens[ey]) dst[offs[ey] + t] = tile[threadIdx.x][ey];
-    }
-    __syncthreads();
-}
-
+// One block transposes a 32-episode x 32-step tile of EVERY field: all loads of the tile (4 floats, 2 bytes and 2
+// 16-byte words per record, 50 B) are issued before the single barrier, so a block keeps ~50 KB in flight instead of
+// 4 KB per field phase; then each episode's run of records is written out contiguously.
+struct CompactTiles {
+    float f[4][32][33];
+    uint8_t b[2][32][33];
+    uint4 q[2][32][33];
+};
 __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, int A) {
+    extern __shared__ __align__(16) unsigned char compact_smem[];
+    CompactTiles& tl = *reinterpret_cast<CompactTiles*>(compact_smem);
     __shared__ int lens[32];
     __shared__ long long offs[32];
-    __shared__ float tile_f[32][33];
-    __shared__ uint8_t tile_b[32][33];
-    __shared__ uint4 tile_q[32][33];
     const int64_t e0 = (int64_t)blockIdx.x * 32;
     const int t0 = blockIdx.y * 32;
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -380,47 +370,92 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
     for (int i = 0; i < 32; ++i) maxlen = max(maxlen, lens[i]);
     if (t0 >= maxlen) return;
 
-    transpose_field<float>(b.rec_value, b.out_values, tile_f, b, e0, t0, lens, offs);
-    transpose_field<float>(b.rec_reward, b.out_rewards, tile_f, b, e0, t0, lens, offs);
-    transpose_field<float>(b.rec_adv, b.out_advs, tile_f, b, e0, t0, lens, offs);
-    transpose_field<float>(b.rec_ret, b.out_rets, tile_f, b, e0, t0, lens, offs);
-    transpose_field<uint8_t>(b.rec_action, b.out_actions, tile_b, b, e0, t0, lens, offs);
-    transpose_field<uint8_t>(reinterpret_cast<const uint8_t*>(b.rec_perm), reinterpret_cast<uint8_t*>(b.out_perms), tile_b,
-                             b, e0, t0, lens, offs);
-
-    // logits: [t][env] float4 -> [record][A] floats
-    for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
-        const int t = t0 + ty;
+    // ---- load phase: row t of the time-major records, 32 consecutive envs per warp (coalesced)
+    {
         const int64_t e = e0 + threadIdx.x;
-        if (e < b.B && t < lens[threadIdx.x]) tile_q[ty][threadIdx.x] = reinterpret_cast<const uint4*>(b.rec_logits)[(int64_t)t * b.B + e];
-    }
-    __syncthreads();
-    for (int ey = threadIdx.y; ey < 32; ey += blockDim.y) {
-        const int nt = min(32, lens[ey] - t0);                 // records of this episode in the tile
-        if (e0 + ey >= b.B || nt <= 0) continue;
-        float* dst = b.out_logits + (offs[ey] + t0) * A;
-        for (int j = threadIdx.x; j < nt * A; j += 32) {
-            const uint4 q = tile_q[j / A][ey];
-            const int c = j % A;
-            const uint32_t w = c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w;
-            dst[j] = __uint_as_float(w);
+        const int len = lens[threadIdx.x];
+        float vf[4][4];
+        uint8_t vb[4][2];
+        uint4 vq[4][2];
+        bool ok[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int t = t0 + threadIdx.y + 8 * it;
+            ok[it] = e < b.B && t < len;
+            if (ok[it]) {
+                const int64_t r = (int64_t)t * b.B + e;
+                vf[it][0] = b.rec_value[r]; vf[it][1] = b.rec_reward[r]; vf[it][2] = b.rec_adv[r]; vf[it][3] = b.rec_ret[r];
+                vb[it][0] = b.rec_action[r]; vb[it][1] = (uint8_t)b.rec_perm[r];
+                vq[it][0] = reinterpret_cast<const uint4*>(b.rec_logits)[r]; vq[it][1] = b.rec_state[r];
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            if (ok[it]) {
+                const int ty = threadIdx.y + 8 * it;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tl.f[k][ty][threadIdx.x] = vf[it][k];
+                tl.b[0][ty][threadIdx.x] = vb[it][0]; tl.b[1][ty][threadIdx.x] = vb[it][1];
+                tl.q[0][ty][threadIdx.x] = vq[it][0]; tl.q[1][ty][threadIdx.x] = vq[it][1];
+            }
         }
     }
     __syncthreads();
-    // obs: 16-byte state -> N u16 one-hot indices per record
-    for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
-        const int t = t0 + ty;
-        const int64_t e = e0 + threadIdx.x;
-        if (e < b.B && t < lens[threadIdx.x]) tile_q[ty][threadIdx.x] = b.rec_state[(int64_t)t * b.B + e];
-    }
-    __syncthreads();
+
+    // ---- store phase: warp `ey` walks episodes ey, ey+8, ..; lane = step inside the tile
     for (int ey = threadIdx.y; ey < 32; ey += blockDim.y) {
-        const int nt = min(32, lens[ey] - t0);
+        const int nt = min(32, lens[ey] - t0);                 // records of this episode in the tile
         if (e0 + ey >= b.B || nt <= 0) continue;
-        uint16_t* dst = b.out_obs + (offs[ey] + t0) * p.N;
-        uint8_t* dst8 = reinterpret_cast<uint8_t*>(b.out_obs) + (offs[ey] + t0) * p.N;
-        for (int j = threadIdx.x; j < nt * p.N; j += 32) {
-            const uint4 q = tile_q[j / p.N][ey];
+        const long long r0 = offs[ey] + t0;
+        const int x = threadIdx.x;
+        if (x < nt) {
+            b.out_values[r0 + x] = tl.f[0][x][ey]; b.out_rewards[r0 + x] = tl.f[1][x][ey];
+            b.out_advs[r0 + x] = tl.f[2][x][ey]; b.out_rets[r0 + x] = tl.f[3][x][ey];
+            b.out_actions[r0 + x] = tl.b[0][x][ey]; b.out_perms[r0 + x] = (int8_t)tl.b[1][x][ey];
+        }
+        // logits: float4 per record -> [record][A] floats
+        if (A == 4) {
+            if (x < nt) reinterpret_cast<uint4*>(b.out_logits)[r0 + x] = tl.q[0][x][ey];
+        } else {
+            float* dst = b.out_logits + r0 * A;
+            for (int j = x; j < nt * A; j += 32) {
+                const uint4 q = tl.q[0][j / A][ey];
+                const int c = j % A;
+                const uint32_t w = c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w;
+                dst[j] = __uint_as_float(w);
+            }
+        }
+        // obs: 16-byte state -> N one-hot indices per record (u16, or u8 for twr_host_buffers.obs_u8)
+        uint16_t* dst = b.out_obs + r0 * p.N;
+        uint8_t* dst8 = reinterpret_cast<uint8_t*>(b.out_obs) + r0 * p.N;
+        if (p.kind == 0 && p.N == 16) {
+            // 16-cell puzzle: one thread per record, the 16 indices leave as one (u8) or two (u16) 16-byte stores
+            if (x < nt) {
+                const uint4 q = tl.q[1][x][ey];
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                if (b.obs_u8) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)            // cell i = 4k+j holds tile byte j of word k; index = i*16 + tile
+                        o[k] = w[k] + (uint32_t)(k * 64) * 0x01010101u + 0x30201000u;
+                    reinterpret_cast<uint4*>(dst8)[x] = make_uint4(o[0], o[1], o[2], o[3]);
+                } else {
+                    uint32_t o[8];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t i0 = (uint32_t)(4 * k) * 16u;
+                        o[2 * k] = ((w[k] & 0xFFu) + i0) | ((((w[k] >> 8) & 0xFFu) + i0 + 16u) << 16);
+                        o[2 * k + 1] = (((w[k] >> 16) & 0xFFu) + i0 + 32u) | ((((w[k] >> 24) & 0xFFu) + i0 + 48u) << 16);
+                    }
+                    uint4* d4 = reinterpret_cast<uint4*>(dst) + 2 * x;
+                    d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                }
+            }
+            continue;
+        }
+        for (int j = x; j < nt * p.N; j += 32) {
+            const uint4 q = tl.q[1][j / p.N][ey];
             EnvState s;
             s.lo = (uint64_t)q.x | ((uint64_t)q.y << 32);
             s.hi = (uint64_t)q.z | ((uint64_t)q.w << 32);
@@ -434,7 +469,9 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
 
 void launch_compact(cudaStream_t st, const EnvParams& p, const CollectBuffers& b, int A) {
     dim3 grid(grid_for(b.B, 32), (unsigned)((b.Tmax + 31) / 32));
-    k_compact<<<grid, dim3(32, 8), 0, st>>>(p, b, A);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompactTiles)); attr_set = true; }
+    k_compact<<<grid, dim3(32, 8), sizeof(CompactTiles), st>>>(p, b, A);
     TWR_COUNT_LAUNCH();
 }
 

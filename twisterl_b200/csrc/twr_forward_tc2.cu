@@ -51,7 +51,9 @@ constexpr int SM_B1 = SM_HEADW + 8192;
 constexpr int SM_EMBB = SM_B1 + 1024;
 constexpr int SM_PART = SM_EMBB + 4096;                   // [2][128][8] float: head partial sums of the upper column half
 constexpr int SM_PERM = SM_PART + 2 * TM * 8 * 4;         // [4][128] int8: twist index of the tiles in flight
-constexpr int SM_BARS = SM_PERM + 4 * TM;
+constexpr int SM_OPERM = SM_PERM + 4 * TM;                // uint8 copy of the twist tables (obs_perms), up to OPERM_MAX entries
+constexpr int OPERM_MAX = 2048;
+constexpr int SM_BARS = SM_OPERM + OPERM_MAX;
 constexpr int SM_TOTAL = SM_BARS + 512;
 static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
@@ -256,6 +258,10 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     float* embb = reinterpret_cast<float*>(smem + SM_EMBB);
     float* part_s = reinterpret_cast<float*>(smem + SM_PART);
     int8_t* perm_s = reinterpret_cast<int8_t*>(smem + SM_PERM);
+    uint8_t* operm_s = smem + SM_OPERM;
+    // twist tables in shared memory when they fit (obs_size <= 256 makes every entry a byte): the one-hot build looks
+    // up 16 of them per env and step
+    const bool operm_smem = p.n_perms > 0 && p.n_perms * p.obs_size <= OPERM_MAX;
     const int NC = t.NC, NKB1 = t.NKB1, H = t.H;
 
     if (threadIdx.x == 0) {
@@ -275,6 +281,8 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         b1s[i] = p.b1[i];
     }
     for (int i = threadIdx.x; i < t.E; i += NTHREADS) embb[i] = p.emb_b[i];
+    if (operm_smem)
+        for (int i = threadIdx.x; i < p.n_perms * p.obs_size; i += NTHREADS) operm_s[i] = (uint8_t)p.obs_perms[i];
     if (warp == 1) {   // both CTAs, same warp id: allocates the same 512 columns in both SMs
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
@@ -508,7 +516,8 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     uint32_t r = 0;
                     if (pos < n) {
                         r = a.obs_rows ? (uint32_t)a.obs_rows[pos * n_obs + i] : (uint32_t)(i * a.env.N) + env_board(a.env, s, i);
-                        if (perm >= 0) r = (uint32_t)p.obs_perms[(size_t)perm * p.obs_size + r];   // twist-in, policy.rs:81-83
+                        if (perm >= 0)                                                         // twist-in, policy.rs:81-83
+                            r = operm_smem ? (uint32_t)operm_s[perm * p.obs_size + (int)r] : (uint32_t)p.obs_perms[(size_t)perm * p.obs_size + r];
                     }
                     const uint32_t k = r & 63u;
                     *reinterpret_cast<__half*>(smem + SM_A1 + (r >> 6) * TILE_BYTES + row_base + ((((k >> 3) ^ rx) & 7u) << 4) + (k & 7u) * 2u) =

@@ -655,3 +655,31 @@ def test_native_safetensors_reader(eng, tmp_path):
         tw.nn.Policy.from_safetensors(bad, engine=eng)
     with pytest.raises(RuntimeError, match="cannot open"):
         tw.nn.Policy.from_safetensors(tmp_path / "missing.safetensors", engine=eng)
+
+
+def test_collect_host_large_uses_round_sized_sub_batches(eng):
+    """Above four kernel rounds twr_ppo_collect_host cuts the collect into two-round sub-batches (37 888 envs on a
+    148-SM device) plus a halved tail; the host buffers must equal the plain collect + to_host path."""
+    import ctypes as C
+    import twisterl_b200 as tw
+    from parity import make_policies
+    from twisterl_b200 import _lib, collector as twc
+    _, sd = trained15()
+    pol, _ = make_policies(sd, 256)
+    env = tw.env.Puzzle(4, 4, 3, 2, 256)
+    E = 120000
+    col = tw.collector.PPOCollector(E, 0.995, 0.995, 32, engine=eng)
+    eng.set_collect_id(23)
+    ref = col.collect(env, pol)
+    L = _lib.load()
+    spec = tw.env.spec_from_env(env)
+    cap = int(L.twr_max_records(C.byref(spec), E))
+    hb, arr, _ = twc._host_buffers(cap, 16, 4, E, pinned=True, obs_u8=True)
+    out = _lib.Collected()
+    eng.set_collect_id(23)
+    _lib.check(L.twr_ppo_collect_host(eng._h, C.byref(spec), pol.device_handle(eng), None, E, 0.995, 0.995, C.byref(hb), C.byref(out)))
+    R = int(out.n_records)
+    assert R == len(ref.values_array) and int(out.successes) == ref.stats["successes"]
+    assert np.array_equal(arr["ep_len"], ref.ep_len)
+    assert np.array_equal(arr["obs"][:R], ref.obs_array.astype(np.uint8)) and np.array_equal(arr["actions"][:R], ref.actions_array)
+    assert np.array_equal(arr["logits"][:R], ref.logits_array) and np.array_equal(arr["rets"][:R], ref.additional_array("rets"))

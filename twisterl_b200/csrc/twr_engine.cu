@@ -1066,8 +1066,13 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
         const int64_t round = (int64_t)(sms / 2) * 256;
         if (split == 2 && e->precision == TWR_PREC_F16X2 && round > 0 && !getenv("TWISTERL_B200_E2E_SPLIT")) {
-            const int64_t first = ((num_episodes / 2 + round - 1) / round) * round;
-            if (first < num_episodes) { parts.push_back(first); parts.push_back(num_episodes - first); }
+            // large collects: sub-batches of two rounds (the kernel's most efficient shape) so that only the copy of a
+            // small last sub-batch stays exposed; the last <= 4 rounds are halved on a round boundary
+            int64_t rem = num_episodes;
+            while (rem >= 4 * round) { parts.push_back(2 * round); rem -= 2 * round; }
+            const int64_t first = ((rem / 2 + round - 1) / round) * round;
+            if (first < rem) { parts.push_back(first); parts.push_back(rem - first); }
+            else parts.push_back(rem);
         }
         if (parts.empty()) {
             const int64_t Bsub = (num_episodes + split - 1) / split;

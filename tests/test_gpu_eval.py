@@ -162,3 +162,31 @@ def test_solve_with_mcts(eng):
     for a in acts:
         oenv.step(a)
     assert oenv.success()
+
+
+def test_engine_and_policy_lifecycle_does_not_leak():
+    """Engines, policies, env batches and collects created and destroyed repeatedly give their device memory back
+    (every cudaMalloc of the library has an owner that frees it)."""
+    torch = pytest.importorskip("torch")
+    import twisterl_b200 as tw
+    from parity import make_policies
+    _, sd = trained15()
+
+    def cycle():
+        eng = tw.Engine(device=0, precision=PRECISION, seed=5)
+        pol, _ = make_policies(sd, 256)
+        env = tw.env.Puzzle(4, 4, 4, 2, 256)
+        tw.collector.PPOCollector(3000, 0.995, 0.995, 1, engine=eng).collect(env, pol)
+        pol8, _ = make_policies(synth_state_dict(8, 81, 512, 256, 4), 81)
+        tw.collector.AZCollector(64, 8, 1.41, 1, 1, engine=eng).collect(tw.env.Puzzle(3, 3, 3, 2, 256), pol8)
+        pol.release(); pol8.release()
+        eng.close()
+
+    cycle()                                   # warm: CUDA context, module load
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(6):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 64 << 20, f"device memory shrank by {(free0 - free1) >> 20} MiB over 6 engine lifecycles"

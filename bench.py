@@ -184,14 +184,27 @@ def run_ours(args, rank, local_rank, world):
     blob.copy_(_torch_view(torch, dptr.value, nblob, dev))
     stats = torch.zeros(4, dtype=torch.float64, device=dev)
 
+    prof = os.environ.get("TWISTERL_BENCH_PROFILE") and rank == 0
+    phase = [0.0, 0.0, 0.0, 0.0]
+
     def one_step():
+        t0 = time.perf_counter()
         if world > 1:
             dist.broadcast(blob, src=0)                              # per-iteration weight broadcast (NCCL)
+        if prof:
+            torch.cuda.synchronize(); t1 = time.perf_counter(); phase[0] += t1 - t0
         _lib.check(L.twr_policy_update_from_device(hpol, C.c_void_p(blob.data_ptr())))
+        if prof:
+            torch.cuda.synchronize(); t2 = time.perf_counter(); phase[1] += t2 - t1
         c = col.collect_device(env, pol)
+        if prof:
+            t3 = time.perf_counter(); phase[2] += t3 - t2
         if world > 1:
             stats.copy_(torch.tensor([c.num_episodes, c.successes, c.reward_sum, c.n_records], dtype=torch.float64))
             dist.all_reduce(stats)                                   # stats reduction (NCCL)
+        if prof:
+            torch.cuda.synchronize(); phase[3] += time.perf_counter() - t3
+            print("[profile] broadcast %.3f update %.3f collect %.3f allreduce %.3f ms (cumulative)" % tuple(1e3 * x for x in phase), file=sys.stderr)
         return int(c.n_records)
 
     def barrier():

@@ -202,6 +202,9 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             stats.copy_(torch.tensor([c.num_episodes, c.successes, c.reward_sum, c.n_records], dtype=torch.float64))
             dist.all_reduce(stats)                                   # stats reduction (NCCL)
+            stats.cpu()                                              # the reduced statistics are read on the host every
+                                                                     # iteration (what a trainer logs); it also keeps the host
+                                                                     # from queueing the next step's NCCL calls behind a peer
         if prof:
             torch.cuda.synchronize(); phase[3] += time.perf_counter() - t3
             print("[profile] broadcast %.3f update %.3f collect %.3f allreduce %.3f ms (cumulative)" % tuple(1e3 * x for x in phase), file=sys.stderr)

@@ -189,4 +189,4 @@ def test_engine_and_policy_lifecycle_does_not_leak():
         cycle()
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info()
-    assert free0 - free1 < 64 << 20, f"device memory shrank by {(free0 - free1) >> 20} MiB over 6 engine lifecycles"
+    assert free0 - free1 < 128 << 20, f"device memory shrank by {(free0 - free1) >> 20} MiB over 6 engine lifecycles"

@@ -469,8 +469,7 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
 
 void launch_compact(cudaStream_t st, const EnvParams& p, const CollectBuffers& b, int A) {
     dim3 grid(grid_for(b.B, 32), (unsigned)((b.Tmax + 31) / 32));
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompactTiles)); attr_set = true; }
+    cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompactTiles));   // per device: set on every launch
     k_compact<<<grid, dim3(32, 8), sizeof(CompactTiles), st>>>(p, b, A);
     TWR_COUNT_LAUNCH();
 }

@@ -27,7 +27,13 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 FLOP_PER_STEP = {"puzzle15": 272_896, "puzzle8": 269_312, "gridworld": 145_152}
-EXECUTED_TENSOR_FLOP_PER_STEP = {"puzzle15": 2 * (2 * 256 * 512) + 3 * (2 * 512 * 256)}   # f16x2: 2 + 3 MMA passes
+# what the tensor pipe executes per env-step: the embedding as a dense one-hot GEMM over the hi and the lo table, and the
+# hidden layer as 3 (f16x2) or 2 (f16x2w16) split products
+EXECUTED_TENSOR_FLOP_PER_STEP = {"f16x2": 2 * (2 * 256 * 512) + 3 * (2 * 512 * 256), "f16x2w16": 2 * (2 * 256 * 512) + 2 * (2 * 512 * 256)}
+DTYPE = {"fp32": "f32",
+         "f16x2": "f16x2 (tcgen05; every operand split into fp16 hi+lo, f32 accumulate; 1e-5-grade)",
+         "f16x2w16": "f16x2w16 (tcgen05; table and activations split into fp16 hi+lo, common-layer weight one fp16 term, f32 accumulate; "
+                     "7e-4 worst case on the shipped trained weights, bar 1e-3)"}
 METRIC = "rollout env-steps/sec incl. policy fwd (puzzle15 PPO)"
 UNIT = "env-steps/s"
 
@@ -281,7 +287,7 @@ def run_ours(args, rank, local_rank, world):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "f16x2 (fp16 hi+lo split operands, f32 accumulate)",
+            "dtype": DTYPE[args.precision],
             "data": "synthetic",
             "config": {"workload": f"examples/ppo_puzzle15_v1.json PPO rollout, {args.episodes} parallel envs per GPU, "
                                    f"difficulty {args.difficulty}, depth budget {2 * args.difficulty}, synthetic N(0,0.05^2) weights",
@@ -298,16 +304,16 @@ def run_ours(args, rank, local_rank, world):
                          # dram read+write bytes of one 32-step k_forward_tc2 launch over 65536 envs (profiles/r1f_tc2_summary.md;
                          # the records it writes -- 88 MB algorithmic, the rest still sits in L2 when the launch ends);
                          # steady-state launches cover 128 steps and move 4x as much
-                         "traffic": 44_504_576 if (args.precision == "f16x2" and args.episodes == 65536) else None,
+                         "traffic": 44_504_576 if (args.precision != "fp32" and args.episodes == 65536) else None,
                          "traffic_launch_steps": 32,
                          "peak_source": pk["src"] + " bf16_tflops_sustained",
                          "forward_ms_per_launch": fwd_ms / max(fwd_launches, 1), "forward_share_of_step": fwd_ms / ms,
                          "algorithmic_flop_per_env_step": FLOP_PER_STEP["puzzle15"]},
         }
-        if args.precision == "f16x2" and achieved:
+        if args.precision != "fp32" and achieved:
             # what the tensor pipe executes for the fp32-grade result: the embedding as a dense one-hot GEMM (x2: table
             # hi/lo) and the hidden layer as 3 split products -- the tensor-pipe utilisation ncu reports follows this figure
-            ex = EXECUTED_TENSOR_FLOP_PER_STEP["puzzle15"]
+            ex = EXECUTED_TENSOR_FLOP_PER_STEP[args.precision]
             line["roofline"]["executed_tensor_flop_per_env_step"] = ex
             line["roofline"]["executed"] = achieved * ex / FLOP_PER_STEP["puzzle15"]
             line["roofline"]["executed_frac"] = line["roofline"]["executed"] / pk["bf16"]
@@ -338,7 +344,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TWISTERL_B200_PRECISION", "f16x2"), choices=["fp32", "f16x2"])
+    ap.add_argument("--precision", default=os.environ.get("TWISTERL_B200_PRECISION", "f16x2w16"), choices=["fp32", "f16x2", "f16x2w16"])
     ap.add_argument("--episodes", type=int, default=65536)
     ap.add_argument("--difficulty", type=int, default=128)
     ap.add_argument("--ref-episodes", type=int, default=2048)

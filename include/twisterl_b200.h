@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TWR_ABI_VERSION 2
+#define TWR_ABI_VERSION 3
 
 typedef enum {
     TWR_OK = 0,
@@ -44,9 +44,14 @@ typedef enum { TWR_ENV_PUZZLE = 0, TWR_ENV_GRIDWORLD = 1 } twr_env_kind;
 /* arithmetic of the policy forward (kernel K2) */
 typedef enum {
     TWR_PREC_FP32 = 0,  /* SIMT fp32 FMA; parity bar 1e-5 */
-    TWR_PREC_F16X2 = 1  /* tcgen05, operands split into fp16 hi+lo, fp32 TMEM accumulate; bar 1e-3 (1e-5 measured).
-                         * Policies whose shape does not fit the tensor-core kernel (obs_size > 256, e.g. GridWorld 5x5)
-                         * and multiset observations run the fp32 SIMT kernel on the same engine. */
+    TWR_PREC_F16X2 = 1, /* tcgen05, every operand split into fp16 hi+lo (hi*hi + hi*lo + lo*hi), fp32 TMEM accumulate:
+                         * fp32-grade results (1e-5 measured on the shipped trained weights; bar 1e-3).
+                         * Policies whose shape does not fit the tensor-core kernel and multiset observations run the
+                         * fp32 SIMT kernel on the same engine. */
+    TWR_PREC_F16X2_W16 = 2 /* same kernel, the common Linear's weight held as ONE fp16 term (h1_hi*W + h1_lo*W; table and
+                         * activations stay split): 2/3 of the GEMM2 work, 7e-4 worst case on the shipped trained
+                         * weights -- the cheapest operand combination inside the 1e-3 bar (tests/test_gpu_precision.py
+                         * holds the whole ladder; plain fp16 operands measure 4e-3 and miss it). */
 } twr_precision;
 
 typedef struct twr_engine twr_engine;
@@ -147,6 +152,9 @@ void twr_envs_destroy(twr_envs* v);
 int  twr_envs_set_difficulty(twr_envs* v, int32_t difficulty);
 /* states: [n][width*height] boards (Env::set_state) */
 int  twr_envs_set_state(twr_envs* v, const int64_t* states);
+/* Puzzle::set_position (rust/src/envs/puzzle.rs:71-73, python_interface/env.rs:150-153): pokes ONE cell of env `env`;
+ * blank location and depth are left alone, exactly like the reference. */
+int  twr_envs_set_cell(twr_envs* v, int64_t env, int32_t cell, int32_t value);
 /* Env::reset for all n, env i drawing from Philox stream (env_id_base + i, *, reset, collect_id) */
 int  twr_envs_reset(twr_envs* v, uint32_t env_id_base, uint32_t collect_id);
 /* Env::step with forced actions[n] */
@@ -174,6 +182,10 @@ int  twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* o
  * (16 int64 per CTA, max_ctas >= number of SMs; layout documented in twr_forward_tc.cu). */
 int  twr_debug_forward_profile(twr_engine* e, const twr_policy* p, twr_envs* v, int64_t* counters, int32_t max_ctas,
                                int32_t experiment_flags /* 0 = none; results are invalid when non-zero */);
+/* Debug / precision ladder: which split-operand terms the tensor-core forward of this engine accumulates on top of the
+ * hi*hi products: bit 0 one-hot * table_lo, bit 1 h1_lo * W_hi, bit 2 h1_hi * W_lo (7 = TWR_PREC_F16X2, 3 = .._W16,
+ * 0 = plain fp16 operands).  -1 restores the engine's precision. */
+int  twr_debug_set_tc_terms(twr_engine* e, int32_t terms);
 
 /* sample_from_logits (rust/src/nn/policy.rs:169-172) for n logit rows, row i using the uniforms
  * of Philox stream (env_id_base + i, step, sample, collect_id).  uniforms_out may be NULL. */

@@ -63,6 +63,20 @@ def transpose_twists(w):
     return [ident, tw], [[0, 1, 2, 3], [1, 0, 3, 2]]
 
 
+def gridworld_transpose_twists(w):
+    """{identity, main-diagonal transpose} twist set of a square w x w GridWorld (examples/grid_world/src/lib.rs): the cell
+    values (empty / agent / goal / trap) keep their meaning, cells move to their transposed position and up<->left,
+    down<->right trade places (actions 0 up, 1 down, 2 left, 3 right, lib.rs:127-136)."""
+    N = w * w
+    T = [(i % w) * w + (i // w) for i in range(N)]
+    ident = list(range(N * N))
+    tw = [0] * (N * N)
+    for i in range(N):
+        for v in range(N):
+            tw[i * N + v] = T[i] * N + v
+    return [ident, tw], [[0, 1, 2, 3], [2, 3, 0, 1]]
+
+
 def trained15():
     z = np.load(GOLDEN / "policy15_trained.npz")
     sd = {k[2:]: z[k] for k in z.files if k.startswith("w.")}

@@ -6,11 +6,13 @@ import os
 import numpy as np
 import pytest
 
+from suite_loader import suite_precision
+
 from helpers import synth_state_dict, trained15, transpose_twists
 from oracle import orc
 
 pytestmark = pytest.mark.gpu
-PRECISION = os.environ.get("TWISTERL_B200_PRECISION", "fp32")
+PRECISION = suite_precision(globals())
 
 
 @pytest.fixture(scope="module")

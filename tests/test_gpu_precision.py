@@ -1,0 +1,87 @@
+"""Precision ladder of the tensor-core forward (k_forward_tc2) on the reference's shipped trained weights.
+
+north_star: logits and values within 1e-3 relative (bf16-class arithmetic) / 1e-5 (fp32).  Every fp32 operand can be fed
+to the tensor cores as one fp16 term or as a hi+lo pair; this test MEASURES each combination of
+
+    GEMM1 (embedding):   one-hot x table_hi            [+ one-hot x table_lo]        (bit 0)
+    GEMM2 (common):      h1_hi x W_hi   [+ h1_lo x W_hi] (bit 1)   [+ h1_hi x W_lo]  (bit 2)
+
+against the logits/values the reference's own torch BasicPolicy produced (tests/golden/policy15_trained.npz) and holds
+each to the bar it is shipped under: all three terms = TWR_PREC_F16X2 (1e-4, fp32-grade); bits 0|1 = TWR_PREC_F16X2_W16
+(1e-3, the cheapest combination inside the north-star bar); every cheaper combination -- plain fp16 operands included --
+MISSES 1e-3 on these weights, which is why none of them is offered.  scripts/precision_ladder_emul.py is the CPU
+emulation of the same table (it also shows bf16 operands an order of magnitude further out)."""
+import json
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import obs_from_states, scramble_states, trained15
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+EXECUTED = lambda terms: 2 * 256 * 512 * (1 + (terms & 1)) + 2 * 512 * 256 * (1 + ((terms >> 1) & 1) + ((terms >> 2) & 1))
+
+
+def _err(a, ref):
+    return float((np.abs(a - ref) / np.maximum(1.0, np.abs(ref))).max())
+
+
+def _f64_reference(sd, obs):
+    E, W = sd["embeddings.weight"].T.astype(np.float64), sd["common.0.weight"].T.astype(np.float64)
+    h1 = np.maximum(E[obs].sum(1) + sd["embeddings.bias"], 0)
+    h2 = np.maximum(h1 @ W + sd["common.0.bias"], 0)
+    return (h2 @ sd["action.0.weight"].T.astype(np.float64) + sd["action.0.bias"],
+            (h2 @ sd["value.0.weight"].T.astype(np.float64) + sd["value.0.bias"])[:, 0])
+
+
+def test_precision_ladder_on_trained_weights():
+    import twisterl_b200 as tw
+    from parity import make_policies
+    from twisterl_b200 import _lib
+    from twisterl_b200.env import EnvBatch
+    from twisterl_b200.nn import forward_batch
+    z, sd = trained15()
+    eng = tw.Engine(device=0, precision="f16x2", seed=1)
+    pol, _ = make_policies(sd, 256)
+    golden = z["states"]
+    wide = scramble_states(np.random.default_rng(1), 8192, 4, 4, 200)          # broader sample, float64 reference
+    wl, wv = _f64_reference(sd, obs_from_states(wide))
+    spec = _lib.EnvSpec(0, 4, 4, 1, 2, 256)
+    bg = EnvBatch(spec, len(golden), eng); bg.set_state(golden)
+    bw = EnvBatch(spec, len(wide), eng); bw.set_state(wide)
+    table = {}
+    for terms in range(8):
+        eng.set_tc_terms(terms)
+        l, v = forward_batch(eng, pol, bg)
+        l2, v2 = forward_batch(eng, pol, bw)
+        table[terms] = dict(g1_passes=1 + (terms & 1), g2_terms=1 + ((terms >> 1) & 1) + ((terms >> 2) & 1),
+                            executed_flop_per_env_step=EXECUTED(terms),
+                            logits_err_golden=_err(l, z["logits"]), values_err_golden=_err(v, z["values"]),
+                            logits_err_8192=_err(l2, wl), values_err_8192=_err(v2, wv))
+    eng.set_tc_terms(-1)
+    print("\nterms  executed    logits(golden) values(golden)  logits(8192)  values(8192)")
+    for t, r in table.items():
+        print(f"  {t:03b}  {r['executed_flop_per_env_step']:8d}    {r['logits_err_golden']:.2e}       {r['values_err_golden']:.2e}"
+              f"      {r['logits_err_8192']:.2e}     {r['values_err_8192']:.2e}")
+    out = Path(os.environ.get("GRAFT_REPO_ROOT", Path(__file__).resolve().parent.parent)) / "gpurun_out"
+    if out.is_dir():
+        (out / "precision_ladder.json").write_text(json.dumps(table, indent=1))
+    worst = lambda r: max(r["logits_err_golden"], r["values_err_golden"], r["logits_err_8192"], r["values_err_8192"])
+    assert worst(table[7]) <= 1e-4, table[7]                       # TWR_PREC_F16X2: fp32-grade
+    assert worst(table[3]) <= 1e-3, table[3]                       # TWR_PREC_F16X2_W16: inside the north-star bar
+    for terms in (0, 1, 2, 4, 5, 6):                               # everything cheaper than / as cheap as W16 misses it
+        assert max(table[terms]["logits_err_golden"], table[terms]["logits_err_8192"]) > 1e-3, (terms, table[terms])
+    # the W16 engine is exactly the 0b011 rung
+    eng.set_tc_terms(3)
+    l3, v3 = forward_batch(eng, pol, bg)
+    eng.set_tc_terms(-1)
+    e16 = tw.Engine(device=0, precision="f16x2w16", seed=1)
+    pol16, _ = make_policies(sd, 256)
+    b16 = EnvBatch(spec, len(golden), e16); b16.set_state(golden)
+    l16, v16 = forward_batch(e16, pol16, b16)
+    assert np.array_equal(l16, l3) and np.array_equal(v16, v3)
+    pol.release(); pol16.release(); eng.close(); e16.close()

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/twisterl_b200.h but not exported"
     assert declared == set(_lib.SYMBOLS)
-    assert L.twr_abi_version() == 2
+    assert L.twr_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_no_cpu_fallback_without_device():
@@ -255,4 +255,4 @@ def test_header_is_plain_c_and_links(tmp_path):
                         f"-L{libdir}", "-ltwisterl_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
-    assert r.returncode == 0 and r.stdout.split() == ["2", "30"], (r.stdout, r.stderr)   # 10 episodes x (2*1 + 1) records
+    assert r.returncode == 0 and r.stdout.split() == ["3", "30"], (r.stdout, r.stderr)   # 10 episodes x (2*1 + 1) records

@@ -17,8 +17,10 @@ LIB_PATH = PKG / "lib" / "libtwisterl_b200.so"
 
 OK = 0
 ENV_PUZZLE, ENV_GRIDWORLD = 0, 1
-PREC_FP32, PREC_F16X2 = 0, 1
-PRECISIONS = {"fp32": PREC_FP32, "f16x2": PREC_F16X2}
+ABI_VERSION = 3                      # TWR_ABI_VERSION of the header these struct layouts / prototypes were written against
+PREC_FP32, PREC_F16X2, PREC_F16X2_W16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "f16x2": PREC_F16X2, "f16x2w16": PREC_F16X2_W16}
+TC_PRECISIONS = ("f16x2", "f16x2w16")   # the tcgen05 forward: all operands split / common-layer weight as one fp16 term
 MAX_ACTIONS = 4
 
 f32p, i32p, i64p, u8p, i8p, u16p = (C.POINTER(t) for t in (C.c_float, C.c_int32, C.c_int64, C.c_uint8, C.c_int8, C.c_uint16))
@@ -67,9 +69,9 @@ SYMBOLS = [
     "twr_abi_version", "twr_last_error", "twr_device_count", "twr_engine_create", "twr_engine_destroy",
     "twr_engine_synchronize", "twr_engine_launch_count", "twr_policy_create", "twr_policy_update",
     "twr_policy_create_from_safetensors", "twr_policy_blob_floats", "twr_policy_update_from_device", "twr_policy_blob_device_ptr", "twr_policy_destroy",
-    "twr_envs_create", "twr_envs_destroy", "twr_envs_set_difficulty", "twr_envs_set_state", "twr_envs_reset",
+    "twr_envs_create", "twr_envs_destroy", "twr_envs_set_difficulty", "twr_envs_set_state", "twr_envs_set_cell", "twr_envs_reset",
     "twr_envs_step", "twr_envs_get_state", "twr_envs_observe", "twr_envs_masks", "twr_envs_reward",
-    "twr_envs_is_final", "twr_envs_success", "twr_envs_depth", "twr_policy_forward", "twr_policy_forward_obs", "twr_debug_forward_profile", "twr_sample", "twr_gae",
+    "twr_envs_is_final", "twr_envs_success", "twr_envs_depth", "twr_policy_forward", "twr_policy_forward_obs", "twr_debug_forward_profile", "twr_debug_set_tc_terms", "twr_sample", "twr_gae",
     "twr_ppo_collect", "twr_engine_set_collect_id", "twr_collected_to_host", "twr_max_records",
     "twr_ppo_collect_host", "twr_evaluate", "twr_solve", "twr_az_collect", "twr_mcts_probs", "twr_host_alloc", "twr_host_free", "twr_engine_set_timing", "twr_engine_last_timing",
 ]
@@ -91,10 +93,16 @@ def load():
         except Exception as exc:  # nvcc missing etc.
             if not LIB_PATH.exists():
                 raise ImportError(f"twisterl_b200: CUDA library missing and cannot be built: {exc}") from exc
+            import warnings
+            warnings.warn(f"twisterl_b200: sources are newer than {LIB_PATH.name} and the rebuild failed ({exc}); "
+                          "loading the existing library (its ABI version is checked)", RuntimeWarning)
         try:
             L = C.CDLL(str(LIB_PATH))
         except OSError as exc:
             raise ImportError(f"twisterl_b200: cannot load {LIB_PATH}: {exc} (there is no CPU fallback)") from exc
+        if int(L.twr_abi_version()) != ABI_VERSION:
+            raise ImportError(f"twisterl_b200: {LIB_PATH} has ABI version {int(L.twr_abi_version())}, this package binds "
+                              f"version {ABI_VERSION}: rebuild with `python -m twisterl_b200.build --force`")
         vp = C.c_void_p
         L.twr_last_error.restype = C.c_char_p
         L.twr_engine_create.argtypes = [C.POINTER(EngineCfg), C.POINTER(vp)]
@@ -115,12 +123,14 @@ def load():
         L.twr_envs_destroy.argtypes = [vp]; L.twr_envs_destroy.restype = None
         L.twr_envs_set_difficulty.argtypes = [vp, C.c_int32]
         L.twr_envs_set_state.argtypes = [vp, vp]
+        L.twr_envs_set_cell.argtypes = [vp, C.c_int64, C.c_int32, C.c_int32]
         L.twr_envs_reset.argtypes = [vp, C.c_uint32, C.c_uint32]
         for name in ("step", "get_state", "observe", "masks", "reward", "is_final", "success", "depth"):
             getattr(L, "twr_envs_" + name).argtypes = [vp, vp]
         L.twr_policy_forward.argtypes = [vp, vp, vp, vp, C.c_int32, vp, vp]
         L.twr_policy_forward_obs.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp, vp, vp]
         L.twr_debug_forward_profile.argtypes = [vp, vp, vp, vp, C.c_int32, C.c_int32]
+        L.twr_debug_set_tc_terms.argtypes = [vp, C.c_int32]
         L.twr_sample.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
         L.twr_gae.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, vp, vp]
         L.twr_ppo_collect.argtypes = [vp, C.POINTER(EnvSpec), vp, C.c_int64, C.c_float, C.c_float, C.POINTER(Collected)]
@@ -183,6 +193,10 @@ class Engine:
     def launch_count(self) -> int: return int(load().twr_engine_launch_count(self._h))
     def set_collect_id(self, cid: int): check(load().twr_engine_set_collect_id(self._h, int(cid)))
     def set_timing(self, on: bool): check(load().twr_engine_set_timing(self._h, int(bool(on))))
+
+    def set_tc_terms(self, terms: int):
+        """Debug / precision ladder: split-operand terms of the tensor-core forward (see twr_debug_set_tc_terms)."""
+        check(load().twr_debug_set_tc_terms(self._h, int(terms)))
 
     def last_timing(self):
         f, t, n = C.c_float(), C.c_float(), C.c_int64()

@@ -83,6 +83,8 @@ int horizon_of(const EnvParams& p) {   // max env steps of one episode
 
 struct twr_engine {
     int device = 0, precision = 0, rank = 0, world = 1;
+    int tc_terms = 0;            // ForwardArgs::tc_terms of every tensor-core forward of this engine (0 = all split terms)
+    bool launch_error = false;   // a forward launch could not be made since the last check (see FWD_CHECK)
     uint64_t seed = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -187,7 +189,7 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
         return fail(TWR_ERR_CUDA, "no CUDA device: the twisterl_b200 engine has no CPU fallback");
     }
     if (cfg->device < 0 || cfg->device >= n) return fail(TWR_ERR_INVALID, "device ordinal out of range");
-    if (cfg->precision != TWR_PREC_FP32 && cfg->precision != TWR_PREC_F16X2)
+    if (cfg->precision != TWR_PREC_FP32 && cfg->precision != TWR_PREC_F16X2 && cfg->precision != TWR_PREC_F16X2_W16)
         return fail(TWR_ERR_INVALID, "unknown precision");
     if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(TWR_ERR_INVALID, "bad rank/world");
     CU_TRY(cudaSetDevice(cfg->device));
@@ -198,6 +200,7 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
     twr_engine* e = new twr_engine();
     e->device = cfg->device; e->precision = cfg->precision; e->seed = cfg->seed;
     e->rank = cfg->rank; e->world = cfg->world;
+    e->tc_terms = cfg->precision == TWR_PREC_F16X2_W16 ? (8 | 1 | 2) : 0;
     if (cfg->stream) {
         e->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
     } else {
@@ -205,14 +208,20 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
         if (se != cudaSuccess) { delete e; return fail(TWR_ERR_CUDA, cudaGetErrorString(se)); }
         e->own_stream = true;
     }
-    cudaEventCreate(&e->ev_t0); cudaEventCreate(&e->ev_t1);
-    cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
-    if (cudaMalloc(reinterpret_cast<void**>(&e->bal_flags), 1024 * sizeof(int32_t)) != cudaSuccess) e->bal_flags = nullptr;
-    for (int i = 0; i < 2; ++i) {
-        cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming);
+    cudaError_t ce2 = cudaEventCreate(&e->ev_t0);
+    if (ce2 == cudaSuccess) ce2 = cudaEventCreate(&e->ev_t1);
+    if (ce2 == cudaSuccess) ce2 = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
+    if (ce2 == cudaSuccess) ce2 = cudaMalloc(reinterpret_cast<void**>(&e->bal_flags), 1024 * sizeof(int32_t));
+    for (int i = 0; i < 2 && ce2 == cudaSuccess; ++i) {
+        ce2 = cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
+        if (ce2 == cudaSuccess) ce2 = cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming);
     }
-    cudaHostAlloc(reinterpret_cast<void**>(&e->h_stats), 8 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (ce2 == cudaSuccess) ce2 = cudaHostAlloc(reinterpret_cast<void**>(&e->h_stats), 8 * sizeof(unsigned long long), cudaHostAllocDefault);
+    if (ce2 != cudaSuccess) {
+        const std::string msg = std::string("twr_engine_create: ") + cudaGetErrorString(ce2);
+        twr_engine_destroy(e);
+        return fail(TWR_ERR_CUDA, msg);
+    }
     e->launches0 = g_twr_launches.load();
     *out = e;
     return TWR_OK;
@@ -433,11 +442,26 @@ int twr_policy_create(twr_engine* e, const twr_policy_desc* d_in, twr_policy** o
         const char* why = "";
         // TWR_PREC_F16X2 = tensor cores where the shape fits the tcgen05 kernel (obs_size <= 256, E % 128 == 0, H in
         // {128, 256}); other shapes (GridWorld's 625-row table) run the fp32 SIMT kernel -- still on the device.
-        use_tc = e->precision == TWR_PREC_F16X2 && forward_tc_supported(probe, dummy, &why);
-        if (!use_tc && !forward_fp32_supported(probe, dummy, &why)) {
-            delete p;
-            return fail(TWR_ERR_UNSUPPORTED, std::string("policy shape not supported on the device: ") + why);
+        // GridWorld-shaped tables (obs_size = N*N > 256, only rows i*N + {0,1,2,3} reachable): the pair kernel runs on
+        // the compact 4N-row table when the twists (if any) keep the reachable rows among themselves
+        if (e->precision != TWR_PREC_FP32 && d->obs_size > 256) {
+            int N = 1;
+            while ((N + 1) * (N + 1) <= d->obs_size) ++N;
+            bool ok = N * N == d->obs_size && N <= TWR_MAX_CELLS && 4 * N <= 256;
+            for (int64_t i = 0; ok && i < (int64_t)d->n_perms * d->obs_size; ++i)
+                if ((i % d->obs_size) % N < 4 && d->obs_perms[i] % N >= 4) ok = false;
+            if (ok) probe.tc_compact_n = p->dev.tc_compact_n = N;
         }
+        use_tc = e->precision != TWR_PREC_FP32 && forward_tc_supported(probe, dummy, &why);
+        // a compact-table policy still meets non-GridWorld callers (twr_policy_forward_obs): those run the fp32 kernel
+        if ((!use_tc || p->dev.tc_compact_n > 0) && !forward_fp32_supported(probe, dummy, &why)) {
+            if (!use_tc) {
+                delete p;
+                return fail(TWR_ERR_UNSUPPORTED, std::string("policy shape not supported on the device: ") + why);
+            }
+            use_tc = false;
+        }
+        if (!use_tc) p->dev.tc_compact_n = 0;
     } else if (max_width > 1024) {
         delete p;
         return fail(TWR_ERR_UNSUPPORTED, "general layer stacks are implemented for layer widths up to 1024");
@@ -463,6 +487,10 @@ int twr_policy_create(twr_engine* e, const twr_policy_desc* d_in, twr_policy** o
         p->dev.tc_pack = p->tc_pack;
     }
     if ((rc = upload_policy(p, d))) { twr_policy_destroy(p); return rc; }
+    if (use_tc && !forward_tc_prepare(p->dev)) {
+        twr_policy_destroy(p);
+        return fail(TWR_ERR_CUDA, "tensor-core forward: cuTensorMapEncodeTiled / kernel attributes unavailable on this device or driver");
+    }
     *out = p;
     return TWR_OK;
 }
@@ -504,7 +532,7 @@ void twr_policy_destroy(twr_policy* p) {
     cudaSetDevice(p->eng->device);
     cudaStreamSynchronize(p->eng->stream);
     dev_free(p->d_blob); dev_free(p->d_obs_perms); dev_free(p->d_act_perms);
-    if (p->tc_pack) cudaFree(p->tc_pack);
+    if (p->tc_pack) { forward_tc_forget(p->dev); cudaFree(p->tc_pack); }
     delete p;
 }
 
@@ -541,6 +569,7 @@ int twr_envs_set_difficulty(twr_envs* v, int32_t difficulty) {
         const int cap = v->p.W + v->p.H;
         v->p.difficulty = difficulty < cap ? difficulty : cap;
     } else {
+        if ((int64_t)v->p.depth_slope * difficulty >= (1 << 24)) return fail(TWR_ERR_INVALID, "depth budget too large");
         v->p.difficulty = difficulty;
     }
     return TWR_OK;
@@ -550,8 +579,13 @@ int twr_envs_set_state(twr_envs* v, const int64_t* states) {
     if (!v || !states) return fail(TWR_ERR_INVALID, "envs/states is NULL");
     if (v->n == 0) return TWR_OK;
     const int N = v->p.N;
+    // the reference indexes its tables with these values and panics on anything else (puzzle.rs:99-117, lib.rs:100-112);
+    // here an out-of-range cell would index past the embedding table on the device, so it is rejected up front
+    const int64_t vmax = v->p.kind == TWR_ENV_PUZZLE ? N - 1 : 3;
     for (int64_t i = 0; i < v->n * N; ++i)
-        if (states[i] < 0 || states[i] > 255) return fail(TWR_ERR_INVALID, "set_state: cell values must be in 0..255");
+        if (states[i] < 0 || states[i] > vmax)
+            return fail(TWR_ERR_INVALID, v->p.kind == TWR_ENV_PUZZLE ? "set_state: Puzzle cell values must be tiles 0..cells-1"
+                                                                     : "set_state: GridWorld cell values must be 0 (empty), 1 (agent), 2 (goal) or 3 (trap)");
     if (v->p.kind == TWR_ENV_PUZZLE) {
         for (int64_t e = 0; e < v->n; ++e) {
             bool zero = false;
@@ -566,6 +600,20 @@ int twr_envs_set_state(twr_envs* v, const int64_t* states) {
     if (rc) return rc;
     CU_TRY(cudaMemcpyAsync(st.d, states, sizeof(int64_t) * (size_t)v->n * N, cudaMemcpyHostToDevice, e->stream));
     launch_envs_set_state(e->stream, v->p, v->cells, v->meta, v->n, st.d);
+    CU_TRY(cudaStreamSynchronize(e->stream));
+    return TWR_OK;
+}
+
+int twr_envs_set_cell(twr_envs* v, int64_t env, int32_t cell, int32_t value) {
+    if (!v) return fail(TWR_ERR_INVALID, "envs is NULL");
+    if (v->p.kind != TWR_ENV_PUZZLE) return fail(TWR_ERR_UNSUPPORTED, "set_cell is Puzzle::set_position; GridWorld has no such method");
+    if (env < 0 || env >= v->n || cell < 0 || cell >= v->p.N) return fail(TWR_ERR_INVALID, "set_cell: env / cell index out of range");
+    if (value < 0 || value >= v->p.N) return fail(TWR_ERR_INVALID, "set_cell: Puzzle cell values must be tiles 0..cells-1");
+    twr_engine* e = v->eng;
+    CU_TRY(cudaSetDevice(e->device));
+    // byte `cell` of the env's 16-byte board; blank index and depth stay as they are (puzzle.rs:71-73)
+    const uint8_t b = (uint8_t)value;
+    CU_TRY(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(v->cells + env) + cell, &b, 1, cudaMemcpyHostToDevice, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     return TWR_OK;
 }
@@ -610,14 +658,28 @@ static int check_policy_env(const twr_policy* p, const EnvParams& env, PolicyDev
     if (p->dev.A != 4) return fail(TWR_ERR_INVALID, "policy has " + std::to_string(p->dev.A) + " actions, env has 4");
     *dev = p->dev;
     dev->n_obs = env.N;
+    if (dev->tc_compact_n > 0 && (env.kind != TWR_ENV_GRIDWORLD || env.N != dev->tc_compact_n)) dev->tc_pack = nullptr;   // fp32 kernel
     return TWR_OK;
 }
 
 static void launch_forward(twr_engine* e, const PolicyDev& dev, const ForwardArgs& a) {
+    bool ok = true;
     if (dev.generic) launch_forward_generic(e->stream, dev, a);   // general layer stacks (f4)
-    else if (dev.tc_pack) launch_forward_tc(e->stream, dev, a);   // policies whose shape fits the tensor-core kernel (f16x2 engines)
-    else launch_forward_fp32(e->stream, dev, a);
+    else if (dev.tc_pack) {                                       // policies whose shape fits the tensor-core kernel (f16x2 engines)
+        ForwardArgs t = a;
+        t.tc_terms = e->tc_terms;
+        ok = launch_forward_tc(e->stream, dev, t);
+    } else ok = launch_forward_fp32(e->stream, dev, a);
+    if (!ok) e->launch_error = true;
 }
+// after the launches of a call: a forward that could not be launched must not look like success (no records, TWR_OK)
+#define FWD_CHECK(e)                                                                                          \
+    do {                                                                                                      \
+        if ((e)->launch_error) {                                                                              \
+            (e)->launch_error = false;                                                                        \
+            return fail(TWR_ERR_CUDA, "policy forward kernel could not be launched (shape / shared memory / tensor map)"); \
+        }                                                                                                     \
+    } while (0)
 
 int twr_policy_forward(twr_engine* e, const twr_policy* p, twr_envs* v, const int32_t* perm_idx, int32_t apply_masks,
                        float* logits, float* values) {
@@ -646,6 +708,7 @@ int twr_policy_forward(twr_engine* e, const twr_policy* p, twr_envs* v, const in
     launch_forward(e, dev, a);
     if (apply_masks) launch_mask_logits(e->stream, v->p, v->cells, v->meta, v->n, dev.A, d_logits.d);
     CU_TRY(cudaGetLastError());
+    FWD_CHECK(e);
     std::vector<float4> h((size_t)v->n);
     CU_TRY(cudaMemcpyAsync(h.data(), d_logits.d, sizeof(float4) * (size_t)v->n, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaMemcpyAsync(values, d_values.d, sizeof(float) * (size_t)v->n, cudaMemcpyDeviceToHost, e->stream));
@@ -672,8 +735,16 @@ int twr_debug_forward_profile(twr_engine* e, const twr_policy* p, twr_envs* v, i
     a.logits = d_logits.d; a.values = d_values.d; a.dbg = d_dbg.d; a.dbg_flags = flags;
     launch_forward(e, dev, a);
     CU_TRY(cudaGetLastError());
+    FWD_CHECK(e);
     CU_TRY(cudaMemcpyAsync(counters, d_dbg.d, sizeof(long long) * ((size_t)148 * 16 + 256), cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
+    return TWR_OK;
+}
+
+int twr_debug_set_tc_terms(twr_engine* e, int32_t terms) {
+    if (!e) return fail(TWR_ERR_INVALID, "engine is NULL");
+    if (terms < -1 || terms > 7) return fail(TWR_ERR_INVALID, "terms must be -1 or a 3-bit mask");
+    e->tc_terms = terms < 0 ? (e->precision == TWR_PREC_F16X2_W16 ? (8 | 1 | 2) : 0) : (8 | terms);
     return TWR_OK;
 }
 
@@ -698,7 +769,7 @@ int twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* ob
     CU_TRY(cudaSetDevice(e->device));
     PolicyDev dev = p->dev;
     dev.n_obs = n_obs;
-    if (multiset) dev.tc_pack = nullptr;
+    if (multiset || dev.tc_compact_n > 0) dev.tc_pack = nullptr;   // arbitrary indices: not the compact GridWorld table
     Staging<float4> d_logits; Staging<float> d_values; Staging<int32_t> d_perm, d_obs;
     int rc;
     if ((rc = d_logits.alloc((size_t)n)) || (rc = d_values.alloc((size_t)n)) || (rc = d_obs.alloc((size_t)n * n_obs))) return rc;
@@ -714,6 +785,7 @@ int twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* ob
     a.logits = d_logits.d; a.values = d_values.d;
     launch_forward(e, dev, a);
     CU_TRY(cudaGetLastError());
+    FWD_CHECK(e);
     std::vector<float4> h((size_t)n);
     CU_TRY(cudaMemcpyAsync(h.data(), d_logits.d, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaMemcpyAsync(values, d_values.d, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
@@ -938,6 +1010,7 @@ static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev&
     launch_episode_offsets(st, b, ids);
     launch_compact(st, env, b, dev.A);
     CU_TRY(cudaGetLastError());
+    FWD_CHECK(e);
     return TWR_OK;
 }
 
@@ -1259,6 +1332,7 @@ static int run_solve(twr_engine* e, const EnvParams& env, const PolicyDev& dev, 
         }
     }
     CU_TRY(cudaGetLastError());
+    FWD_CHECK(e);
     CU_TRY(cudaStreamSynchronize(st));       // staging buffers are freed on return
     return TWR_OK;
 }
@@ -1389,6 +1463,7 @@ int twr_mcts_probs(twr_engine* e, const twr_policy* p, twr_envs* v, int32_t n_si
     enqueue_mcts(e, dev, a, live.d, n_live.d, B);
     launch_mcts_read(e->stream, a, B, d_probs.d, d_vis.d);
     CU_TRY(cudaGetLastError());
+    FWD_CHECK(e);
     CU_TRY(cudaMemcpyAsync(probs, d_probs.d, sizeof(float) * (size_t)B * dev.A, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaMemcpyAsync(visits, d_vis.d, sizeof(int32_t) * (size_t)B * dev.A, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
@@ -1417,6 +1492,7 @@ int twr_az_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p,
     cudaStream_t st = e->stream;
     e->has_last = false;
     b.B = B;
+    b.obs_u8 = 0;
     select_outset(e, 0);
     const uint32_t cid = e->collect_id++;
     const EnvIds ids{(uint32_t)((int64_t)e->rank * B), (uint32_t)(B - 1), (uint32_t)B, 0u};
@@ -1443,6 +1519,7 @@ int twr_az_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p,
     launch_episode_offsets(st, b, ids);
     launch_compact(st, plan.env, b, plan.dev.A);
     CU_TRY(cudaGetLastError());
+    FWD_CHECK(e);
     CU_TRY(cudaMemcpyAsync(e->h_stats, b.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     twr_collected& c = e->last;

@@ -267,11 +267,13 @@ int forward_fp32_supported(const PolicyDev& p, const EnvParams& env, const char*
     if (p.obs_size >= 65536 || p.n_obs > TWR_MAX_CELLS) { *why = msg_o; return 0; }
     ForwardArgs a{};
     a.n = 1;
-    if (!dispatch(nullptr, p, a, true)) { *why = msg_e; return 0; }
+    PolicyDev q = p;
+    q.n_obs = TWR_MAX_CELLS;                 // the fit must hold for any observation length a later launch may carry
+    if (!dispatch(nullptr, q, a, true)) { *why = msg_e; return 0; }
     return 1;
 }
 
-void launch_forward_fp32(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a) {
-    if (a.n <= 0) return;
-    dispatch(st, p, a, false);
+bool launch_forward_fp32(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a) {
+    if (a.n <= 0) return true;
+    return dispatch(st, p, a, false);
 }

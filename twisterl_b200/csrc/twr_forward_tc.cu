@@ -422,12 +422,10 @@ TcParams make_params(const PolicyDev& p) {
     return t;
 }
 
-int g_num_sms = 0;
-
 }  // namespace
 
 
-int forward_tc_supported(const PolicyDev& p, const EnvParams&, const char** why) {
+static int single_supported(const PolicyDev& p, const char** why) {
     static const char* m1 = "tensor-core forward needs obs_size <= 256 (one-hot operand must fit 64 KB of shared memory)";
     static const char* m2 = "tensor-core forward needs embedding size a multiple of 128, <= 1024";
     static const char* m3 = "tensor-core forward needs common width 128 or 256";
@@ -436,10 +434,21 @@ int forward_tc_supported(const PolicyDev& p, const EnvParams&, const char** why)
     if (p.E % 128 || p.E > 1024 || p.E < 128) { *why = m2; return 0; }
     if (p.H != 128 && p.H != 256) { *why = m3; return 0; }
     if (p.n_obs > MAX_OBS) { *why = m4; return 0; }
+    if (p.tc_compact_n > 0) { *why = m1; return 0; }
     return 1;
 }
 
+// either kernel: the CTA-pair kernel (twr_forward_tc2.cu; also takes the compact GridWorld table) or the single-CTA one
+int forward_tc_supported(const PolicyDev& p, const EnvParams&, const char** why) {
+    if (forward_tc2_supported(p) && p.n_obs <= MAX_OBS) return 1;
+    return single_supported(p, why);
+}
+
 static size_t single_pack_bytes(const PolicyDev& p) {
+    const char* why = "";
+    PolicyDev q = p;
+    q.n_obs = 1;
+    if (!single_supported(q, &why)) return 0;
     const TcParams t = make_params(p);
     return (g1_tiles(t) + g2_tiles(t)) * TILE_BYTES;
 }
@@ -448,9 +457,11 @@ static size_t single_pack_bytes(const PolicyDev& p) {
 size_t forward_tc_pack_bytes(const PolicyDev& p) { return single_pack_bytes(p) + forward_tc2_pack_bytes(p); }
 
 void launch_forward_tc_pack(cudaStream_t st, const PolicyDev& p, void* pack) {
-    const TcParams t = make_params(p);
-    k_tc_pack<<<1024, 256, 0, st>>>(p, t, reinterpret_cast<__half*>(pack));
-    g_twr_launches.fetch_add(1, std::memory_order_relaxed);
+    if (single_pack_bytes(p)) {
+        const TcParams t = make_params(p);
+        k_tc_pack<<<1024, 256, 0, st>>>(p, t, reinterpret_cast<__half*>(pack));
+        g_twr_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     if (forward_tc2_supported(p)) launch_forward_tc2_pack(st, p, reinterpret_cast<unsigned char*>(pack) + single_pack_bytes(p));
 }
 
@@ -483,18 +494,27 @@ int forward_tc_can_fuse(const PolicyDev& p) {
     return g_pair && forward_tc2_supported(p);
 }
 
-void launch_forward_tc(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a) {
-    if (a.n <= 0) return;
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+static bool use_pair(const PolicyDev& p) {
     resolve_mode();
-    if (g_pair && forward_tc2_supported(p)) {
-        if (launch_forward_tc2(st, p, a, reinterpret_cast<const unsigned char*>(p.tc_pack) + single_pack_bytes(p))) return;
-        g_pair = 0;   // tensor map could not be created: use the single-CTA kernel from now on
-    }
+    return (g_pair || !single_pack_bytes(p)) && forward_tc2_supported(p);
+}
+
+bool forward_tc_prepare(const PolicyDev& p) {
+    if (!use_pair(p)) return true;
+    return forward_tc2_prepare(p, reinterpret_cast<const unsigned char*>(p.tc_pack) + single_pack_bytes(p));
+}
+
+void forward_tc_forget(const PolicyDev& p) {
+    if (p.tc_pack && forward_tc2_supported(p)) forward_tc2_forget(reinterpret_cast<const unsigned char*>(p.tc_pack) + single_pack_bytes(p));
+}
+
+bool launch_forward_tc(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a) {
+    if (a.n <= 0) return true;
+    // no silent change of kernel: a pair-kernel launch that cannot be made is an error of the call
+    if (use_pair(p)) return launch_forward_tc2(st, p, a, reinterpret_cast<const unsigned char*>(p.tc_pack) + single_pack_bytes(p));
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_cluster < 0) {
         const char* e = getenv("TWISTERL_B200_CLUSTER");
         g_cluster = e ? atoi(e) : 1;
@@ -504,7 +524,7 @@ void launch_forward_tc(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a
     const int csz = g_cluster;
     const int n_tiles = (int)((a.n + TM - 1) / TM);
     const int n_groups = (n_tiles + csz - 1) / csz;
-    const int max_clusters = g_num_sms / csz;
+    const int max_clusters = sms / csz;
     const int grid = (n_groups < max_clusters ? n_groups : max_clusters) * csz;
     if (t.NH == 2) {
         if (csz == 1) launch_cfg<2, 1>(st, p, a, t, grid); else if (csz == 2) launch_cfg<2, 2>(st, p, a, t, grid); else launch_cfg<2, 4>(st, p, a, t, grid);
@@ -512,4 +532,5 @@ void launch_forward_tc(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a
         if (csz == 1) launch_cfg<1, 1>(st, p, a, t, grid); else if (csz == 2) launch_cfg<1, 2>(st, p, a, t, grid); else launch_cfg<1, 4>(st, p, a, t, grid);
     }
     g_twr_launches.fetch_add(1, std::memory_order_relaxed);
+    return true;
 }

@@ -124,16 +124,19 @@ __device__ __forceinline__ void tc2_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 constexpr uint32_t IDESC_256x128 = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 constexpr uint32_t IDESC_256x256 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
 
-struct Tc2Params { int NC, NKB1, E, H; };
+// cN > 0: GEMM1 runs over the COMPACT table of a GridWorld policy -- compact row k = cell (k / 4), value (k % 4) stands
+// for table row (k / 4) * cN + (k % 4); the other obs_size - 4 * cN rows are unreachable (lib.rs:74-81: cell values 0..3)
+struct Tc2Params { int NC, NKB1, E, H, cN; };
 __host__ __device__ inline size_t slots_g1(const Tc2Params& t) { return (size_t)t.NC * t.NKB1; }
-__host__ __device__ inline size_t slots_g2(const Tc2Params& t) { return (size_t)t.NC * 4; }
+__host__ __device__ inline size_t slots_g2(const Tc2Params& t) { return (size_t)t.NC * (t.H == 256 ? 4 : 2); }
 __host__ __device__ inline size_t slots_per_rank(const Tc2Params& t) { return slots_g1(t) + slots_g2(t); }
 
 // Operand image per CTA rank r (rank 0 image, then rank 1 image), in streaming order, 16 KB per ring slot:
 //   G1 slot (s,kb,part) : [128 rows x 64 k] of the hi (part 0) or lo (part 1) table, rows n = feature (2s+r)*128 + (0..127),
 //                         k = obs row kb*64 + kk -- GEMM1 runs as N = 256 MMAs over a PAIR of 128-feature chunks (both D1
 //                         buffers at once; rank r's half of B is chunk 2s+r): N = 128 MMAs issue at half rate
-//   G2 slot (j,kb,part) : [128 rows x 64 k], rows n = output r*128 + (0..127), k = feature j*128 + kb*64 + kk
+//   G2 slot (j,kb,part) : [128 rows x 64 k], rows n = output r*128 + (0..127), k = feature j*128 + kb*64 + kk      (H = 256)
+//   G2 slot (j,part)    : two [64 rows x 64 k] sub-tiles (kb = 0, 1), rows n = output r*64 + (0..63)              (H = 128)
 __global__ void __launch_bounds__(256) k_tc2_pack(PolicyDev p, Tc2Params t, __half* __restrict__ pack) {
     const size_t spr = slots_per_rank(t), n1 = slots_g1(t);
     const size_t total = 2 * spr * (TILE_BYTES / 2);
@@ -152,10 +155,11 @@ __global__ void __launch_bounds__(256) k_tc2_pack(PolicyDev p, Tc2Params t, __ha
             // rows of rank r: chunk 2sc+r for the N = 256 MMAs; in the LAST k-block the two chunks are finished one after
             // the other with N = 128 MMAs (rows 0..63 = rank r's half of chunk 2sc, rows 64..127 = its half of chunk 2sc+1)
             const int f = kb == t.NKB1 - 1 ? (2 * sc + (int)(row >> 6)) * 128 + r * 64 + (int)(row & 63u) : (2 * sc + r) * 128 + (int)row;
-            const int k = kb * 64 + (int)kk;
+            int k = kb * 64 + (int)kk;
+            if (t.cN > 0) k = (k >> 2) < t.cN ? (k >> 2) * t.cN + (k & 3) : p.obs_size;
             if (k < p.obs_size) x = p.emb[(size_t)k * p.E + f];
             off = tile_off(row, kk);
-        } else {
+        } else if (t.H == 256) {
             const size_t q = slot - n1;
             const int j = (int)(q / 4), kb = (int)((q % 4) / 2);
             lo_part = (int)(q % 2);
@@ -163,6 +167,15 @@ __global__ void __launch_bounds__(256) k_tc2_pack(PolicyDev p, Tc2Params t, __ha
             const int o = r * 128 + (int)row, f = j * 128 + kb * 64 + (int)kk;
             x = p.w1[(size_t)f * p.H + o];
             off = tile_off(row, kk);
+        } else {
+            const size_t q = slot - n1;
+            const int j = (int)(q / 2);
+            lo_part = (int)(q % 2);
+            const uint32_t row = within >> 6, kk = within & 63u;
+            const int kb = (int)(row >> 6);
+            const int o = r * 64 + (int)(row & 63u), f = j * 128 + kb * 64 + (int)kk;
+            x = p.w1[(size_t)f * p.H + o];
+            off = (uint32_t)kb * 8192u + tile_off(row & 63u, kk);
         }
         const __half hi = __float2half_rn(x);
         const __half v = lo_part ? __float2half_rn(x - __half2float(hi)) : hi;
@@ -261,8 +274,15 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     uint8_t* operm_s = smem + SM_OPERM;
     // twist tables in shared memory when they fit (obs_size <= 256 makes every entry a byte): the one-hot build looks
     // up 16 of them per env and step
-    const bool operm_smem = p.n_perms > 0 && p.n_perms * p.obs_size <= OPERM_MAX;
+    const bool operm_smem = p.n_perms > 0 && p.obs_size <= 256 && p.n_perms * p.obs_size <= OPERM_MAX;
     const int NC = t.NC, NKB1 = t.NKB1, H = t.H;
+    // Split-operand terms of this launch (ForwardArgs::tc_terms; 0 = all): GEMM1 always has one-hot x table_hi and GEMM2
+    // h1_hi x W_hi; bit 0 adds one-hot x table_lo, bit 1 h1_lo x W_hi, bit 2 h1_hi x W_lo.  Skipped terms are neither
+    // streamed nor issued.
+    const int terms = a.tc_terms ? a.tc_terms : 7;
+    const bool g1_lo = (terms & 1) != 0, g2_alo = (terms & 2) != 0, g2_wlo = (terms & 4) != 0;
+    const uint32_t idesc2 = H == 256 ? IDESC_256x256 : IDESC_256x128;   // GEMM2: N = H
+    const int g2_units = H == 256 ? 4 : 2;                               // ring slots of one chunk's GEMM2 (see k_tc2_pack)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSLOTS; ++i) { mbar_init(bar(B_FULL0 + i), 1); mbar_init(bar(B_EMPTY0 + i), 1); }
@@ -319,8 +339,14 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 }
                 ++use;
             };
-            auto push_g1 = [&](int sc) { for (int i = 0; i < 2 * NKB1; ++i) push(g1_row0 + (sc * 2 * NKB1 + i) * (TILE_BYTES / 128)); };
-            auto push_g2 = [&](int j) { for (int i = 0; i < 4; ++i) push(g2_row0 + (j * 4 + i) * (TILE_BYTES / 128)); };
+            auto push_g1 = [&](int sc) {
+                for (int i = 0; i < 2 * NKB1; ++i)
+                    if (!(i & 1) || g1_lo) push(g1_row0 + (sc * 2 * NKB1 + i) * (TILE_BYTES / 128));
+            };
+            auto push_g2 = [&](int j) {                     // unit u: part = u & 1 (H = 256: u = kb * 2 + part; H = 128: u = part)
+                for (int u = 0; u < g2_units; ++u)
+                    if (!(u & 1) || g2_wlo) push(g2_row0 + (j * g2_units + u) * (TILE_BYTES / 128));
+            };
             for (int it = 0; it < n_items; ++it)
                 for (int sc = 0; sc < NC / 2; ++sc) { push_g1(sc); push_g2(2 * sc); push_g2(2 * sc + 1); }
             if (a.dbg) a.dbg[blockIdx.x * 16 + 8] = w_empty;
@@ -350,7 +376,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     const uint32_t d = tmem + D1_COL;
                     for (int kb = 0; kb < NKB1 - 1; ++kb) {
                         const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
-                        for (int part = 0; part < 2; ++part) {
+                        for (int part = 0; part < (g1_lo ? 2 : 1); ++part) {
                             const long long w0 = w_slot;
                             const uint32_t slot = wait_slot();
                             w_slot_g1 += w_slot - w0;
@@ -372,7 +398,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                         const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
                         const long long w0 = w_slot;
                         const uint32_t slot_h = wait_slot();
-                        const uint32_t slot_l = wait_slot();
+                        const uint32_t slot_l = g1_lo ? wait_slot() : slot_h;
                         w_slot_g1 += w_slot - w0;
                         const uint64_t bh = make_desc(sbase + SM_RING + slot_h * TILE_BYTES);
                         const uint64_t bl = make_desc(sbase + SM_RING + slot_l * TILE_BYTES);
@@ -381,7 +407,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 tc2_mma(d, ad + 2u * ks, bh + 2u * ks, IDESC_256x128, (kb | ks) != 0);
-                                tc2_mma(d, ad + 2u * ks, bl + 2u * ks, IDESC_256x128, 1u);
+                                if (g1_lo) tc2_mma(d, ad + 2u * ks, bl + 2u * ks, IDESC_256x128, 1u);
                             }
                         }
                         tc2_commit(bar(B_D1_FULL0));
@@ -389,11 +415,11 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 tc2_mma(d + 128u, ad + 2u * ks, bh + half + 2u * ks, IDESC_256x128, (kb | ks) != 0);
-                                tc2_mma(d + 128u, ad + 2u * ks, bl + half + 2u * ks, IDESC_256x128, 1u);
+                                if (g1_lo) tc2_mma(d + 128u, ad + 2u * ks, bl + half + 2u * ks, IDESC_256x128, 1u);
                             }
                         }
                         tc2_commit(bar(B_EMPTY0 + slot_h));
-                        tc2_commit(bar(B_EMPTY0 + slot_l));
+                        if (g1_lo) tc2_commit(bar(B_EMPTY0 + slot_l));
                         tc2_commit(bar(B_D1_FULL1));
                     }
                     if (sc == NC / 2 - 1) tc2_commit(bar(B_A1_EMPTY));
@@ -407,22 +433,25 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     stamp(it, 5 + j);
                     const uint32_t a_base = tmem + D1_COL + buf * 128u;
                     const uint32_t d = tmem + D2_COL;
-                    for (int kb = 0; kb < 2; ++kb) {
-                        for (int part = 0; part < 2; ++part) {
-                            const uint32_t slot = wait_slot();
-                            const uint64_t bd = make_desc(sbase + SM_RING + slot * TILE_BYTES);
-                            const bool first = (j == 0 && kb == 0 && part == 0);
-                            if (!(a.dbg_flags & 4)) {
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    const uint32_t sidx = kb * 4 + ks;
-                                    const uint32_t ah = a_base + 32u * (sidx >> 1) + 8u * (sidx & 1u);
-                                    tc2_mma_ts(d, ah, bd + 2u * ks, IDESC_256x256, !(first && ks == 0));
-                                    if (part == 0) tc2_mma_ts(d, ah + 16u, bd + 2u * ks, IDESC_256x256, 1u);
-                                }
+                    // unit u = one ring slot: H = 256 -> (kb, part) = (u >> 1, u & 1), 4 k-steps of 16 features;
+                    // H = 128 -> part = u, both k-blocks (two 64-row sub-tiles), 8 k-steps
+                    for (int u = 0; u < g2_units; ++u) {
+                        const int part = u & 1;
+                        if (part && !g2_wlo) continue;
+                        const uint32_t slot = wait_slot();
+                        const uint64_t bd = make_desc(sbase + SM_RING + slot * TILE_BYTES);
+                        const bool first = (j == 0 && u == 0);
+                        if (!(a.dbg_flags & 4)) {
+                            const int nks = H == 256 ? 4 : 8;
+                            for (int ks = 0; ks < nks; ++ks) {
+                                const uint32_t sidx = H == 256 ? (uint32_t)((u >> 1) * 4 + ks) : (uint32_t)ks;
+                                const uint32_t ah = a_base + 32u * (sidx >> 1) + 8u * (sidx & 1u);
+                                const uint64_t bk = H == 256 ? bd + 2u * ks : bd + (uint64_t)((ks >> 2) * (8192 >> 4)) + 2u * (ks & 3);
+                                tc2_mma_ts(d, ah, bk, idesc2, !(first && ks == 0));
+                                if (part == 0 && g2_alo) tc2_mma_ts(d, ah + 16u, bk, idesc2, 1u);
                             }
-                            tc2_commit(bar(B_EMPTY0 + slot));
                         }
+                        tc2_commit(bar(B_EMPTY0 + slot));
                     }
                     ++a2use;
                     if (j == NC - 1) tc2_commit(bar(B_D2_FULL));
@@ -488,7 +517,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             // bookkeeping of the previous tile's ones), then set one fp16 1.0 per observation index.
             const uint32_t rx = (uint32_t)row & 7u;
             const uint32_t row_base = ((uint32_t)row >> 3) * 1024u + rx * 128u;
-            const bool fast = a.env.kind == 0 && !a.obs_rows && perm < 0 && n_obs <= 16;   // Puzzle, no twist
+            const bool fast = a.env.kind == 0 && !a.obs_rows && perm < 0 && n_obs <= 16 && t.cN == 0;   // Puzzle, no twist
             if (threadIdx.x == 192) stamp(it, 20);
             mbar_wait_t(bar(B_A1_EMPTY), (it & 1) ^ 1, w_a1e, timed);      // GEMM1 of the previous item is done with A1
             if (threadIdx.x == 192) stamp(it, 21);
@@ -518,6 +547,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                         r = a.obs_rows ? (uint32_t)a.obs_rows[pos * n_obs + i] : (uint32_t)(i * a.env.N) + env_board(a.env, s, i);
                         if (perm >= 0)                                                         // twist-in, policy.rs:81-83
                             r = operm_smem ? (uint32_t)operm_s[perm * p.obs_size + (int)r] : (uint32_t)p.obs_perms[(size_t)perm * p.obs_size + r];
+                        if (t.cN > 0) r = (r / (uint32_t)t.cN) * 4u + (r % (uint32_t)t.cN);   // compact GridWorld table (values 0..3)
                     }
                     const uint32_t k = r & 63u;
                     *reinterpret_cast<__half*>(smem + SM_A1 + (r >> 6) * TILE_BYTES + row_base + ((((k >> 3) ^ rx) & 7u) << 4) + (k & 7u) * 2u) =
@@ -643,9 +673,9 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             const long long t_e2 = timed ? clock64() : 0;
             float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < H / 128; ++q) {
                 uint32_t v0[32], v1[32];
-                const uint32_t col0 = (uint32_t)chalf * 128u + (uint32_t)q * 64u;
+                const uint32_t col0 = (uint32_t)(chalf * (H / 2)) + (uint32_t)q * 64u;
                 tc_ld32(tmem + lane_addr + D2_COL + col0, v0);
                 tc_ld32(tmem + lane_addr + D2_COL + col0 + 32u, v1);
                 tc_wait_ld();
@@ -729,20 +759,37 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
 
 Tc2Params make_params2(const PolicyDev& p) {
     Tc2Params t;
-    t.E = p.E; t.H = p.H; t.NC = p.E / 128; t.NKB1 = (p.obs_size + 63) / 64;
+    t.E = p.E; t.H = p.H; t.NC = p.E / 128; t.cN = p.tc_compact_n;
+    t.NKB1 = ((p.tc_compact_n > 0 ? 4 * p.tc_compact_n : p.obs_size) + 63) / 64;
     return t;
 }
 
-int g_sms = 0;
-std::mutex g_tmap_mu;
-std::map<std::pair<const void*, size_t>, CUtensorMap> g_tmaps;   // keyed by (image address, bytes): a freed image's address can be reused by a larger one
+// Per-device launch state (one engine per device, several devices per process): SM count, whether every cluster of a
+// full grid is resident at once (the balanced schedule needs it), the shared-memory attribute, and the tensor maps of
+// the operand images that live on that device.
+struct DevState {
+    int sms = 0;
+    int max_clusters = -1;
+    bool attr_set = false;
+    std::map<std::pair<const void*, size_t>, CUtensorMap> tmaps;   // keyed by (image address, bytes): a freed image's address can be reused by a larger one
+};
+constexpr int MAX_DEVICES = 64;
+std::mutex g_dev_mu;
+DevState g_dev[MAX_DEVICES];
+
+DevState* dev_state() {                      // call with g_dev_mu held
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return nullptr;
+    DevState& d = g_dev[dev];
+    if (d.sms == 0) cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    return &d;
+}
 
 // Tensor map over the packed operand image viewed as [rows][128 bytes]; one 128 x 128 box = one ring slot.
-bool get_tmap(const void* pack, size_t bytes, CUtensorMap* out) {
-    std::lock_guard<std::mutex> lk(g_tmap_mu);
+bool get_tmap(DevState& d, const void* pack, size_t bytes, CUtensorMap* out) {
     const std::pair<const void*, size_t> key(pack, bytes);
-    auto it = g_tmaps.find(key);
-    if (it != g_tmaps.end()) { *out = it->second; return true; }
+    auto it = d.tmaps.find(key);
+    if (it != d.tmaps.end()) { *out = it->second; return true; }
     typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -758,14 +805,18 @@ bool get_tmap(const void* pack, size_t bytes, CUtensorMap* out) {
                                                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
-    g_tmaps[key] = m;
+    d.tmaps[key] = m;
     *out = m;
     return true;
 }
 
 }  // namespace
 
-int forward_tc2_supported(const PolicyDev& p) { return p.H == 256 && p.E % 256 == 0; }   // GEMM1 works on chunk pairs
+// GEMM1 works on chunk pairs (E % 256), the one-hot operand holds <= 256 (compact) rows, GEMM2 is N = H in {128, 256}
+int forward_tc2_supported(const PolicyDev& p) {
+    const int k1 = p.tc_compact_n > 0 ? 4 * p.tc_compact_n : p.obs_size;
+    return (p.H == 256 || p.H == 128) && p.E % 256 == 0 && p.E <= 1024 && k1 <= 64 * MAX_KB1;
+}
 
 size_t forward_tc2_pack_bytes(const PolicyDev& p) {
     if (!forward_tc2_supported(p)) return 0;
@@ -777,41 +828,58 @@ void launch_forward_tc2_pack(cudaStream_t st, const PolicyDev& p, void* pack) {
     g_twr_launches.fetch_add(1, std::memory_order_relaxed);
 }
 
-bool launch_forward_tc2(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a, const void* pack) {
-    if (a.n <= 0) return true;
+// Everything a launch needs besides the arguments, resolved once (at policy creation) so that a launch cannot fail for
+// a reason known earlier: the tensor map of `pack`, the kernel's shared-memory attribute, cluster residency.
+bool forward_tc2_prepare(const PolicyDev& p, const void* pack) {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    DevState* d = dev_state();
+    if (!d) return false;
     CUtensorMap tmap;
-    if (!get_tmap(pack, forward_tc2_pack_bytes(p), &tmap)) return false;
-    if (g_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!get_tmap(*d, pack, forward_tc2_pack_bytes(p), &tmap)) return false;
+    if (!d->attr_set) {
+        if (cudaFuncSetAttribute(k_forward_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) != cudaSuccess) return false;
+        d->attr_set = true;
     }
-    const int n_tiles = (int)((a.n + TM - 1) / TM);
-    const int n_groups = (n_tiles + 1) / 2, max_pairs = g_sms / 2;
-    const int grid = (n_groups < max_pairs ? n_groups : max_pairs) * 2;
-    cudaFuncSetAttribute(k_forward_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-    // The balanced schedule lets a pair wait for another pair's progress, which needs every cluster of the grid to
-    // be resident at once: query it once and keep the plain schedule when the device cannot hold them all.
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
+    if (d->max_clusters < 0) {
+        // The balanced schedule lets a pair wait for another pair's progress, which needs every cluster of the grid to
+        // be resident at once: query it once per device and keep the plain schedule when the device cannot hold them all.
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(max_pairs * 2)); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SM_TOTAL;
+        cfg.gridDim = dim3((unsigned)((d->sms / 2) * 2)); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = SM_TOTAL;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int nc = 0;
-        max_clusters = cudaOccupancyMaxActiveClusters(&nc, k_forward_tc2, &cfg) == cudaSuccess ? nc : 0;
+        d->max_clusters = cudaOccupancyMaxActiveClusters(&nc, k_forward_tc2, &cfg) == cudaSuccess ? nc : 0;
         cudaGetLastError();
     }
-    if (a.bal_flags && max_clusters < grid / 2) {
-        ForwardArgs plain = a;
-        plain.bal_flags = nullptr; plain.bal_delta = 0;
-        k_forward_tc2<<<grid, NTHREADS, SM_TOTAL, st>>>(p, plain, make_params2(p), tmap);
-        g_twr_launches.fetch_add(1, std::memory_order_relaxed);
-        return true;
+    return true;
+}
+
+void forward_tc2_forget(const void* pack) {   // the operand image is being freed: drop its tensor map
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    DevState* d = dev_state();
+    if (!d) return;
+    for (auto it = d->tmaps.begin(); it != d->tmaps.end();)
+        it = it->first.first == pack ? d->tmaps.erase(it) : std::next(it);
+}
+
+bool launch_forward_tc2(cudaStream_t st, const PolicyDev& p, const ForwardArgs& a, const void* pack) {
+    if (a.n <= 0) return true;
+    CUtensorMap tmap;
+    int sms, max_clusters;
+    {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        DevState* d = dev_state();
+        if (!d || !d->attr_set || !get_tmap(*d, pack, forward_tc2_pack_bytes(p), &tmap)) return false;   // forward_tc2_prepare did not run / failed
+        sms = d->sms; max_clusters = d->max_clusters;
     }
-    k_forward_tc2<<<grid, NTHREADS, SM_TOTAL, st>>>(p, a, make_params2(p), tmap);
+    const int n_tiles = (int)((a.n + TM - 1) / TM);
+    const int n_groups = (n_tiles + 1) / 2, max_pairs = sms / 2;
+    const int grid = (n_groups < max_pairs ? n_groups : max_pairs) * 2;
+    ForwardArgs args = a;
+    if (a.bal_flags && max_clusters < grid / 2) { args.bal_flags = nullptr; args.bal_delta = 0; }
+    k_forward_tc2<<<grid, NTHREADS, SM_TOTAL, st>>>(p, args, make_params2(p), tmap);
     g_twr_launches.fetch_add(1, std::memory_order_relaxed);
     return true;
 }

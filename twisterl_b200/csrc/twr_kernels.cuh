@@ -19,6 +19,10 @@ struct PolicyDev {
     const int32_t* act_perms;  // [n_perms][A]
     // tensor-core operands (fp16 hi/lo split, UMMA canonical K-major tiles), see twr_forward_tc.cu
     const void* tc_pack;
+    // > 0: the pair kernel's GEMM1 image holds only the 4 * tc_compact_n reachable rows of a GridWorld table
+    // (row (i, v) = i * tc_compact_n + v, v in 0..3; examples/grid_world/src/lib.rs:74-81,161-163); such a policy takes
+    // the tensor-core path only for GridWorld envs of that size whose observation comes from the env state
+    int tc_compact_n;
     // General layer stacks: any policy that is not "embedding+ReLU -> one common Linear+ReLU ->
     // single-Linear heads" runs k_forward_generic (twr_forward_generic.cu) from this description instead.
     int generic;                              // 1: the fields above (w1..bv, H) are unused
@@ -105,22 +109,30 @@ struct ForwardArgs {
     // balanced item schedule of the persistent pair kernel: groups beyond a whole number per CTA pair are cut along
     // TIME into pieces handed from pair to pair; bal_flags[g] counts the finished steps of such a group (zeroed per launch)
     int32_t* bal_flags; int bal_delta;   // bal_delta: extra item slots granted to each hand-off (0 = balancing off)
+    // split-operand terms of the tensor-core forward (k_forward_tc2): 0 = all (f16x2); otherwise 8 | bit 0 one-hot x table_lo
+    // | bit 1 h1_lo x W_hi | bit 2 h1_hi x W_lo on top of the hi x hi products (TWR_PREC_F16X2_W16 = 8 | 1 | 2)
+    int tc_terms;
     int dbg_flags;    // ablations (k_forward_tc2, timing only): 1 skip epilogue-1 TMEM traffic, 2 no operand TMA traffic, 4 skip GEMM2 MMAs, 8 skip GEMM1 MMAs
     long long* dbg;   // optional [gridDim][16] cycle counters written by k_forward_tc (debug/profiling)
 };
 int  forward_fp32_supported(const PolicyDev& p, const EnvParams& env, const char** why);
-void launch_forward_fp32(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a);
+bool launch_forward_fp32(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a);   // false: shape does not fit shared memory
 int  forward_tc_supported(const PolicyDev& p, const EnvParams& env, const char** why);
 // builds / refreshes the packed fp16 hi/lo operand tiles from the fp32 blob
 size_t forward_tc_pack_bytes(const PolicyDev& p);
 void launch_forward_tc_pack(cudaStream_t s, const PolicyDev& p, void* pack);
-void launch_forward_tc(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a);
+bool launch_forward_tc(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a);   // false: the launch could not be made (see forward_tc_prepare)
+// resolves, at policy creation, everything a later launch depends on (tensor map of the operand image, kernel attributes)
+bool forward_tc_prepare(const PolicyDev& p);
+void forward_tc_forget(const PolicyDev& p);    // before the operand image is freed
 // CTA-pair (cta_group::2) variant, twr_forward_tc2.cu; `pack` is its own operand image
 int    forward_tc2_supported(const PolicyDev& p);
 size_t forward_tc2_pack_bytes(const PolicyDev& p);
 void   launch_forward_tc2_pack(cudaStream_t s, const PolicyDev& p, void* pack);
 int    forward_tc_can_fuse(const PolicyDev& p);   // 1 when launch_forward_tc will run the fusable pair kernel
-bool   launch_forward_tc2(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a, const void* pack);  // false: tensor map unavailable
+bool   launch_forward_tc2(cudaStream_t s, const PolicyDev& p, const ForwardArgs& a, const void* pack);  // false: forward_tc2_prepare missing / failed
+bool   forward_tc2_prepare(const PolicyDev& p, const void* pack);
+void   forward_tc2_forget(const void* pack);
 
 // f1: batched single_solve step (rust/src/rl/solve.rs:17-71) for every live env
 struct SolveArgs {

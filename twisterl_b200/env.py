@@ -46,6 +46,9 @@ class EnvBatch:
         a = np.ascontiguousarray(states, dtype=np.int64).reshape(self.n, self.cells)
         _lib.check(_lib.load().twr_envs_set_state(self._h, _lib.ptr(a)))
 
+    def set_cell(self, env: int, cell: int, value: int):
+        _lib.check(_lib.load().twr_envs_set_cell(self._h, int(env), int(cell), int(value)))
+
     def reset(self, env_id_base: int = 0, collect_id: int = 0):
         _lib.check(_lib.load().twr_envs_reset(self._h, int(env_id_base), int(collect_id)))
 
@@ -158,9 +161,10 @@ class Puzzle(PyBaseEnv):
         return self.get_state()[y * self._spec.width + x]
 
     def set_position(self, x: int, y: int, val: int) -> None:
-        # envs/puzzle.rs:71-73 pokes one cell without touching zero_location/depth; the device state
-        # keeps the blank index packed with the board, so this debug helper is not offered.
-        raise NotImplementedError("Puzzle.set_position is not supported on the device path; use set_state")
+        # envs/puzzle.rs:71-73: pokes one cell, zero_location and depth untouched (twr_envs_set_cell)
+        if not (0 <= int(x) < self._spec.width and 0 <= int(y) < self._spec.height):
+            raise IndexError("index out of bounds")                # the reference panics on state[y*width + x]
+        self._b().set_cell(0, int(y) * self._spec.width + int(x), int(val))
 
     def display(self) -> None:
         st, w = self.get_state(), self._spec.width

@@ -452,15 +452,17 @@ def test_collect_full_size_properties(eng):
     assert rep["records"] > 40
 
 
-def test_collect_host_pipelined_matches_plain(eng, monkeypatch):
-    """twr_ppo_collect_host splits large collects into sub-batches whose D2H overlaps the next rollout; the
-    host buffers must hold exactly what the plain collect + to_host path produces."""
+@pytest.mark.parametrize("twists", [False, True])
+def test_collect_host_pipelined_matches_plain(eng, monkeypatch, twists):
+    """twr_ppo_collect_host splits large collects into sub-batches whose D2H overlaps the next rollout, and moves action /
+    twist index / reward as one packed byte (advantages not at all) that host threads expand; the host buffers must hold
+    exactly what the plain collect + to_host path produces."""
     import ctypes as C
     import twisterl_b200 as tw
     from parity import make_policies
     from twisterl_b200 import _lib, collector as twc
     _, sd = trained15()
-    pol, _ = make_policies(sd, 256)
+    pol, _ = make_policies(sd, 256, *(transpose_twists(4) if twists else ((), ())))
     env = tw.env.Puzzle(4, 4, 12, 2, 256)
     E = 1000
     col = tw.collector.PPOCollector(E, 0.995, 0.995, 32, engine=eng)
@@ -490,6 +492,8 @@ def test_collect_host_pipelined_matches_plain(eng, monkeypatch):
         assert np.array_equal(arr["rewards"][:R], ref.rewards_array) and np.array_equal(arr["perms"][:R], ref.perms_array)
         assert np.array_equal(arr["advs"][:R], ref.additional_array("advs"))
         assert np.array_equal(arr["rets"][:R], ref.additional_array("rets"))
+    assert set(np.unique(ref.perms_array)) == ({0, 1} if twists else {-1})
+    assert len(set(np.unique(ref.rewards_array))) >= 2            # step reward and solved (and, for some seeds, out-of-budget) all cross as codes
 
 
 @pytest.mark.parametrize("E,difficulty,chunk,trained", [(65536, 128, None, False), (60000, 6, "8", True), (57100, 20, "5", False),

@@ -11,7 +11,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 extern std::atomic<long long> g_twr_launches;
@@ -105,7 +107,8 @@ struct twr_engine {
     }
     int32_t* bal_flags = nullptr;   // hand-off counters of the balanced pair-kernel schedule (one per CTA pair)
     int bal_delta = 3;
-    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+#define TWR_MAX_SUBBATCH 64
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[TWR_MAX_SUBBATCH] = {};
     unsigned long long* h_stats = nullptr;   // pinned
     bool has_last = false;
     twr_collected last{};
@@ -212,10 +215,8 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
     if (ce2 == cudaSuccess) ce2 = cudaEventCreate(&e->ev_t1);
     if (ce2 == cudaSuccess) ce2 = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
     if (ce2 == cudaSuccess) ce2 = cudaMalloc(reinterpret_cast<void**>(&e->bal_flags), 1024 * sizeof(int32_t));
-    for (int i = 0; i < 2 && ce2 == cudaSuccess; ++i) {
-        ce2 = cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
-        if (ce2 == cudaSuccess) ce2 = cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming);
-    }
+    for (int i = 0; i < 2 && ce2 == cudaSuccess; ++i) ce2 = cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
+    for (int i = 0; i < TWR_MAX_SUBBATCH && ce2 == cudaSuccess; ++i) ce2 = cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming);
     if (ce2 == cudaSuccess) ce2 = cudaHostAlloc(reinterpret_cast<void**>(&e->h_stats), 8 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (ce2 != cudaSuccess) {
         const std::string msg = std::string("twr_engine_create: ") + cudaGetErrorString(ce2);
@@ -248,7 +249,8 @@ void twr_engine_destroy(twr_engine* e) {
     free_collect_buffers(e);
     for (auto ev : e->ev) cudaEventDestroy(ev);
     dev_free(e->ep_len_id);
-    for (int i = 0; i < 2; ++i) { if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]); }
+    for (int i = 0; i < 2; ++i) if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+    for (int i = 0; i < TWR_MAX_SUBBATCH; ++i) if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->bal_flags) cudaFree(e->bal_flags);
     if (e->h_stats) cudaFreeHost(e->h_stats);
@@ -1111,8 +1113,43 @@ int twr_collected_to_host(twr_engine* e, const twr_host_buffers* dst) {
     return TWR_OK;
 }
 
-// End-to-end collect with host buffers.  Large collects are split into sub-batches of consecutive local
-// episodes so that the D2H copy of sub-batch k (copy stream) overlaps the rollout of sub-batch k+1.
+// End-to-end collect with host buffers.  Large collects are split into sub-batches of consecutive local episodes so
+// that the D2H copy of sub-batch k (copy stream) overlaps the rollout of sub-batch k+1.  For Puzzle envs the copy is
+// 41 instead of 50 bytes per record: action, twist index and the three-valued reward cross PCIe as ONE byte and the
+// advantages not at all (advs = rets - values, the very f32 subtraction of collector/ppo.rs:87-91); host threads
+// rebuild the caller's rewards / advs / actions / perms arrays per sub-batch while later sub-batches roll out.
+static std::vector<int64_t> host_collect_parts(twr_engine* e, int64_t num_episodes) {
+    std::vector<int64_t> parts;
+    if (const char* ps = getenv("TWISTERL_B200_E2E_PARTS")) {         // explicit sizes "a,b,c" (must sum to num_episodes)
+        int64_t sum = 0;
+        for (const char* q = ps; *q;) { char* end; const long long v = strtoll(q, &end, 10); if (end == q || v <= 0) break; parts.push_back(v); sum += v; q = *end ? end + 1 : end; }
+        if (sum == num_episodes) return parts;
+        parts.clear();
+    }
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+    const int64_t round = (int64_t)(sms / 2) * 256;      // envs the pair kernel works on at once
+    if (const char* sp = getenv("TWISTERL_B200_E2E_SPLIT")) {          // equal split into this many sub-batches
+        int split = atoi(sp);
+        if (split < 1) split = 1;
+        if (split > 64) split = 64;
+        if (split > num_episodes) split = (int)num_episodes;
+        const int64_t Bsub = (num_episodes + split - 1) / split;
+        for (int64_t lo = 0; lo < num_episodes; lo += Bsub) parts.push_back(lo + Bsub <= num_episodes ? Bsub : num_episodes - lo);
+        return parts;
+    }
+    if (num_episodes < 32768 || e->precision == TWR_PREC_FP32 || round <= 0) { parts.push_back(num_episodes); return parts; }
+    // The call is bound by whichever is longer, the rollouts plus the LAST copy or the FIRST rollout plus the copies, so
+    // both ends are short: sub-batches of two kernel rounds in the middle (the pair kernel's most efficient shape), one
+    // round first and the remainder (<= 2 rounds, cut on a round boundary) last.
+    int64_t rem = num_episodes;
+    parts.push_back(round); rem -= round;
+    while (rem > 3 * round) { parts.push_back(2 * round); rem -= 2 * round; }
+    if (rem > 2 * round) { const int64_t a = ((rem / 2 + round - 1) / round) * round; parts.push_back(a); rem -= a; }
+    if (rem > 0) parts.push_back(rem);
+    return parts;
+}
+
 int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p, const twr_policy_desc* desc,
                          int64_t num_episodes, float gamma, float lambda, const twr_host_buffers* dst, twr_collected* out) {
     if (!e || !p || !dst || !out) return fail(TWR_ERR_INVALID, "NULL argument");
@@ -1123,42 +1160,19 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
     const bool u8 = !dst->obs && dst->obs_u8;
     if (u8 && plan.dev.obs_size > 256) return fail(TWR_ERR_INVALID, "obs_u8 needs obs_size <= 256");
     CU_TRY(cudaSetDevice(e->device));
-    // Sub-batch sizes.  The rollout kernel works in rounds of (#SM pairs x 256) envs, so the first sub-batch is a whole
-    // number of rounds (at least half of the episodes) and the remainder -- whose copy is the exposed tail -- is smaller.
-    std::vector<int64_t> parts;
-    if (const char* ps = getenv("TWISTERL_B200_E2E_PARTS")) {         // explicit sizes "a,b,c" (must sum to num_episodes)
-        int64_t sum = 0;
-        for (const char* q = ps; *q;) { char* end; const long long v = strtoll(q, &end, 10); if (end == q || v <= 0) break; parts.push_back(v); sum += v; q = *end ? end + 1 : end; }
-        if (sum != num_episodes) parts.clear();
-    }
-    if (parts.empty()) {
-        int split = num_episodes >= 32768 ? 2 : 1;
-        if (const char* sp = getenv("TWISTERL_B200_E2E_SPLIT")) { const int v = atoi(sp); if (v >= 1 && v <= 64) split = v; }
-        if (split > num_episodes) split = (int)num_episodes;
-        int sms = 0;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
-        const int64_t round = (int64_t)(sms / 2) * 256;
-        if (split == 2 && e->precision == TWR_PREC_F16X2 && round > 0 && !getenv("TWISTERL_B200_E2E_SPLIT")) {
-            // large collects: sub-batches of two rounds (the kernel's most efficient shape) so that only the copy of a
-            // small last sub-batch stays exposed; the last <= 4 rounds are halved on a round boundary
-            int64_t rem = num_episodes;
-            while (rem >= 4 * round) { parts.push_back(2 * round); rem -= 2 * round; }
-            const int64_t first = ((rem / 2 + round - 1) / round) * round;
-            if (first < rem) { parts.push_back(first); parts.push_back(rem - first); }
-            else parts.push_back(rem);
-        }
-        if (parts.empty()) {
-            const int64_t Bsub = (num_episodes + split - 1) / split;
-            for (int64_t lo = 0; lo < num_episodes; lo += Bsub) parts.push_back(lo + Bsub <= num_episodes ? Bsub : num_episodes - lo);
-        }
-    }
+    const std::vector<int64_t> parts = host_collect_parts(e, num_episodes);
     if (parts.size() == 1 && !u8) {
         if ((rc = twr_ppo_collect(e, spec, p, num_episodes, gamma, lambda, out))) return rc;
         return twr_collected_to_host(e, dst);
     }
+    if (parts.size() > TWR_MAX_SUBBATCH) return fail(TWR_ERR_INVALID, "too many sub-batches");
     int64_t Bmax = 0;
     for (int64_t v : parts) Bmax = v > Bmax ? v : Bmax;
     if ((rc = ensure_collect_buffers(e, Bmax, plan.T, plan.env.N, num_episodes))) return rc;
+    // one byte for action / reward / twist when they fit: Puzzle rewards (three values) and at most 14 twists
+    const bool pack = plan.env.kind == TWR_ENV_PUZZLE && plan.dev.n_perms <= 14 && dst->actions && (!dst->advs || (dst->rets && dst->values)) &&
+                      !getenv("TWISTERL_B200_E2E_NOPACK");
+    const float reward_of_code[4] = {-0.5f / (float)plan.env.max_depth, -0.5f, 1.0f, 0.0f};     // puzzle.rs:171-177
     e->has_last = false;
     const uint32_t cid = e->collect_id++;
     const uint32_t base = (uint32_t)((int64_t)e->rank * num_episodes);
@@ -1168,33 +1182,79 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
     const bool timing = e->timing;
     e->timing = false;                                  // per-forward events are only kept for the device-resident path
     e->buf.obs_u8 = u8 ? 1 : 0;
-    auto bail = [&](int code) { e->timing = timing; e->buf.obs_u8 = 0; return code; };
-    for (size_t k = 0; k < parts.size(); ++k) {
-        const int64_t B = parts[k];
-        const int which = (int)(k & 1);
-        if (k >= 2) CU_TRY(cudaStreamWaitEvent(e->stream, e->ev_copied[which], 0));   // output set free again
-        // global local index = lo + i; episode id = (lo + i + E - 1) mod E
-        const EnvIds ids{base, (uint32_t)((lo + num_episodes - 1) % num_episodes), (uint32_t)num_episodes};
-        if ((rc = enqueue_collect(e, plan.env, plan.dev, B, ids, cid, gamma, lambda, which, &n_fwd))) return bail(rc);
-        CU_TRY(cudaMemcpyAsync(e->h_stats, e->buf.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, e->stream));
-        CU_TRY(cudaEventRecord(e->ev_done[which], e->stream));
-        CU_TRY(cudaStreamSynchronize(e->stream));       // record count of this sub-batch -> host offsets
-        e->note_survival();
-        const size_t R = (size_t)e->h_stats[1];
-        successes += (int64_t)e->h_stats[0];
-        double rs; memcpy(&rs, &e->h_stats[2], sizeof(double)); reward_sum += rs;
-        if (at + (int64_t)R > dst->capacity) return bail(fail(TWR_ERR_INVALID, "host buffers too small for the collected records"));
-        CU_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_done[which], 0));
-        if ((rc = copy_out(e, e->copy_stream, dst, at, R, plan.env.N, plan.dev.A))) return bail(rc);
-        CU_TRY(cudaEventRecord(e->ev_copied[which], e->copy_stream));
-        at += (int64_t)R;
-        lo += B;
-    }
-    e->buf.obs_u8 = 0;
+    e->buf.pack_misc = pack ? 1 : 0;
+    std::vector<std::thread> stages;                    // one per sub-batch: waits for its copy, then rebuilds the packed fields
+    int hw = (int)std::thread::hardware_concurrency();
+    int workers = hw / (2 * (e->world > 0 ? e->world : 1));
+    if (const char* w = getenv("TWISTERL_B200_E2E_THREADS")) workers = atoi(w);
+    workers = workers < 1 ? 1 : (workers > 16 ? 16 : workers);
+    auto body = [&]() -> int {
+        for (size_t k = 0; k < parts.size(); ++k) {
+            const int64_t B = parts[k];
+            const int which = (int)(k & 1);
+            if (k >= 2) CU_TRY(cudaStreamWaitEvent(e->stream, e->ev_copied[k - 2], 0));   // output set `which` free again
+            // global local index = lo + i; episode id = (lo + i + E - 1) mod E
+            const EnvIds ids{base, (uint32_t)((lo + num_episodes - 1) % num_episodes), (uint32_t)num_episodes};
+            int r2 = enqueue_collect(e, plan.env, plan.dev, B, ids, cid, gamma, lambda, which, &n_fwd);
+            if (r2) return r2;
+            CU_TRY(cudaMemcpyAsync(e->h_stats, e->buf.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, e->stream));
+            CU_TRY(cudaEventRecord(e->ev_done[which], e->stream));
+            CU_TRY(cudaStreamSynchronize(e->stream));       // record count of this sub-batch -> host offsets
+            FWD_CHECK(e);
+            e->note_survival();
+            const size_t R = (size_t)e->h_stats[1];
+            successes += (int64_t)e->h_stats[0];
+            double rs; memcpy(&rs, &e->h_stats[2], sizeof(double)); reward_sum += rs;
+            if (at + (int64_t)R > dst->capacity) return fail(TWR_ERR_INVALID, "host buffers too small for the collected records");
+            CU_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_done[which], 0));
+            if (pack) {
+                twr_host_buffers d2 = *dst;
+                d2.rewards = nullptr; d2.advs = nullptr; d2.perms = nullptr;      // rebuilt on the host from the packed byte in `actions`
+                if ((r2 = copy_out(e, e->copy_stream, &d2, at, R, plan.env.N, plan.dev.A))) return r2;
+            } else if ((r2 = copy_out(e, e->copy_stream, dst, at, R, plan.env.N, plan.dev.A))) return r2;
+            CU_TRY(cudaEventRecord(e->ev_copied[k], e->copy_stream));
+            if (pack) {
+                cudaEvent_t ev = e->ev_copied[k];
+                const int dev_id = e->device;
+                const int64_t at0 = at;
+                const twr_host_buffers d = *dst;
+                const float* rtab = reward_of_code;
+                stages.emplace_back([ev, dev_id, at0, R, d, rtab, workers]() {
+                    cudaSetDevice(dev_id);
+                    cudaEventSynchronize(ev);
+                    auto span = [&](int64_t a, int64_t b) {
+                        for (int64_t i = a; i < b; ++i) {
+                            const uint32_t m = d.actions[i];
+                            d.actions[i] = (uint8_t)(m & 3u);
+                            if (d.perms) d.perms[i] = (int8_t)((int)(m >> 4) - 1);
+                            if (d.rewards) d.rewards[i] = rtab[(m >> 2) & 3u];
+                        }
+                        if (d.advs && d.rets && d.values)
+                            for (int64_t i = a; i < b; ++i) d.advs[i] = d.rets[i] - d.values[i];
+                    };
+                    std::vector<std::thread> ws;
+                    const int64_t per = ((int64_t)R + workers - 1) / workers;
+                    for (int w = 1; w < workers; ++w) {
+                        const int64_t a = at0 + w * per, b = std::min<int64_t>(at0 + (int64_t)R, a + per);
+                        if (a < b) ws.emplace_back(span, a, b);
+                    }
+                    span(at0, std::min<int64_t>(at0 + (int64_t)R, at0 + per));
+                    for (auto& t : ws) t.join();
+                });
+            }
+            at += (int64_t)R;
+            lo += B;
+        }
+        if (dst->ep_len)
+            CU_TRY(cudaMemcpyAsync(dst->ep_len, e->ep_len_id, sizeof(int32_t) * (size_t)num_episodes, cudaMemcpyDeviceToHost, e->copy_stream));
+        CU_TRY(cudaStreamSynchronize(e->copy_stream));
+        return TWR_OK;
+    };
+    rc = body();
+    for (auto& t : stages) t.join();                    // every exit path: workers done, engine flags restored
+    e->buf.obs_u8 = 0; e->buf.pack_misc = 0;
     e->timing = timing;
-    if (dst->ep_len)
-        CU_TRY(cudaMemcpyAsync(dst->ep_len, e->ep_len_id, sizeof(int32_t) * (size_t)num_episodes, cudaMemcpyDeviceToHost, e->copy_stream));
-    CU_TRY(cudaStreamSynchronize(e->copy_stream));
+    if (rc) { cudaStreamSynchronize(e->stream); cudaStreamSynchronize(e->copy_stream); return rc; }
     twr_collected c{};
     c.n_records = at; c.num_episodes = num_episodes; c.n_cells = plan.env.N; c.num_actions = plan.dev.A;
     c.successes = successes; c.reward_sum = reward_sum;    // device pointers stay NULL: the data now lives in `dst`

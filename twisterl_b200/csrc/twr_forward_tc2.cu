@@ -243,6 +243,11 @@ __device__ __forceinline__ void wait_handoff(const int32_t* flag, int target) {
     __syncwarp();
 }
 
+// HT = common width (GEMM2 N): 256 or 128.  TERMS = the split-operand terms as a compile-time constant (7 = f16x2,
+// 3 = f16x2w16) or -1 = taken from ForwardArgs::tc_terms at run time (precision ladder / debugging).  Both are template
+// parameters because ONE thread issues every MMA: its loops must unroll to straight-line descriptor arithmetic, or the
+// issue rate, not the tensor pipe, bounds the kernel (measured: runtime trip counts cost 13 % of the whole collect).
+template <int HT, int TERMS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -275,14 +280,15 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     // twist tables in shared memory when they fit (obs_size <= 256 makes every entry a byte): the one-hot build looks
     // up 16 of them per env and step
     const bool operm_smem = p.n_perms > 0 && p.obs_size <= 256 && p.n_perms * p.obs_size <= OPERM_MAX;
-    const int NC = t.NC, NKB1 = t.NKB1, H = t.H;
+    const int NC = t.NC, NKB1 = t.NKB1;
+    constexpr int H = HT;
     // Split-operand terms of this launch (ForwardArgs::tc_terms; 0 = all): GEMM1 always has one-hot x table_hi and GEMM2
     // h1_hi x W_hi; bit 0 adds one-hot x table_lo, bit 1 h1_lo x W_hi, bit 2 h1_hi x W_lo.  Skipped terms are neither
     // streamed nor issued.
-    const int terms = a.tc_terms ? a.tc_terms : 7;
+    const int terms = TERMS >= 0 ? TERMS : (a.tc_terms ? a.tc_terms : 7);
     const bool g1_lo = (terms & 1) != 0, g2_alo = (terms & 2) != 0, g2_wlo = (terms & 4) != 0;
-    const uint32_t idesc2 = H == 256 ? IDESC_256x256 : IDESC_256x128;   // GEMM2: N = H
-    const int g2_units = H == 256 ? 4 : 2;                               // ring slots of one chunk's GEMM2 (see k_tc2_pack)
+    constexpr uint32_t idesc2 = H == 256 ? IDESC_256x256 : IDESC_256x128;   // GEMM2: N = H
+    constexpr int g2_units = H == 256 ? 4 : 2;                               // ring slots of one chunk's GEMM2 (see k_tc2_pack)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSLOTS; ++i) { mbar_init(bar(B_FULL0 + i), 1); mbar_init(bar(B_EMPTY0 + i), 1); }
@@ -376,7 +382,9 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     const uint32_t d = tmem + D1_COL;
                     for (int kb = 0; kb < NKB1 - 1; ++kb) {
                         const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
-                        for (int part = 0; part < (g1_lo ? 2 : 1); ++part) {
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {
+                            if (part && !g1_lo) break;
                             const long long w0 = w_slot;
                             const uint32_t slot = wait_slot();
                             w_slot_g1 += w_slot - w0;
@@ -435,6 +443,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     const uint32_t d = tmem + D2_COL;
                     // unit u = one ring slot: H = 256 -> (kb, part) = (u >> 1, u & 1), 4 k-steps of 16 features;
                     // H = 128 -> part = u, both k-blocks (two 64-row sub-tiles), 8 k-steps
+#pragma unroll
                     for (int u = 0; u < g2_units; ++u) {
                         const int part = u & 1;
                         if (part && !g2_wlo) continue;
@@ -442,7 +451,8 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                         const uint64_t bd = make_desc(sbase + SM_RING + slot * TILE_BYTES);
                         const bool first = (j == 0 && u == 0);
                         if (!(a.dbg_flags & 4)) {
-                            const int nks = H == 256 ? 4 : 8;
+                            constexpr int nks = H == 256 ? 4 : 8;
+#pragma unroll
                             for (int ks = 0; ks < nks; ++ks) {
                                 const uint32_t sidx = H == 256 ? (uint32_t)((u >> 1) * 4 + ks) : (uint32_t)ks;
                                 const uint32_t ah = a_base + 32u * (sidx >> 1) + 8u * (sidx & 1u);
@@ -837,7 +847,9 @@ bool forward_tc2_prepare(const PolicyDev& p, const void* pack) {
     CUtensorMap tmap;
     if (!get_tmap(*d, pack, forward_tc2_pack_bytes(p), &tmap)) return false;
     if (!d->attr_set) {
-        if (cudaFuncSetAttribute(k_forward_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) != cudaSuccess) return false;
+        for (auto k : {k_forward_tc2<256, 7>, k_forward_tc2<256, 3>, k_forward_tc2<256, -1>, k_forward_tc2<128, 7>, k_forward_tc2<128, 3>,
+                       k_forward_tc2<128, -1>})
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) != cudaSuccess) return false;
         d->attr_set = true;
     }
     if (d->max_clusters < 0) {
@@ -850,7 +862,7 @@ bool forward_tc2_prepare(const PolicyDev& p, const void* pack) {
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int nc = 0;
-        d->max_clusters = cudaOccupancyMaxActiveClusters(&nc, k_forward_tc2, &cfg) == cudaSuccess ? nc : 0;
+        d->max_clusters = cudaOccupancyMaxActiveClusters(&nc, k_forward_tc2<256, 7>, &cfg) == cudaSuccess ? nc : 0;
         cudaGetLastError();
     }
     return true;
@@ -879,7 +891,11 @@ bool launch_forward_tc2(cudaStream_t st, const PolicyDev& p, const ForwardArgs& 
     const int grid = (n_groups < max_pairs ? n_groups : max_pairs) * 2;
     ForwardArgs args = a;
     if (a.bal_flags && max_clusters < grid / 2) { args.bal_flags = nullptr; args.bal_delta = 0; }
-    k_forward_tc2<<<grid, NTHREADS, SM_TOTAL, st>>>(p, args, make_params2(p), tmap);
+    const int terms = a.tc_terms ? (a.tc_terms & 7) : 7;
+    const Tc2Params t = make_params2(p);
+    auto go = [&](auto kern) { kern<<<grid, NTHREADS, SM_TOTAL, st>>>(p, args, t, tmap); };
+    if (p.H == 256) { if (terms == 7) go(k_forward_tc2<256, 7>); else if (terms == 3) go(k_forward_tc2<256, 3>); else go(k_forward_tc2<256, -1>); }
+    else            { if (terms == 7) go(k_forward_tc2<128, 7>); else if (terms == 3) go(k_forward_tc2<128, 3>); else go(k_forward_tc2<128, -1>); }
     g_twr_launches.fetch_add(1, std::memory_order_relaxed);
     return true;
 }

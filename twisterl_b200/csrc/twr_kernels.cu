@@ -409,9 +409,15 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
         const long long r0 = offs[ey] + t0;
         const int x = threadIdx.x;
         if (x < nt) {
-            b.out_values[r0 + x] = tl.f[0][x][ey]; b.out_rewards[r0 + x] = tl.f[1][x][ey];
-            b.out_advs[r0 + x] = tl.f[2][x][ey]; b.out_rets[r0 + x] = tl.f[3][x][ey];
-            b.out_actions[r0 + x] = tl.b[0][x][ey]; b.out_perms[r0 + x] = (int8_t)tl.b[1][x][ey];
+            b.out_values[r0 + x] = tl.f[0][x][ey]; b.out_rets[r0 + x] = tl.f[3][x][ey];
+            if (b.pack_misc) {
+                const float rw = tl.f[1][x][ey];
+                const uint32_t rcode = rw == 1.0f ? 2u : rw == -0.5f ? 1u : 0u;
+                b.out_actions[r0 + x] = (uint8_t)((uint32_t)tl.b[0][x][ey] | (rcode << 2) | ((uint32_t)((int8_t)tl.b[1][x][ey] + 1) << 4));
+            } else {
+                b.out_rewards[r0 + x] = tl.f[1][x][ey]; b.out_advs[r0 + x] = tl.f[2][x][ey];
+                b.out_actions[r0 + x] = tl.b[0][x][ey]; b.out_perms[r0 + x] = (int8_t)tl.b[1][x][ey];
+            }
         }
         // logits: float4 per record -> [record][A] floats
         if (A == 4) {

@@ -52,6 +52,9 @@ struct CollectBuffers {
     int32_t* ep_len_id;   // [total episodes] episode length by episode id (filled by k_episode_offsets)
     int64_t out_base;     // records of earlier sub-batches (pipelined host collect)
     int obs_u8;           // compaction writes one byte per observation index (twr_host_buffers.obs_u8)
+    int pack_misc;        // compaction writes ONE byte per record into out_actions -- action | reward code << 2 | (perm + 1) << 4 --
+                          // and skips out_perms / out_rewards / out_advs: the pipelined host collect rebuilds those on the host
+                          // (Puzzle rewards take three values, puzzle.rs:171-177; advs = rets - values, ppo.rs:87-91)
     unsigned long long* stats;  // [0] successes, [1] total records ; double at [2] = reward sum
     // compacted outputs
     uint16_t* out_obs; float* out_logits; float* out_values; float* out_rewards;

@@ -281,6 +281,29 @@ int  twr_az_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p
 int  twr_mcts_probs(twr_engine* e, const twr_policy* p, twr_envs* v, int32_t n_sims, float C, int32_t max_expand_depth,
                     uint32_t env_id_base, uint32_t collect_id, int32_t t, float* probs, int32_t* visits);
 
+/* ------------------------------------------------------------ multi-GPU --- */
+/* One engine per GPU (twr_engine_cfg.rank / world); envs shard by rank with no data-path collective (the reference maps
+ * episodes over rayon threads, rust/src/collector/ppo.rs:119-123).  NCCL carries the two per-iteration exchanges:
+ * the trainer rank's weights to every engine (replaces rebuilding nn.Policy on every worker,
+ * src/twisterl/rl/algorithm.py:91-93,112) and the sum of the collect statistics the trainer logs (:124-141).
+ * NCCL is bound at run time (libnccl.so.2 or $TWISTERL_B200_NCCL_LIB); without it these return TWR_ERR_UNSUPPORTED. */
+#define TWR_COMM_ID_BYTES 128   /* sizeof(ncclUniqueId) */
+#define TWR_COMM_MAX_STATS 16
+typedef enum { TWR_REDUCE_SUM = 0, TWR_REDUCE_MAX = 1 } twr_reduce_op;
+/* NCCL version code (e.g. 22809), 0 when NCCL cannot be loaded */
+int  twr_comm_version(void);
+/* rank 0: creates the id every rank passes to twr_comm_init (the host distributes the bytes: file, env, MPI, TCP store) */
+int  twr_comm_unique_id(uint8_t* id /* [TWR_COMM_ID_BYTES] */);
+/* collective over the `world` engines of the job (ncclCommInitRank with this engine's rank) */
+int  twr_comm_init(twr_engine* e, const uint8_t* id);
+void twr_comm_destroy(twr_engine* e);
+/* ncclBroadcast of rank `root`'s fp32 parameter blob into policy `p` of every engine (same shapes everywhere), on the
+ * engine stream, then the in-place operand refresh of twr_policy_update_from_device.  world == 1: refresh only. */
+int  twr_broadcast_weights(twr_engine* e, twr_policy* p, int32_t root);
+/* in-place all-reduce of n <= TWR_COMM_MAX_STATS host doubles (episodes, successes, reward sum, records, ...);
+ * returns after the reduced values are in `stats`.  world == 1: no-op. */
+int  twr_allreduce_stats(twr_engine* e, double* stats, int32_t n, int32_t op /* twr_reduce_op */);
+
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for the e2e path */
 int  twr_host_alloc(void** ptr, int64_t bytes);
 void twr_host_free(void* ptr);

@@ -16,15 +16,17 @@ def _free_port():
 
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
     from twisterl_b200 import dist as twd
+    comm = twd.Comm()                                        # no engine: torch.distributed (gloo) stands in for NCCL
+    assert comm.backend == "gloo" and (comm.rank, comm.world) == (rank, world)
     blob = torch.full((1000,), float(rank + 1))
-    twd.broadcast_weights(blob, src=0)
-    stats = twd.allreduce_stats(episodes=10, successes=3 + rank, reward_sum=1.5 * (rank + 1), records=100 + rank)
-    mx = twd.max_over_ranks(float(rank) + 0.25)
+    comm.broadcast_weights(blob, root=0)
+    stats = comm.allreduce_stats(episodes=10, successes=3 + rank, reward_sum=1.5 * (rank + 1), records=100 + rank)
+    mx = comm.max_over_ranks(float(rank) + 0.25)
+    comm.barrier()
     base = twd.env_id_base(rank, 65536)
     q.put((rank, float(blob.sum()), stats, mx, base))
-    dist.destroy_process_group()
+    comm.close()
 
 
 def test_two_rank_plumbing():
@@ -48,7 +50,9 @@ def test_two_rank_plumbing():
 
 def test_single_process_is_a_noop():
     from twisterl_b200 import dist as twd
+    comm = twd.Comm(rank=0, world=1)
     b = torch.arange(4.0)
-    assert twd.broadcast_weights(b) is b
-    assert twd.allreduce_stats(2, 1, 0.5, 7)["records"] == 7
-    assert twd.max_over_ranks(3.0) == 3.0
+    assert comm.broadcast_weights(b) is b
+    assert comm.allreduce_stats(2, 1, 0.5, 7)["records"] == 7
+    assert comm.max_over_ranks(3.0) == 3.0
+    comm.barrier(); comm.close()

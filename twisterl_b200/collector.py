@@ -220,7 +220,8 @@ class AZCollector(PyBaseCollector):
     def engine(self) -> _lib.Engine:
         return self._engine or _lib.default_engine()
 
-    def collect(self, env, policy: Policy) -> CollectedData:
+    def collect_device(self, env, policy: Policy) -> _lib.Collected:
+        """Run the collect and leave the result in device memory (pointers in the returned struct)."""
         if not isinstance(policy, Policy):
             raise TypeError("argument 'policy': expected twisterl.nn.Policy")
         spec = spec_from_env(env)
@@ -228,6 +229,11 @@ class AZCollector(PyBaseCollector):
         c = _lib.Collected()
         _lib.check(_lib.load().twr_az_collect(eng._h, C.byref(spec), policy.device_handle(eng), self.num_episodes,
                                               self.num_mcts_searches, self.C, self.max_expand_depth, C.byref(c)))
+        return c
+
+    def collect(self, env, policy: Policy) -> CollectedData:
+        c = self.collect_device(env, policy)
+        eng = self.engine
         R = int(c.n_records)
         hb, arr, holders = _host_buffers(R, c.n_cells, c.num_actions, int(c.num_episodes), False)
         _lib.check(_lib.load().twr_collected_to_host(eng._h, C.byref(hb)))

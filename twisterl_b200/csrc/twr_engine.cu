@@ -6,6 +6,7 @@
 #include "twr_kernels.cuh"
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cmath>
 #include <cstdlib>
@@ -83,61 +84,7 @@ int horizon_of(const EnvParams& p) {   // max env steps of one episode
 
 }  // namespace
 
-struct twr_engine {
-    int device = 0, precision = 0, rank = 0, world = 1;
-    int tc_terms = 0;            // ForwardArgs::tc_terms of every tensor-core forward of this engine (0 = all split terms)
-    bool launch_error = false;   // a forward launch could not be made since the last check (see FWD_CHECK)
-    uint64_t seed = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    uint32_t collect_id = 0;
-    long long launches0 = 0;
-    // collect buffers: working set + two compacted-output sets (double buffered for the pipelined host collect)
-    CollectBuffers buf{};
-    struct OutSet { uint16_t* obs = nullptr; float* logits = nullptr; float* values = nullptr; float* rewards = nullptr;
-                    float* advs = nullptr; float* rets = nullptr; uint8_t* actions = nullptr; int8_t* perms = nullptr; };
-    OutSet outs[2];
-    int32_t* ep_len_id = nullptr; int64_t cap_E = 0;
-    int64_t cap_B = 0; int cap_T = 0; int64_t cap_R = 0; int cap_cells = 0;
-    cudaStream_t copy_stream = nullptr;
-    std::map<uint64_t, float> survive_half;   // (env, batch) shape -> fraction of envs alive past half the horizon, last collect
-    uint64_t hint_key = 0; int64_t hint_B = 0;
-    void note_survival() {                    // call after h_stats of an enqueue_collect has landed
-        if (hint_B > 0) survive_half[hint_key] = (float)((double)(h_stats[3] & 0xFFFFFFFFull) / (double)hint_B);
-    }
-    int32_t* bal_flags = nullptr;   // hand-off counters of the balanced pair-kernel schedule (one per CTA pair)
-    int bal_delta = 3;
-#define TWR_MAX_SUBBATCH 64
-    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[TWR_MAX_SUBBATCH] = {};
-    unsigned long long* h_stats = nullptr;   // pinned
-    bool has_last = false;
-    twr_collected last{};
-    // timing
-    bool timing = false;
-    std::vector<cudaEvent_t> ev;
-    float last_fwd_ms = 0.f, last_total_ms = 0.f; int64_t last_fwd_launches = 0;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
-};
-
-struct twr_policy {
-    twr_engine* eng = nullptr;
-    PolicyDev dev{};
-    float* d_blob = nullptr;
-    int64_t blob_floats = 0;
-    int32_t* d_obs_perms = nullptr;
-    int32_t* d_act_perms = nullptr;
-    void* tc_pack = nullptr;
-    int64_t off_emb_b = 0;
-    std::vector<int64_t> off_w, off_b;   // blob offsets of every Linear (common..., action_net..., value_net...)
-};
-
-struct twr_envs {
-    twr_engine* eng = nullptr;
-    EnvParams p{};
-    int64_t n = 0;
-    uint4* cells = nullptr;
-    uint32_t* meta = nullptr;
-};
+#include "twr_private.cuh"
 
 template <typename T>
 struct Staging {
@@ -204,6 +151,7 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
     e->device = cfg->device; e->precision = cfg->precision; e->seed = cfg->seed;
     e->rank = cfg->rank; e->world = cfg->world;
     e->tc_terms = cfg->precision == TWR_PREC_F16X2_W16 ? (8 | 1 | 2) : 0;
+    if (const char* f = getenv("TWISTERL_B200_TC_FLAGS")) e->tc_flags = atoi(f);
     if (cfg->stream) {
         e->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
     } else {
@@ -216,7 +164,10 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
     if (ce2 == cudaSuccess) ce2 = cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking);
     if (ce2 == cudaSuccess) ce2 = cudaMalloc(reinterpret_cast<void**>(&e->bal_flags), 1024 * sizeof(int32_t));
     for (int i = 0; i < 2 && ce2 == cudaSuccess; ++i) ce2 = cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming);
-    for (int i = 0; i < TWR_MAX_SUBBATCH && ce2 == cudaSuccess; ++i) ce2 = cudaEventCreateWithFlags(&e->ev_copied[i], cudaEventDisableTiming);
+    for (int i = 0; i < TWR_MAX_SUBBATCH && ce2 == cudaSuccess; ++i) {
+        ce2 = cudaEventCreate(&e->ev_copied[i]);   // timing on: TWISTERL_B200_E2E_TRACE
+        if (ce2 == cudaSuccess) ce2 = cudaEventCreateWithFlags(&e->ev_small[i], cudaEventDisableTiming);
+    }
     if (ce2 == cudaSuccess) ce2 = cudaHostAlloc(reinterpret_cast<void**>(&e->h_stats), 8 * sizeof(unsigned long long), cudaHostAllocDefault);
     if (ce2 != cudaSuccess) {
         const std::string msg = std::string("twr_engine_create: ") + cudaGetErrorString(ce2);
@@ -246,11 +197,15 @@ void twr_engine_destroy(twr_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    twr_comm_destroy(e);
     free_collect_buffers(e);
     for (auto ev : e->ev) cudaEventDestroy(ev);
     dev_free(e->ep_len_id);
     for (int i = 0; i < 2; ++i) if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
-    for (int i = 0; i < TWR_MAX_SUBBATCH; ++i) if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
+    for (int i = 0; i < TWR_MAX_SUBBATCH; ++i) {
+        if (e->ev_copied[i]) cudaEventDestroy(e->ev_copied[i]);
+        if (e->ev_small[i]) cudaEventDestroy(e->ev_small[i]);
+    }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->bal_flags) cudaFree(e->bal_flags);
     if (e->h_stats) cudaFreeHost(e->h_stats);
@@ -670,6 +625,7 @@ static void launch_forward(twr_engine* e, const PolicyDev& dev, const ForwardArg
     else if (dev.tc_pack) {                                       // policies whose shape fits the tensor-core kernel (f16x2 engines)
         ForwardArgs t = a;
         t.tc_terms = e->tc_terms;
+        t.dbg_flags |= e->tc_flags;
         ok = launch_forward_tc(e->stream, dev, t);
     } else ok = launch_forward_fp32(e->stream, dev, a);
     if (!ok) e->launch_error = true;
@@ -1118,6 +1074,26 @@ int twr_collected_to_host(twr_engine* e, const twr_host_buffers* dst) {
 // 41 instead of 50 bytes per record: action, twist index and the three-valued reward cross PCIe as ONE byte and the
 // advantages not at all (advs = rets - values, the very f32 subtraction of collector/ppo.rs:87-91); host threads
 // rebuild the caller's rewards / advs / actions / perms arrays per sub-batch while later sub-batches roll out.
+// Host side of CollectBuffers::pack_misc for records [a, b): `actions` holds action | reward code << 2 | (perm + 1) << 4;
+// blocked so that every loop is a plain element-wise pass the host compiler vectorises.
+static void expand_packed(uint8_t* __restrict__ actions, int8_t* __restrict__ perms, float* __restrict__ rewards, float* __restrict__ advs,
+                          const float* __restrict__ rets, const float* __restrict__ values, float r_step, int64_t a, int64_t b) {
+    constexpr int BK = 512;
+    uint8_t m[BK];
+    for (int64_t i0 = a; i0 < b; i0 += BK) {
+        const int n = (int)std::min<int64_t>(BK, b - i0);
+        memcpy(m, actions + i0, (size_t)n);
+        for (int i = 0; i < n; ++i) actions[i0 + i] = (uint8_t)(m[i] & 3u);
+        if (perms) for (int i = 0; i < n; ++i) perms[i0 + i] = (int8_t)((int)(m[i] >> 4) - 1);
+        if (rewards)
+            for (int i = 0; i < n; ++i) {
+                const int c = (m[i] >> 2) & 3;
+                rewards[i0 + i] = c == 2 ? 1.0f : (c == 1 ? -0.5f : r_step);       // puzzle.rs:171-177
+            }
+        if (advs) for (int i = 0; i < n; ++i) advs[i0 + i] = rets[i0 + i] - values[i0 + i];   // ppo.rs:87-91
+    }
+}
+
 static std::vector<int64_t> host_collect_parts(twr_engine* e, int64_t num_episodes) {
     std::vector<int64_t> parts;
     if (const char* ps = getenv("TWISTERL_B200_E2E_PARTS")) {         // explicit sizes "a,b,c" (must sum to num_episodes)
@@ -1139,13 +1115,11 @@ static std::vector<int64_t> host_collect_parts(twr_engine* e, int64_t num_episod
         return parts;
     }
     if (num_episodes < 32768 || e->precision == TWR_PREC_FP32 || round <= 0) { parts.push_back(num_episodes); return parts; }
-    // The call is bound by whichever is longer, the rollouts plus the LAST copy or the FIRST rollout plus the copies, so
-    // both ends are short: sub-batches of two kernel rounds in the middle (the pair kernel's most efficient shape), one
-    // round first and the remainder (<= 2 rounds, cut on a round boundary) last.
+    // Sub-batches of two kernel rounds -- the smallest shape the pair kernel runs at full rate (one round is a serial
+    // chain of one tile per SM pair: 18 944 envs take 4.9 ms, 37 888 take 6.9 ms) -- and the remainder last, whose copy is
+    // the exposed tail.  Measured on 65 536 envs (scripts/e2e_sweep.py): any finer or front-loaded split is slower.
     int64_t rem = num_episodes;
-    parts.push_back(round); rem -= round;
-    while (rem > 3 * round) { parts.push_back(2 * round); rem -= 2 * round; }
-    if (rem > 2 * round) { const int64_t a = ((rem / 2 + round - 1) / round) * round; parts.push_back(a); rem -= a; }
+    while (rem > 2 * round) { parts.push_back(2 * round); rem -= 2 * round; }
     if (rem > 0) parts.push_back(rem);
     return parts;
 }
@@ -1184,6 +1158,12 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
     e->buf.obs_u8 = u8 ? 1 : 0;
     e->buf.pack_misc = pack ? 1 : 0;
     std::vector<std::thread> stages;                    // one per sub-batch: waits for its copy, then rebuilds the packed fields
+    // TWISTERL_B200_E2E_TRACE=1: host-clock milestones of every sub-batch on stderr (ms since the call started)
+    const bool trace = getenv("TWISTERL_B200_E2E_TRACE") != nullptr;
+    const auto t_call = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count(); };
+    std::vector<double> tr_enq, tr_done, tr_exp(parts.size(), 0.0);
+    std::vector<size_t> tr_R;
     int hw = (int)std::thread::hardware_concurrency();
     int workers = hw / (2 * (e->world > 0 ? e->world : 1));
     if (const char* w = getenv("TWISTERL_B200_E2E_THREADS")) workers = atoi(w);
@@ -1197,40 +1177,42 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
             const EnvIds ids{base, (uint32_t)((lo + num_episodes - 1) % num_episodes), (uint32_t)num_episodes};
             int r2 = enqueue_collect(e, plan.env, plan.dev, B, ids, cid, gamma, lambda, which, &n_fwd);
             if (r2) return r2;
+            if (trace) tr_enq.push_back(now_ms());
             CU_TRY(cudaMemcpyAsync(e->h_stats, e->buf.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, e->stream));
             CU_TRY(cudaEventRecord(e->ev_done[which], e->stream));
             CU_TRY(cudaStreamSynchronize(e->stream));       // record count of this sub-batch -> host offsets
             FWD_CHECK(e);
             e->note_survival();
             const size_t R = (size_t)e->h_stats[1];
+            if (trace) { tr_done.push_back(now_ms()); tr_R.push_back(R); }
             successes += (int64_t)e->h_stats[0];
             double rs; memcpy(&rs, &e->h_stats[2], sizeof(double)); reward_sum += rs;
             if (at + (int64_t)R > dst->capacity) return fail(TWR_ERR_INVALID, "host buffers too small for the collected records");
             CU_TRY(cudaStreamWaitEvent(e->copy_stream, e->ev_done[which], 0));
             if (pack) {
-                twr_host_buffers d2 = *dst;
-                d2.rewards = nullptr; d2.advs = nullptr; d2.perms = nullptr;      // rebuilt on the host from the packed byte in `actions`
+                // the 9 bytes per record the host rebuild reads go first, so that it overlaps the bulk (obs, logits) of the
+                // same sub-batch instead of trailing the last copy
+                twr_host_buffers d2{};
+                d2.values = dst->values; d2.rets = dst->rets; d2.actions = dst->actions;
                 if ((r2 = copy_out(e, e->copy_stream, &d2, at, R, plan.env.N, plan.dev.A))) return r2;
+                CU_TRY(cudaEventRecord(e->ev_small[k], e->copy_stream));
+                twr_host_buffers d3{};
+                d3.obs = dst->obs; d3.obs_u8 = dst->obs_u8; d3.logits = dst->logits;
+                if ((r2 = copy_out(e, e->copy_stream, &d3, at, R, plan.env.N, plan.dev.A))) return r2;
             } else if ((r2 = copy_out(e, e->copy_stream, dst, at, R, plan.env.N, plan.dev.A))) return r2;
             CU_TRY(cudaEventRecord(e->ev_copied[k], e->copy_stream));
             if (pack) {
-                cudaEvent_t ev = e->ev_copied[k];
+                cudaEvent_t ev = e->ev_small[k];
                 const int dev_id = e->device;
                 const int64_t at0 = at;
                 const twr_host_buffers d = *dst;
                 const float* rtab = reward_of_code;
-                stages.emplace_back([ev, dev_id, at0, R, d, rtab, workers]() {
+                double* t_exp = trace ? &tr_exp[k] : nullptr;
+                stages.emplace_back([ev, dev_id, at0, R, d, rtab, workers, t_exp, t_call]() {
                     cudaSetDevice(dev_id);
                     cudaEventSynchronize(ev);
                     auto span = [&](int64_t a, int64_t b) {
-                        for (int64_t i = a; i < b; ++i) {
-                            const uint32_t m = d.actions[i];
-                            d.actions[i] = (uint8_t)(m & 3u);
-                            if (d.perms) d.perms[i] = (int8_t)((int)(m >> 4) - 1);
-                            if (d.rewards) d.rewards[i] = rtab[(m >> 2) & 3u];
-                        }
-                        if (d.advs && d.rets && d.values)
-                            for (int64_t i = a; i < b; ++i) d.advs[i] = d.rets[i] - d.values[i];
+                        expand_packed(d.actions, d.perms, d.rewards, d.advs, d.rets, d.values, rtab[0], a, b);
                     };
                     std::vector<std::thread> ws;
                     const int64_t per = ((int64_t)R + workers - 1) / workers;
@@ -1240,6 +1222,7 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
                     }
                     span(at0, std::min<int64_t>(at0 + (int64_t)R, at0 + per));
                     for (auto& t : ws) t.join();
+                    if (t_exp) *t_exp = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
                 });
             }
             at += (int64_t)R;
@@ -1251,7 +1234,17 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
         return TWR_OK;
     };
     rc = body();
+    const double t_copies = trace ? now_ms() : 0.0;
     for (auto& t : stages) t.join();                    // every exit path: workers done, engine flags restored
+    if (trace && !rc) {
+        for (size_t k = 0; k < tr_done.size(); ++k) {
+            float copy_ms = 0.f;
+            if (k > 0) cudaEventElapsedTime(&copy_ms, e->ev_copied[k - 1], e->ev_copied[k]);
+            fprintf(stderr, "[e2e] part %zu: %lld envs, %zu records | enqueued %.2f  rollout done %.2f  copy end-to-end gap %.2f  expanded %.2f\n",
+                    k, (long long)parts[k], tr_R[k], tr_enq[k], tr_done[k], copy_ms, tr_exp[k]);
+        }
+        fprintf(stderr, "[e2e] copies done %.2f  all done %.2f ms (pack %d, %d workers)\n", t_copies, now_ms(), (int)pack, workers);
+    }
     e->buf.obs_u8 = 0; e->buf.pack_misc = 0;
     e->timing = timing;
     if (rc) { cudaStreamSynchronize(e->stream); cudaStreamSynchronize(e->copy_stream); return rc; }

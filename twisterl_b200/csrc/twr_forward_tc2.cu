@@ -382,21 +382,25 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     const uint32_t d = tmem + D1_COL;
                     for (int kb = 0; kb < NKB1 - 1; ++kb) {
                         const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
+                        const long long w0 = w_slot;
+                        const uint32_t slot_h = wait_slot();
+                        const uint32_t slot_l = g1_lo ? wait_slot() : slot_h;
+                        w_slot_g1 += w_slot - w0;
+                        if (kb == 0) w_slot_first += w_slot - w0;
+                        const uint64_t bh = make_desc(sbase + SM_RING + slot_h * TILE_BYTES);
+                        const uint64_t bl = make_desc(sbase + SM_RING + slot_l * TILE_BYTES);
+                        if (!(a.dbg_flags & 8)) {
+                            // per k-step: table_hi then table_lo against the SAME one-hot A tile -- back-to-back MMAs that share
+                            // their shared-memory A operand issue faster than the (all hi, then all lo) order: +4 % on the whole
+                            // collect; explicit collector::a::fill / lastuse hints on the pair add nothing on top
 #pragma unroll
-                        for (int part = 0; part < 2; ++part) {
-                            if (part && !g1_lo) break;
-                            const long long w0 = w_slot;
-                            const uint32_t slot = wait_slot();
-                            w_slot_g1 += w_slot - w0;
-                            if (kb == 0 && part == 0) w_slot_first += w_slot - w0;
-                            const uint64_t bd = make_desc(sbase + SM_RING + slot * TILE_BYTES);
-                            if (!(a.dbg_flags & 8)) {
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    tc2_mma(d, ad + 2u * ks, bd + 2u * ks, IDESC_256x256, (kb | part | ks) != 0);
+                            for (int ks = 0; ks < 4; ++ks) {
+                                tc2_mma(d, ad + 2u * ks, bh + 2u * ks, IDESC_256x256, (kb | ks) != 0);
+                                if (g1_lo) tc2_mma(d, ad + 2u * ks, bl + 2u * ks, IDESC_256x256, 1u);
                             }
-                            tc2_commit(bar(B_EMPTY0 + slot));
                         }
+                        tc2_commit(bar(B_EMPTY0 + slot_h));
+                        if (g1_lo) tc2_commit(bar(B_EMPTY0 + slot_l));
                     }
                     // last k-block: chunk 2sc is completed first (N = 128 MMAs on rows 0..63 of the hi and the lo slot) and
                     // published, so that its epilogue-1 runs while chunk 2sc+1 (rows 64..127 of the same two slots) finishes --

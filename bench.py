@@ -348,7 +348,7 @@ def run_ours(args, rank, local_rank, world):
 
 
 # dram bytes (read + write) of one steady-state forward launch, from the committed ncu capture of the same command
-TRAFFIC = {("f16x2w16", 65536): None, ("f16x2", 65536): None}
+TRAFFIC = {("f16x2w16", 65536): 3_088_896 + 296_557_568}   # profiles/r2_tc2_summary.md, launch 0 (128 steps x 65 536 envs)
 
 
 # ------------------------------------------------------------- the other BASELINE configs ---

@@ -263,6 +263,11 @@ int  twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p
 int  twr_evaluate(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes,
                   int32_t deterministic, int32_t num_searches, int32_t num_mcts_searches, float C,
                   int32_t max_expand_depth, float* success_rate, float* mean_reward);
+/* same, also returning every episode's best (success, reward) (what rl/evaluate.rs:41-46 sums): [num_episodes] each, or NULL */
+int  twr_evaluate_episodes(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes,
+                           int32_t deterministic, int32_t num_searches, int32_t num_mcts_searches, float C,
+                           int32_t max_expand_depth, float* success_rate, float* mean_reward, float* best_success,
+                           float* best_reward);
 /* collector.solve (rl/solve.rs:73-101) from the state held by the one-env batch `start`: best of
  * num_searches rollouts; writes its action list (actions may be NULL to only query the score). */
 int  twr_solve(twr_engine* e, twr_envs* start, const twr_policy* p, int32_t deterministic, int32_t num_searches,
@@ -303,6 +308,12 @@ int  twr_broadcast_weights(twr_engine* e, twr_policy* p, int32_t root);
 /* in-place all-reduce of n <= TWR_COMM_MAX_STATS host doubles (episodes, successes, reward sum, records, ...);
  * returns after the reduced values are in `stats`.  world == 1: no-op. */
 int  twr_allreduce_stats(twr_engine* e, double* stats, int32_t n, int32_t op /* twr_reduce_op */);
+
+/* Parity API: twr_mcts_probs plus, per env and simulation, the leaf the UCB descent ended on and the node the value was
+ * backed up from, as tree-local node indices in expansion order: trace [n_sims][n][2].  tests/ use it to find the first
+ * simulation in which the device search and the oracle's part ways (and hold that one to a near-tie). */
+int  twr_debug_mcts_trace(twr_engine* e, const twr_policy* p, twr_envs* v, int32_t n_sims, float C, int32_t max_expand_depth,
+                          uint32_t env_id_base, uint32_t collect_id, int32_t t, float* probs, int32_t* visits, int32_t* trace);
 
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for the e2e path */
 int  twr_host_alloc(void** ptr, int64_t bytes);

@@ -345,6 +345,21 @@ def mcts_probs(env: Env, policy: Policy, n_sims, c_puct, max_expand_depth, seed=
     return probs, visits
 
 
+def mcts_trace(env: Env, policy: Policy, n_sims, c_puct, max_expand_depth, seed=0, collect_id=0, stream_id=0, t=0):
+    """mcts_probs plus the per-simulation trace: (probs, visits, leaf[n_sims], backed_up_node[n_sims], margin[n_sims])."""
+    probs = np.zeros(policy.num_actions, dtype=np.float32)
+    visits = np.zeros(policy.num_actions, dtype=np.int32)
+    leaf = np.zeros(max(n_sims, 1), dtype=np.int32); child = np.zeros(max(n_sims, 1), dtype=np.int32)
+    margin = np.zeros(max(n_sims, 1), dtype=np.float32)
+    f = lib().orc_mcts_trace
+    f.argtypes = [C.POINTER(_Env), C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32,
+                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f.restype = None
+    f(C.byref(env._e), policy._h, int(n_sims), float(c_puct), int(max_expand_depth), int(seed), int(collect_id),
+      int(stream_id), int(t), probs.ctypes.data, visits.ctypes.data, leaf.ctypes.data, child.ctypes.data, margin.ctypes.data)
+    return probs, visits, leaf[:n_sims], child[:n_sims], margin[:n_sims]
+
+
 def az_collect(spec: EnvSpec, policy: Policy, num_episodes, n_sims, c_puct, max_expand_depth, seed=0, collect_id=0,
                env_id_base=0) -> dict:
     c = _AzCollected()
@@ -373,3 +388,18 @@ def evaluate(spec: EnvSpec, policy: Policy, num_episodes, deterministic, num_sea
                             int(collect_id), int(reset_base), int(search_base), C.byref(s), C.byref(r), bs.ctypes.data,
                             bt.ctypes.data)
     return float(s.value), float(r.value), bs, bt
+
+
+def evaluate_margins(spec: EnvSpec, policy: Policy, num_episodes, deterministic, num_searches, seed=0, collect_id=0,
+                     reset_base=0, search_base=0, num_mcts_searches=0, c_puct=1.41, max_expand_depth=1):
+    """(per-episode best success, best reward, smallest decision margin) -- see orc_evaluate_margins."""
+    bs = np.zeros(num_episodes, dtype=np.float32); bt = np.zeros(num_episodes, dtype=np.float32)
+    mm = np.zeros(num_episodes, dtype=np.float32)
+    f = lib().orc_evaluate_margins
+    f.argtypes = [C.POINTER(EnvSpec), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_uint64,
+                  C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    f.restype = None
+    f(C.byref(spec), policy._h, int(num_episodes), int(bool(deterministic)), int(num_searches), int(num_mcts_searches),
+      float(c_puct), int(max_expand_depth), int(seed), int(collect_id), int(reset_base), int(search_base),
+      bs.ctypes.data, bt.ctypes.data, mm.ctypes.data)
+    return bs, bt, mm

@@ -644,6 +644,14 @@ void orc_collected_free(orc_collected* c) {
 
 /* ------------------------------------------------------- solve / evaluate --- */
 
+/* Test infrastructure: while a sink is installed, every data-dependent decision of solve / evaluate / MCTS reports how
+ * close it was to going the other way (argmax: best minus second best; weighted draw: distance to the nearest bin edge
+ * as a fraction of the total weight; UCB descent: best minus second-best UCB).  The parity tests use the minimum over an
+ * episode to tell a flipped near-tie from a real difference. */
+static __thread float* g_margin_sink = NULL;
+static void note_margin(float m) { if (g_margin_sink && m < *g_margin_sink) *g_margin_sink = m; }
+static float weighted_margin(const float* w, int n, float u);
+
 void orc_single_solve(orc_env* env, const orc_policy* p, int32_t deterministic, uint64_t seed, uint32_t collect_id,
                       uint32_t stream_id, float* success, float* total, int32_t* actions, int32_t* n_actions) {
     orc_single_solve_mcts(env, p, deterministic, 0, 0.0f, 0, seed, collect_id, stream_id, success, total, actions, n_actions);
@@ -678,6 +686,11 @@ void orc_single_solve_mcts(orc_env* env, const orc_policy* p, int32_t determinis
         int act = 0;
         if (deterministic) {
             act = orc_argmax(probs, na);
+            if (g_margin_sink) {
+                float second = -INFINITY;
+                for (int i = 0; i < na; ++i) if (i != act && probs[i] > second) second = probs[i];
+                if (na > 1) note_margin(probs[act] - second);
+            }
         } else {
             /* nn/policy.rs:153-167: WeightedIndex -- first index whose cumulative weight exceeds the draw */
             float tw = 0.0f;
@@ -687,6 +700,7 @@ void orc_single_solve_mcts(orc_env* env, const orc_policy* p, int32_t determinis
                 uint32_t w[4];
                 orc_philox4x32_10(ctr, key, w);
                 const float chosen = orc_u32_to_unit_f32(w[0]) * tw;
+                if (g_margin_sink) note_margin(weighted_margin(probs, na, orc_u32_to_unit_f32(w[0])));
                 float cum = 0.0f;
                 int last = 0, found = 0;
                 for (int i = 0; i < na; ++i) {
@@ -757,9 +771,26 @@ void orc_evaluate_mcts(const orc_env_spec* spec, const orc_policy* p, int32_t nu
         succ += s1; rew += r1;
         if (best_success) best_success[ep] = s1;
         if (best_total) best_total[ep] = r1;
+        if (g_margin_sink) ++g_margin_sink, *g_margin_sink = INFINITY;      /* next episode's slot (orc_evaluate_margins) */
     }
     *success_rate = succ / (float)num_episodes;
     *mean_reward = rew / (float)num_episodes;
+}
+
+void orc_evaluate_margins(const orc_env_spec* spec, const orc_policy* p, int32_t num_episodes, int32_t deterministic,
+                          int32_t num_searches, int32_t n_mcts, float C, int32_t max_expand_depth, uint64_t seed,
+                          uint32_t collect_id, uint32_t reset_base, uint32_t search_base, float* best_success,
+                          float* best_total, float* min_margin) {
+    /* orc_evaluate_mcts with the smallest decision margin of every episode (all its searches and steps) */
+    float* sink = (float*)malloc(sizeof(float) * (size_t)(num_episodes + 1));
+    float sr, mr;
+    sink[0] = INFINITY;
+    g_margin_sink = sink;
+    orc_evaluate_mcts(spec, p, num_episodes, deterministic, num_searches, n_mcts, C, max_expand_depth, seed, collect_id,
+                      reset_base, search_base, &sr, &mr, best_success, best_total);
+    g_margin_sink = NULL;
+    memcpy(min_margin, sink, sizeof(float) * (size_t)num_episodes);
+    free(sink);
 }
 
 /* ---------------------------------------------------------------- AlphaZero --- */
@@ -808,9 +839,29 @@ static void mcts_expand(mtree* t, int idx, const float* priors, int na) {
     t->nodes[idx].n_children = cnt;
 }
 
-void orc_mcts_probs(const orc_env* env, const orc_policy* p, int32_t n_sims, float C, int32_t max_expand_depth,
-                    uint64_t seed, uint32_t collect_id, uint32_t stream_id, int32_t t_step, float* probs, int32_t* visits) {
-    /* search.rs:104-189 */
+/* distance of a weighted draw from the nearest bin edge, as a fraction of the total weight: a device/host difference
+ * of that size in the priors can move the draw into the neighbouring child */
+static float weighted_margin(const float* w, int n, float u) {
+    float tw = 0.0f, cum = 0.0f, m = INFINITY;
+    for (int i = 0; i < n; ++i) tw += w[i];
+    if (!(tw > 0.0f)) return INFINITY;
+    const float chosen = u * tw;
+    for (int i = 0; i + 1 < n; ++i) {                        /* the last edge (cum == tw) is never crossed: u < 1 */
+        cum += w[i];
+        const float d = fabsf(cum - chosen) / tw;
+        if (d < m) m = d;
+    }
+    return m;
+}
+
+/* search.rs:104-189.  Optional per-simulation trace (test infrastructure): the leaf the UCB descent of simulation s
+ * ended on, the node its value was backed up from (the sampled child, or the leaf itself when it was terminal), and the
+ * smallest decision margin of that simulation -- best minus second-best UCB over the levels of the descent and the
+ * bin-edge distance of the child draw.  Node indices count expansions in order, so two implementations that made the
+ * same decisions so far agree on them. */
+static void mcts_core(const orc_env* env, const orc_policy* p, int32_t n_sims, float C, int32_t max_expand_depth,
+                      uint64_t seed, uint32_t collect_id, uint32_t stream_id, int32_t t_step, float* probs, int32_t* visits,
+                      int32_t* trace_leaf, int32_t* trace_child, float* trace_margin) {
     const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
     const int nc = orc_env_num_cells(env), na = orc_env_num_actions(env);
     const int med = max_expand_depth > 1 ? max_expand_depth : 1;
@@ -827,18 +878,22 @@ void orc_mcts_probs(const orc_env* env, const orc_policy* p, int32_t n_sims, flo
     mcts_expand(&tr, 0, pr, na);
     for (int sim = 0; sim < n_sims; ++sim) {
         int node = 0;
+        float margin = INFINITY;
         while (tr.nodes[node].n_children > 0) {                      /* next(): argmax UCB, strict '>' (search.rs:77-91) */
             const mnode* par = &tr.nodes[node];
-            int best = -1; float best_ucb = -INFINITY;
+            int best = -1; float best_ucb = -INFINITY, second = -INFINITY;
             for (int k = 0; k < par->n_children; ++k) {
                 const mnode* ch = &tr.nodes[par->first_child + k];
                 const float q = ch->visits == 0 ? 0.0f : ch->value_sum / (float)ch->visits;      /* search.rs:29-39 */
                 const float ucb = q + C * (sqrtf((float)par->visits) / ((float)ch->visits + 1.0f)) * ch->prior;
-                if (ucb > best_ucb) { best = par->first_child + k; best_ucb = ucb; }
+                if (ucb > best_ucb) { second = best_ucb; best = par->first_child + k; best_ucb = ucb; }
+                else if (ucb > second) second = ucb;
             }
             if (best < 0) break;
+            if (par->n_children > 1 && best_ucb - second < margin) margin = best_ucb - second;
             node = best;
         }
+        if (trace_leaf) trace_leaf[sim] = node;
         float v = 0.0f;
         for (int d = 0; d < max_expand_depth; ++d) {
             const orc_env* st = &tr.nodes[node].state;
@@ -854,9 +909,15 @@ void orc_mcts_probs(const orc_env* env, const orc_policy* p, int32_t n_sims, flo
             float cp[16];
             const mnode* par = &tr.nodes[node];
             for (int k = 0; k < par->n_children; ++k) cp[k] = tr.nodes[par->first_child + k].prior;
-            node = par->first_child + weighted_index(cp, par->n_children, orc_u32_to_unit_f32(w[0]));   /* next_sample */
+            const float u = orc_u32_to_unit_f32(w[0]);
+            const float wm = weighted_margin(cp, par->n_children, u);
+            if (wm < margin) margin = wm;
+            node = par->first_child + weighted_index(cp, par->n_children, u);   /* next_sample */
             v = nv;
         }
+        if (trace_child) trace_child[sim] = node;
+        if (trace_margin) trace_margin[sim] = margin;
+        note_margin(margin);
         for (int b = node; b >= 0; b = tr.nodes[b].parent) { tr.nodes[b].value_sum += v; tr.nodes[b].visits += 1; }
     }
     float sum = 0.0f;
@@ -870,6 +931,17 @@ void orc_mcts_probs(const orc_env* env, const orc_policy* p, int32_t n_sims, flo
     if (sum > 0.0f) { for (int a = 0; a < na; ++a) probs[a] /= sum; }
     else { for (int a = 0; a < na; ++a) probs[a] = 1.0f / (float)na; }
     free(tr.nodes);
+}
+
+void orc_mcts_probs(const orc_env* env, const orc_policy* p, int32_t n_sims, float C, int32_t max_expand_depth,
+                    uint64_t seed, uint32_t collect_id, uint32_t stream_id, int32_t t_step, float* probs, int32_t* visits) {
+    mcts_core(env, p, n_sims, C, max_expand_depth, seed, collect_id, stream_id, t_step, probs, visits, NULL, NULL, NULL);
+}
+
+void orc_mcts_trace(const orc_env* env, const orc_policy* p, int32_t n_sims, float C, int32_t max_expand_depth,
+                    uint64_t seed, uint32_t collect_id, uint32_t stream_id, int32_t t_step, float* probs, int32_t* visits,
+                    int32_t* trace_leaf, int32_t* trace_child, float* trace_margin) {
+    mcts_core(env, p, n_sims, C, max_expand_depth, seed, collect_id, stream_id, t_step, probs, visits, trace_leaf, trace_child, trace_margin);
 }
 
 int orc_az_collect(const orc_env_spec* spec, const orc_policy* p, int32_t num_episodes, int32_t n_sims, float C,

@@ -161,11 +161,24 @@ void orc_evaluate_mcts(const orc_env_spec* spec, const orc_policy* p, int32_t nu
                        uint32_t collect_id, uint32_t reset_base, uint32_t search_base, float* success_rate,
                        float* mean_reward, float* best_success, float* best_total);
 
+/* the same evaluation plus, per episode, the smallest decision margin met by any of its rollouts (argmax gap, weighted-draw
+ * distance to a bin edge, UCB gap inside MCTS): an episode whose margin is tiny may legitimately differ between two
+ * implementations whose logits differ in the last bits */
+void orc_evaluate_margins(const orc_env_spec* spec, const orc_policy* p, int32_t num_episodes, int32_t deterministic,
+                          int32_t num_searches, int32_t n_mcts, float C, int32_t max_expand_depth, uint64_t seed,
+                          uint32_t collect_id, uint32_t reset_base, uint32_t search_base, float* best_success,
+                          float* best_total, float* min_margin);
+
 /* ---- AlphaZero path (rust/src/rl/search.rs, rust/src/rl/tree.rs, rust/src/collector/az.rs) ---- */
 /* predict_probs_mcts (search.rs:104-189) from `env`; the child draw of simulation `sim`, expansion round d uses
  * Philox (stream_id, (t*(n_sims+1)+sim)*max(1,max_expand_depth)+d, MCTS, collect_id).  visits may be NULL. */
 void orc_mcts_probs(const orc_env* env, const orc_policy* p, int32_t n_sims, float C, int32_t max_expand_depth,
                     uint64_t seed, uint32_t collect_id, uint32_t stream_id, int32_t t, float* probs, int32_t* visits);
+/* same search with a per-simulation trace [n_sims]: the leaf the UCB descent ended on, the node the value was backed up
+ * from, and the simulation's smallest decision margin (UCB best - second best; child-draw distance to a bin edge) */
+void orc_mcts_trace(const orc_env* env, const orc_policy* p, int32_t n_sims, float C, int32_t max_expand_depth,
+                    uint64_t seed, uint32_t collect_id, uint32_t stream_id, int32_t t, float* probs, int32_t* visits,
+                    int32_t* trace_leaf, int32_t* trace_child, float* trace_margin);
 typedef struct {
     int64_t n_records; int32_t num_episodes, n_cells, num_actions;
     int32_t* ep_len; int32_t* obs; float* probs; float* rewards; int32_t* actions; float* remaining_values;

@@ -23,13 +23,33 @@ def eng():
     e.close()
 
 
+# A device search and the oracle's run the same f32 expressions on the same Philox streams; their leaf evaluations differ
+# in the last bits (1e-6-grade on the fp32 path, 1e-5-grade logits on the split-fp16 tensor-core path), which can flip a
+# decision only where the oracle saw a near-tie.  Every search that does not reproduce the oracle's visit counts exactly
+# is therefore traced to the FIRST simulation in which the two part ways, and the oracle's smallest decision margin of
+# that simulation (best minus second-best UCB along the descent, bin-edge distance of the child draw) must be tiny.
+# UCB = q + C*sqrt(N)/(1+n)*prior amplifies a prior difference by up to C*sqrt(N) ~ 20 at these search sizes.
+NEAR_TIE = {"fp32": 2e-4, "f16x2": 2e-3, "f16x2w16": 2e-2}[PRECISION]
+
+
 def _mcts(eng, pol, batch, n_sims, c, med, base, cid, t):
+    """(probs [n][A], visits [n][A], trace [n_sims][n][2]) of twr_debug_mcts_trace."""
     from twisterl_b200 import _lib
     n, A = batch.n, 4
     probs = np.zeros((n, A), np.float32); visits = np.zeros((n, A), np.int32)
-    _lib.check(_lib.load().twr_mcts_probs(eng._h, pol.device_handle(eng), batch._h, n_sims, c, med, base, cid, t,
-                                          _lib.ptr(probs), _lib.ptr(visits)))
-    return probs, visits
+    trace = np.zeros((max(n_sims, 1), n, 2), np.int32)
+    _lib.check(_lib.load().twr_debug_mcts_trace(eng._h, pol.device_handle(eng), batch._h, n_sims, c, med, base, cid, t,
+                                                _lib.ptr(probs), _lib.ptr(visits), _lib.ptr(trace)))
+    return probs, visits, trace[:n_sims]
+
+
+def _first_divergence_margin(dev_trace, oenv, opol, n_sims, c, med, seed, cid, stream_id, t):
+    """Oracle margin of the first simulation whose (leaf, backed-up node) differs from the device's; None if none does."""
+    _, _, leaf, child, margin = orc.mcts_trace(oenv, opol, n_sims, c, med, seed=seed, collect_id=cid, stream_id=stream_id, t=t)
+    for s in range(n_sims):
+        if dev_trace[s][0] != leaf[s] or dev_trace[s][1] != child[s]:
+            return s, float(margin[s])
+    return None
 
 
 @pytest.mark.parametrize("n_sims,med", [(0, 1), (24, 1), (40, 2), (16, 0), (200, 1)])
@@ -44,25 +64,55 @@ def test_mcts_probs_match_oracle(eng, n_sims, med):
     states = scramble_states(rng, n, 4, 4, 12)
     b = EnvBatch(_lib.EnvSpec(0, 4, 4, 5, 2, 256), n, eng)
     b.set_state(states)
-    probs, visits = _mcts(eng, pol, b, n_sims, 1.41, med, 500, 3, 2)
-    same = 0
+    probs, visits, trace = _mcts(eng, pol, b, n_sims, 1.41, med, 500, 3, 2)
+    same, worst = 0, 0.0
     for i in range(n):
         env = orc.Env(orc.puzzle_spec(4, 4, 5, 2, 256)); env.set_state(states[i])
         op, ov = orc.mcts_probs(env, opol, n_sims, 1.41, med, seed=eng.seed, collect_id=3, stream_id=500 + i, t=2)
-        assert visits[i].sum() == ov.sum() == (n_sims if not env.is_final() or n_sims == 0 or True else 0) or env.is_final()
+        assert visits[i].sum() == ov.sum()                       # one backup per simulation on both sides
         assert abs(probs[i].sum() - 1.0) < 1e-5
         masks = env.masks()
         if not env.is_final():
             assert all(visits[i][a] == 0 for a in range(4) if not masks[a])
-        same += int(np.array_equal(visits[i], ov))
-        # a flipped UCB near-tie (ulp-level exp/forward differences) can move a few visits, never the bulk
-        assert np.abs(probs[i] - op).sum() <= 0.35
-    assert same >= 0.9 * n, same
+        if np.array_equal(visits[i], ov):
+            same += 1
+            assert np.allclose(probs[i], op, atol=1e-6)
+            continue
+        div = _first_divergence_margin(trace[:, i], env, opol, n_sims, 1.41, med, eng.seed, 3, 500 + i, 2)
+        assert div is not None, f"env {i}: visit counts differ but every simulation took the oracle's path"
+        assert div[1] < NEAR_TIE, f"env {i}: first divergence at simulation {div[0]} where the oracle's margin was {div[1]}"
+        worst = max(worst, div[1])
+    print(f"[mcts n_sims={n_sims} med={med}] identical {same}/{n}, largest margin at a divergence {worst:.2e}")
+    assert same >= n // 2                                         # near-ties are the exception, not the rule
+
+
+def _weighted_index_f32(w, u):
+    """rand's WeightedIndex as nn/policy.rs:153-167 uses it, in f32 like the device and the oracle."""
+    w = np.asarray(w, np.float32)
+    tw = np.float32(0)
+    for x in w:
+        tw = np.float32(tw + x)
+    if not tw > 0:
+        return 0
+    chosen = np.float32(np.float32(u) * tw)
+    cum, last = np.float32(0), 0
+    for i, x in enumerate(w):
+        if x > 0:
+            cum = np.float32(cum + x); last = i
+            if cum > chosen:
+                return i
+    return last
 
 
 def test_az_collect_structure_and_replay(eng):
+    """Every record of a device AZ collect, replayed through the oracle in merge order: observation, reward and terminal
+    flag bit-exact; the stored MCTS distribution equal to the oracle's or explained by a near-tie at the first divergent
+    simulation; the recorded action the exact WeightedIndex draw of the stored distribution under the shared uniform;
+    remaining_values the f32 reward-to-go of az.rs:93."""
     import twisterl_b200 as tw
     from parity import make_policies
+    from twisterl_b200 import _lib
+    from twisterl_b200.env import EnvBatch
     sd = synth_state_dict(4, 81, 512, 128, 4)
     pol, opol = make_policies(sd, 81)
     ospec = orc.puzzle_spec(3, 3, 3, 2, 256)
@@ -84,23 +134,35 @@ def test_az_collect_structure_and_replay(eng):
         o = orc.Env(ospec); o.reset(seed=eng.seed, env_id=int(ep), collect_id=9)
         tot = np.float32(0); prefix = []
         for t in range(n):
-            assert o.observe() == d.obs_array[off + t].tolist()
-            assert np.float32(o.reward()) == d.step_rewards[off + t]
+            r = off + t
+            assert o.observe() == d.obs_array[r].tolist()
+            assert np.float32(o.reward()) == d.step_rewards[r]
             assert o.is_final() == (t == n - 1)
             masks = o.masks()
-            assert all(probs[off + t][a] == 0 for a in range(4) if not masks[a])
-            assert probs[off + t][int(d.step_actions[off + t])] > 0          # the drawn action has MCTS mass
+            assert all(probs[r][a] == 0 for a in range(4) if not masks[a])
             op, _ = orc.mcts_probs(o, opol, sims, 1.41, 1, seed=eng.seed, collect_id=9, stream_id=int(ep), t=t)
-            match += int(np.allclose(op, probs[off + t], atol=1e-6))
-            prefix.append(tot); tot = np.float32(tot + d.step_rewards[off + t])
-            o.step(int(d.step_actions[off + t]))
+            if np.allclose(op, probs[r], atol=1e-6):
+                match += 1
+            else:
+                # rebuild this state on the device (same reset stream, the recorded actions) and trace the search
+                b = EnvBatch(_lib.EnvSpec(0, 3, 3, 3, 2, 256), 1, eng)
+                b.reset(env_id_base=int(ep), collect_id=9)
+                for a in d.step_actions[off:r]:
+                    b.step([int(a)])
+                assert b.get_state()[0].tolist() == o.get_state()
+                p2, _, trace = _mcts(eng, pol, b, sims, 1.41, 1, int(ep), 9, t)
+                assert np.array_equal(p2[0], probs[r])           # the parity API reruns the collect's search exactly
+                div = _first_divergence_margin(trace[:, 0], o, opol, sims, 1.41, 1, eng.seed, 9, int(ep), t)
+                assert div is not None and div[1] < NEAR_TIE, (int(ep), t, div)
+            w = orc.philox([int(ep), t, 5, 9], [eng.seed & 0xFFFFFFFF, eng.seed >> 32])      # TWR_RNG_AZ_ACT = 5
+            assert _weighted_index_f32(probs[r], orc.u32_to_unit_f32(int(w[0]))) == int(d.step_actions[r])   # az.rs:72
+            prefix.append(tot); tot = np.float32(tot + d.step_rewards[r])
+            o.step(int(d.step_actions[r]))
         want = np.array([np.float32(tot - q) for q in prefix], dtype=np.float32)
         assert np.array_equal(want, d.additional_array("remaining_values")[off:off + n])
         off += n
-    assert match >= 0.9 * R
-    # whole-collect comparison with the oracle collector on the same streams
-    oc = orc.az_collect(ospec, opol, E, sims, 1.41, 1, seed=eng.seed, collect_id=9)
-    assert sum(int(a == b) for a, b in zip(oc["ep_len"], d.ep_len)) >= 0.8 * E
+    print(f"[az collect] {match}/{R} records with the oracle's distribution, the rest explained by near-ties")
+    assert match >= R // 2
 
 
 def test_az_errors_and_trained_policy_solves(eng):

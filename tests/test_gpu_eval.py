@@ -22,15 +22,33 @@ def eng():
     return tw.default_engine()
 
 
-def _evaluate(eng, env, pol, n, det, searches, cid, mcts=0, c_puct=1.41, depth=1):
+# Device and oracle evaluate the same f32 expressions on the same Philox streams; their logits differ in the last bits, so
+# an episode may differ only where one of its decisions was a near-tie in the oracle (argmax gap, weighted-draw distance
+# to a bin edge, UCB gap inside MCTS; orc_evaluate_margins reports the smallest of an episode).
+NEAR_TIE = {"fp32": 2e-4, "f16x2": 2e-3, "f16x2w16": 2e-2}[PRECISION]
+
+
+def _evaluate(eng, env, pol, n, det, searches, cid, mcts=0, c_puct=1.41, depth=1, episodes=False):
     from twisterl_b200 import _lib
     import twisterl_b200 as tw
     spec = tw.env.spec_from_env(env)
     s, r = C.c_float(), C.c_float()
+    bs, bt = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32)
     eng.set_collect_id(cid)
-    _lib.check(_lib.load().twr_evaluate(eng._h, C.byref(spec), pol.device_handle(eng), n, int(det), searches, mcts, c_puct, depth,
-                                        C.byref(s), C.byref(r)))
+    _lib.check(_lib.load().twr_evaluate_episodes(eng._h, C.byref(spec), pol.device_handle(eng), n, int(det), searches, mcts, c_puct,
+                                                 depth, C.byref(s), C.byref(r), _lib.ptr(bs), _lib.ptr(bt)))
+    if episodes:
+        return float(s.value), float(r.value), bs[:n], bt[:n]
     return float(s.value), float(r.value)
+
+
+def _check_episodes(bs, bt, obs, obt, margins, what):
+    """per-episode best (success, reward): equal to the oracle's, or the oracle met a near-tie in that episode"""
+    diff = [i for i in range(len(bs)) if bs[i] != obs[i] or abs(float(bt[i]) - float(obt[i])) > 1e-5]
+    for i in diff:
+        assert margins[i] < NEAR_TIE, f"{what}: episode {i} differs ({bs[i]}, {bt[i]}) vs ({obs[i]}, {obt[i]}) with smallest margin {margins[i]}"
+    print(f"[{what}] {len(bs) - len(diff)}/{len(bs)} episodes identical, {len(diff)} explained by near-ties")
+    assert len(diff) <= len(bs) // 4
 
 
 @pytest.mark.parametrize("det,searches", [(True, 1), (False, 1), (False, 6)])
@@ -42,11 +60,10 @@ def test_evaluate_matches_oracle(eng, det, searches):
     ospec = orc.puzzle_spec(4, 4, 10, 2, 256)
     env = tw.env.Puzzle(4, 4, 10, 2, 256)
     n = 200
-    s, r = _evaluate(eng, env, pol, n, det, searches, cid=7)
-    os_, or_, bs, bt = orc.evaluate(ospec, opol, n, det, searches, seed=eng.seed, collect_id=7)
-    # identical streams: results agree except where ulp-level logit differences flip an argmax tie or move a
-    # weighted draw across a bin edge (rare) -- means must agree closely
-    assert abs(s - os_) <= 2.0 / n and abs(r - or_) <= 0.05
+    s, r, bs, bt = _evaluate(eng, env, pol, n, det, searches, cid=7, episodes=True)
+    obs_, obt, mm = orc.evaluate_margins(ospec, opol, n, det, searches, seed=eng.seed, collect_id=7)
+    _check_episodes(bs, bt, obs_, obt, mm, f"evaluate det={det} searches={searches}")
+    assert abs(s - float(bs.mean())) < 1e-6 and abs(r - float(bt.mean())) < 1e-4          # the means are the means of these
     assert 0.0 <= s <= 1.0
 
 
@@ -139,10 +156,10 @@ def test_evaluate_with_mcts_matches_oracle(eng, det, searches, sims):
     ospec = orc.puzzle_spec(3, 3, 4, 2, 256)
     env = tw.env.Puzzle(3, 3, 4, 2, 256)
     n = 96
-    s, r = _evaluate(eng, env, pol, n, det, searches, cid=13, mcts=sims, c_puct=1.41, depth=1)
-    os_, or_, _, _ = orc.evaluate(ospec, opol, n, det, searches, seed=eng.seed, collect_id=13, num_mcts_searches=sims,
-                                  c_puct=1.41, max_expand_depth=1)
-    assert abs(s - os_) <= 4.0 / n and abs(r - or_) <= 0.06
+    s, r, bs, bt = _evaluate(eng, env, pol, n, det, searches, cid=13, mcts=sims, c_puct=1.41, depth=1, episodes=True)
+    obs_, obt, mm = orc.evaluate_margins(ospec, opol, n, det, searches, seed=eng.seed, collect_id=13, num_mcts_searches=sims,
+                                         c_puct=1.41, max_expand_depth=1)
+    _check_episodes(bs, bt, obs_, obt, mm, f"evaluate+mcts det={det} searches={searches} sims={sims}")
     # the search must help: MCTS-guided evaluation solves at least as often as the raw synthetic policy
     s0, _ = _evaluate(eng, env, pol, n, det, searches, cid=13)
     assert s >= s0 - 2.0 / n

@@ -73,3 +73,25 @@ def test_solve_with_mcts_searches():
     s0, _, _, _ = orc.evaluate(spec, pol, 24, True, 1, seed=5)
     s1, _, _, _ = orc.evaluate(spec, pol, 24, True, 1, seed=5, num_mcts_searches=12)
     assert s1 >= s0 - 1e-6
+
+
+def test_trace_and_margin_instrumentation_leave_results_unchanged():
+    """orc_mcts_trace / orc_evaluate_margins (used by the GPU near-tie rule) return exactly what the plain calls return;
+    the trace is consistent with the search (each simulation backs up from the leaf or one of its new children)."""
+    from helpers import synth_state_dict
+    pol = orc.Policy.from_torch_state_dict(synth_state_dict(8, 81, 512, 256, 4))
+    env = orc.Env(orc.puzzle_spec(3, 3, 4, 2, 256)); env.reset(seed=3, env_id=5, collect_id=1)
+    for sims, med in ((20, 1), (12, 2), (8, 0)):
+        p0, v0 = orc.mcts_probs(env, pol, sims, 1.41, med, seed=3, collect_id=1, stream_id=5, t=0)
+        p1, v1, leaf, child, margin = orc.mcts_trace(env, pol, sims, 1.41, med, seed=3, collect_id=1, stream_id=5, t=0)
+        assert np.array_equal(p0, p1) and np.array_equal(v0, v1)
+        assert len(leaf) == sims and (margin >= 0).all()
+        assert leaf[0] in (1, 2, 3, 4) and all(c >= l for l, c in zip(leaf, child))      # children are allocated after their parent
+        if med == 0:
+            assert np.array_equal(leaf, child)
+    spec = orc.puzzle_spec(3, 3, 4, 2, 256)
+    for det, mcts in ((True, 0), (False, 0), (False, 6)):
+        s, r, bs, bt = orc.evaluate(spec, pol, 12, det, 2, seed=9, collect_id=2, num_mcts_searches=mcts)
+        bs2, bt2, mm = orc.evaluate_margins(spec, pol, 12, det, 2, seed=9, collect_id=2, num_mcts_searches=mcts)
+        assert np.array_equal(bs, bs2) and np.array_equal(bt, bt2)
+        assert (mm >= 0).all() and np.isfinite(mm).any()

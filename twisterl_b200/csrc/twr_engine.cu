@@ -1393,6 +1393,13 @@ static int run_solve(twr_engine* e, const EnvParams& env, const PolicyDev& dev, 
 int twr_evaluate(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, int32_t deterministic,
                  int32_t num_searches, int32_t num_mcts_searches, float C, int32_t max_expand_depth,
                  float* success_rate, float* mean_reward) {
+    return twr_evaluate_episodes(e, spec, p, num_episodes, deterministic, num_searches, num_mcts_searches, C, max_expand_depth,
+                                 success_rate, mean_reward, nullptr, nullptr);
+}
+
+int twr_evaluate_episodes(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, int32_t deterministic,
+                          int32_t num_searches, int32_t num_mcts_searches, float C, int32_t max_expand_depth,
+                          float* success_rate, float* mean_reward, float* best_success, float* best_reward) {
     if (!success_rate || !mean_reward) return fail(TWR_ERR_INVALID, "NULL argument");
     if (num_mcts_searches < 0 || max_expand_depth < 0) return fail(TWR_ERR_INVALID, "negative argument");
     const MctsOpt mo{num_mcts_searches, C, max_expand_depth};
@@ -1428,6 +1435,8 @@ int twr_evaluate(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, i
             if (s1 > bs || (s1 == bs && r1 > br)) { bs = s1; br = r1; }   // tuple '>' (lexicographic), solve.rs:94
         }
         succ += bs; rew += br;
+        if (best_success) best_success[ep] = bs;
+        if (best_reward) best_reward[ep] = br;
     }
     *success_rate = succ / (float)num_episodes;
     *mean_reward = rew / (float)num_episodes;
@@ -1484,8 +1493,22 @@ int twr_solve(twr_engine* e, twr_envs* start, const twr_policy* p, int32_t deter
 
 
 // ------------------------------------------------------------- AlphaZero (K6) ---
+static int mcts_probs_impl(twr_engine* e, const twr_policy* p, twr_envs* v, int32_t n_sims, float C, int32_t max_expand_depth,
+                           uint32_t env_id_base, uint32_t collect_id, int32_t t, float* probs, int32_t* visits, int32_t* trace);
+
 int twr_mcts_probs(twr_engine* e, const twr_policy* p, twr_envs* v, int32_t n_sims, float C, int32_t max_expand_depth,
                    uint32_t env_id_base, uint32_t collect_id, int32_t t, float* probs, int32_t* visits) {
+    return mcts_probs_impl(e, p, v, n_sims, C, max_expand_depth, env_id_base, collect_id, t, probs, visits, nullptr);
+}
+
+int twr_debug_mcts_trace(twr_engine* e, const twr_policy* p, twr_envs* v, int32_t n_sims, float C, int32_t max_expand_depth,
+                         uint32_t env_id_base, uint32_t collect_id, int32_t t, float* probs, int32_t* visits, int32_t* trace) {
+    if (!trace) return fail(TWR_ERR_INVALID, "NULL argument");
+    return mcts_probs_impl(e, p, v, n_sims, C, max_expand_depth, env_id_base, collect_id, t, probs, visits, trace);
+}
+
+static int mcts_probs_impl(twr_engine* e, const twr_policy* p, twr_envs* v, int32_t n_sims, float C, int32_t max_expand_depth,
+                           uint32_t env_id_base, uint32_t collect_id, int32_t t, float* probs, int32_t* visits, int32_t* trace) {
     if (!e || !p || !v || !probs || !visits) return fail(TWR_ERR_INVALID, "NULL argument");
     if (p->eng != e || v->eng != e) return fail(TWR_ERR_INVALID, "policy/envs belong to another engine");
     if (n_sims < 0 || max_expand_depth < 0 || t < 0) return fail(TWR_ERR_INVALID, "negative argument");
@@ -1513,10 +1536,18 @@ int twr_mcts_probs(twr_engine* e, const twr_policy* p, twr_envs* v, int32_t n_si
     a.env = v->p; a.seed = e->seed; a.cid = collect_id; a.ids = EnvIds{env_id_base, 0u, 0u, 0u};
     a.t = t; a.n_sims = n_sims; a.max_expand_depth = max_expand_depth; a.C = C;
     a.env_cells = v->cells; a.env_meta = v->meta; a.logits = logits.d; a.values = values.d;
+    Staging<int32_t> d_trace;
+    const size_t n_trace = (size_t)(n_sims > 0 ? n_sims : 1) * (size_t)B * 2;
+    if (trace) {
+        if ((rc = d_trace.alloc(n_trace))) return rc;
+        CU_TRY(cudaMemsetAsync(d_trace.d, 0xFF, sizeof(int32_t) * n_trace, e->stream));
+        a.trace = d_trace.d;
+    }
     enqueue_mcts(e, dev, a, live.d, n_live.d, B);
     launch_mcts_read(e->stream, a, B, d_probs.d, d_vis.d);
     CU_TRY(cudaGetLastError());
     FWD_CHECK(e);
+    if (trace) CU_TRY(cudaMemcpyAsync(trace, d_trace.d, sizeof(int32_t) * (size_t)n_sims * (size_t)B * 2, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaMemcpyAsync(probs, d_probs.d, sizeof(float) * (size_t)B * dev.A, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaMemcpyAsync(visits, d_vis.d, sizeof(int32_t) * (size_t)B * dev.A, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));

@@ -178,6 +178,7 @@ __device__ __forceinline__ void expand_body(const MctsArgs& a, int e, int pos, i
     philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)((a.t * (a.n_sims + 1) + sim) * med + d), TWR_RNG_MCTS, a.cid,
                   (uint32_t)a.seed, (uint32_t)(a.seed >> 32), w);
     const int child = nch > 0 ? first + weighted_index(cp, nch, u32_to_unit_f32(w[0])) : node;
+    if (a.trace) a.trace[((int64_t)sim * m.B + e) * 2 + 1] = child;
     const float v = a.values[pos];
     int len = m.path_len[e];
     if (child != node && len >= 0) {                     // the drawn child joins the recorded path
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(128) k_mcts_expand(MctsArgs a, int mode, int s
 }
 
 // descent + first rollout round (search.rs:132-146) of one env; returns whether its leaf needs a policy evaluation
-__device__ __forceinline__ bool select_body(const MctsArgs& a, int e, int64_t& gnode) {
+__device__ __forceinline__ bool select_body(const MctsArgs& a, int e, int64_t& gnode, int sim) {
     bool want = false;
     {
         const MctsPool& m = a.pool;
@@ -232,6 +233,7 @@ __device__ __forceinline__ bool select_body(const MctsArgs& a, int e, int64_t& g
         }
         m.path_len[e] = len;
         a.cur_node[e] = node;
+        if (a.trace && sim < a.n_sims) { a.trace[((int64_t)sim * m.B + e) * 2] = node; a.trace[((int64_t)sim * m.B + e) * 2 + 1] = node; }
         if (a.max_expand_depth <= 0) {
             backprop(m, e, base, node, len, 0.0f);                             // the rollout loop never runs: value stays 0
             a.active[e] = 0;
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(128) k_mcts_select(MctsArgs a, const int32_t* 
     int64_t gnode = 0;
     if (valid) {
         e = live[pos];
-        want = select_body(a, e, gnode);
+        want = select_body(a, e, gnode, sim);
     }
     push_leaf(a, want, gnode, e, a.fwd_count + which);
 }
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(128) k_mcts_expand_select(MctsArgs a, const in
     if (valid) {
         e = live[pos];
         if (a.active[e]) expand_body(a, e, a.leaf_pos[e], 1, sim, 0);
-        want = select_body(a, e, gnode);
+        want = select_body(a, e, gnode, sim + 1);
     }
     push_leaf(a, want, gnode, e, a.fwd_count + (which ^ 1));
 }

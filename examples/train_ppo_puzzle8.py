@@ -1,6 +1,7 @@
 """End-to-end check that the engine's rollouts train a policy: a compact PyTorch PPO loop (the reference's loss,
 src/twisterl/rl/ppo.py:63-113, and curriculum, rl/algorithm.py:165-171) on the 8-puzzle, with collection and
-evaluation on the B200 engine.  Not part of the product path; the reference's own trainer runs unmodified on
+evaluation on the B200 engine: the collect is handed to torch on the device (`collect_torch`) and the weights go back
+device-to-device (`Policy.update_from_torch`).  Not part of the product path; the reference's own trainer runs unmodified on
 `twisterl_b200.install_as_twisterl()`.
 
     python examples/train_ppo_puzzle8.py [iterations]
@@ -45,18 +46,13 @@ def main(iters=60):
     opt = torch.optim.Adam(policy.parameters(), lr=1.5e-4)
     env = tw.env.Puzzle(3, 3, 1, 2, 256)
     collector = tw.collector.PPOCollector(num_episodes=4096, gamma=0.995, num_cores=32, **{"lambda": 0.995})
+    rs = policy.to_engine()                  # built once; refreshed in place from the live CUDA parameters afterwards
     t0 = time.time()
     for it in range(iters):
-        rs = policy.to_engine()
+        rs.update_from_torch(policy)         # f3: device-to-device weight sync (no to_rust() round trip)
         succ, rew = tw.collector.evaluate(env, rs, 256, False, 1, 0, 0, 1.41, 1, 32)
-        data = collector.collect(env, rs)
-        obs = torch.zeros((len(data.values_array), 81), device=dev)
-        idx = torch.as_tensor(data.obs_array.astype(np.int64), device=dev)
-        obs.scatter_(1, idx, 1.0)
-        logits = torch.as_tensor(data.logits_array, device=dev)
-        acts = torch.as_tensor(data.actions_array.astype(np.int64), device=dev)
-        rets = torch.as_tensor(data.additional_array("rets"), device=dev)
-        advs = torch.as_tensor(data.additional_array("advs"), device=dev)
+        data = collector.collect_torch(env, rs)      # f2: torch CUDA tensors aliasing the engine's output
+        obs, logits, acts, rets, advs = data["obs"], data["logits"], data["actions"], data["rets"], data["advs"]
         advs = (advs - advs.mean()) / (advs.std() + 1e-8)
         old_lp = torch.distributions.Categorical(logits=logits).log_prob(acts)
         illegal = logits <= -1e9

@@ -121,6 +121,54 @@ class Policy:
             self._dev = (engine, h)
         return self._dev[1]
 
+    def update_from_torch(self, module, engine: _lib.Engine | None = None) -> None:
+        """In-place weight refresh from the LIVE parameters of a torch policy: what the reference
+        does every iteration through `policy.to_rust()` -- `.cpu().numpy().T.flatten().tolist()` per layer
+        (src/twisterl/nn/utils.py:17-59, rl/algorithm.py:91-93) -- becomes device-to-device copies into the engine's
+        parameter blob (each Linear as W.T, the layout twr_policy_desc documents) and one operand re-pack
+        (twr_policy_update_from_device).  `module` is a BasicPolicy-shaped torch module on the engine's GPU: `embeddings`
+        (Linear), `common` / `action` / `value` (Sequentials of Linear and ReLU); this policy must have been built from
+        the same architecture (e.g. by `module.to_rust()`).  Raises NotImplementedError for other embedding kinds."""
+        import torch
+        engine = engine or (self._dev[0] if self._dev is not None else _lib.default_engine())
+        h = self.device_handle(engine)
+        emb = module.embeddings
+        if type(emb).__name__ != "Linear" or len(self.embeddings.obs_shape) != 1:
+            raise NotImplementedError("update_from_torch covers the Linear embedding of BasicPolicy; rebuild with to_rust() instead")
+        lins = [l for seq in (module.common, module.action, module.value) for l in seq if type(l).__name__ == "Linear"]
+        mine = self.common.layers + self.action_net.layers + self.value_net.layers
+        if len(lins) != len(mine) or any((l.in_features, l.out_features) != (m.in_, m.out) for l, m in zip(lins, mine)) or \
+                tuple(emb.weight.shape) != (self.embeddings.bias.size, self.embeddings.vectors.shape[0]):
+            raise ValueError("torch module and engine policy have different architectures")
+        L = _lib.load()
+        n = int(L.twr_policy_blob_floats(h))
+        dptr = C.c_void_p()
+        _lib.check(L.twr_policy_blob_device_ptr(h, C.byref(dptr)))
+        dev = torch.device("cuda", engine.device)
+        if emb.weight.device != dev:
+            raise ValueError(f"torch module lives on {emb.weight.device}, the engine on {dev}")
+
+        class _Blob:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (int(dptr.value), False), "version": 2}
+        blob = torch.as_tensor(_Blob(), device=dev)
+        off = 0
+
+        def put(t, shape):
+            nonlocal off
+            k = int(np.prod(shape))
+            blob[off:off + k].view(*shape).copy_(t.detach())
+            off += k
+        with torch.no_grad():
+            E, O = emb.weight.shape
+            put(emb.weight.T, (O, E))                              # vec_vectors[obs][E]
+            put(emb.bias if getattr(emb, "bias", None) is not None else torch.zeros(E, device=dev), (E,))
+            for l in lins:
+                put(l.weight.T, (l.in_features, l.out_features))   # W.T.flatten(): w[i*out + o] == W[o][i]
+                put(l.bias, (l.out_features,))
+        assert off == n
+        torch.cuda.current_stream(dev).synchronize()               # the engine refreshes its operand tiles on its own stream
+        _lib.check(L.twr_policy_update_from_device(h, dptr))
+
     def release(self):
         if self._dev is not None:
             eng, h = self._dev

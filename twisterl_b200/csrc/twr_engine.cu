@@ -1282,6 +1282,8 @@ static int mcts_pool_nodes(int A, int n_sims, int med) { return 1 + A * (n_sims 
 // predict_probs_mcts (rl/search.rs:104-189) for every live env, in lockstep over the simulations
 static void enqueue_mcts(twr_engine* e, const PolicyDev& dev, MctsArgs& a, const int32_t* live, const int32_t* n_live, int64_t B) {
     cudaStream_t st = e->stream;
+    // small batches: one persistent launch runs every simulation of the search (twr_mcts.cu, k_mcts_persistent)
+    if (!getenv("TWISTERL_B200_MCTS_LOCKSTEP") && launch_mcts_persistent(st, a, dev, live, n_live, B)) return;
     ForwardArgs fa{};
     fa.env = a.env; fa.seed = e->seed; fa.cid = a.cid; fa.ids = a.ids; fa.t = -1;
     fa.cells = a.pool.cells; fa.live = a.fwd_list; fa.n = B;

@@ -175,5 +175,6 @@ void launch_mcts_select(cudaStream_t s, const MctsArgs& a, const int32_t* live, 
 void launch_mcts_expand_select(cudaStream_t s, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int sim, int which, int64_t max_n);
 void launch_mcts_pre(cudaStream_t s, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int which, int64_t max_n);
 void launch_mcts_read(cudaStream_t s, const MctsArgs& a, int64_t n, float* probs, int32_t* visits);
+bool launch_mcts_persistent(cudaStream_t s, const MctsArgs& a, const PolicyDev& p, const int32_t* live, const int32_t* n_live, int64_t max_n);
 void launch_az_finish(cudaStream_t s, const MctsArgs& a, const CollectBuffers& b, const int32_t* live, int32_t* live_next);
 void launch_az_remaining(cudaStream_t s, const CollectBuffers& b);

@@ -396,6 +396,241 @@ __global__ void __launch_bounds__(256) k_az_remaining(CollectBuffers b) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent whole-search kernel for SMALL batches (the reference's AlphaZero default is 512 episodes x 1000 simulations,
+// src/twisterl/defaults.py:82-90).  The lockstep path above costs two dependent launches per simulation, and its forward
+// keeps 2-4 SMs busy on a 512-leaf batch: ~115 us per simulation, below the host.  Here ONE launch runs all simulations of
+// a search: a cluster of PM_CS CTAs owns up to PM_TPC trees and holds the policy STATIONARY in shared memory, split by
+// columns -- CTA r keeps features [r*EC, (r+1)*EC) of the embedding table and columns [r*HC, (r+1)*HC) of the common
+// Linear (fp32, the oracle's arithmetic) -- so a simulation is four short phases separated by cluster barriers, with no
+// launch, no global operand traffic and no inter-cluster dependency:
+//   A  owner thread of each tree (tree j -> CTA j % PM_CS): UCB descent; the leaf's 16-byte state goes to every CTA (DSMEM)
+//   B  every CTA: its EC features of h1 = relu(bias + sum of table rows) for every leaf, stored into EVERY CTA's h1 (DSMEM)
+//   C  every CTA: its HC columns of h2 = relu(W1.h1 + b1) (k ascending, layers.rs:31-37) and their share of the five head
+//      dot products, warp-reduced and sent to the owner CTA
+//   D  owner thread: logits / value = sum of the PM_CS partial sums (+ bias), then Policy::predict's epilogue, expand,
+//      child draw and backup exactly as expand_body does
+// Trees stay in the global node pool (L2-resident: 512 trees x 160 KB), touched by one thread each.
+constexpr int PM_CS = 8;
+constexpr int PM_THREADS = 256;
+constexpr int PM_TPC = 32;
+
+struct PmLayout { int E, H, EC, HC, obs; size_t w1s, tab, h1, b1s, embb, headw, part, cells, flag, total; };
+__host__ __device__ inline PmLayout pm_layout(int E, int H, int obs) {
+    PmLayout l;
+    l.E = E; l.H = H; l.obs = obs; l.EC = E / PM_CS; l.HC = H / PM_CS;
+    size_t o = 0;
+    l.w1s = o; o += sizeof(float) * (size_t)E * l.HC;
+    l.tab = o; o += sizeof(float) * (size_t)obs * l.EC;
+    l.h1 = o; o += sizeof(float) * (size_t)PM_TPC * E;
+    l.b1s = o; o += sizeof(float) * (size_t)l.HC;
+    l.embb = o; o += sizeof(float) * (size_t)l.EC;
+    l.headw = o; o += sizeof(float) * (size_t)l.HC * 8;
+    l.part = o; o += sizeof(float) * (size_t)PM_TPC * PM_CS * 8;
+    l.cells = o; o += sizeof(uint4) * (size_t)PM_TPC;
+    l.flag = o; o += sizeof(int) * (size_t)PM_TPC;
+    l.total = (o + 15) & ~(size_t)15;
+    return l;
+}
+
+__device__ __forceinline__ uint32_t pm_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t pm_cluster_id() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t pm_nclusters() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void pm_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// generic address of `p` (a shared-memory address of this CTA) inside CTA `rank` of the cluster
+template <typename T>
+__device__ __forceinline__ T* pm_remote(T* p, uint32_t rank) {
+    uint64_t out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"(reinterpret_cast<uint64_t>(p)), "r"(rank));
+    return reinterpret_cast<T*>(out);
+}
+
+__global__ void __launch_bounds__(PM_THREADS, 1)
+k_mcts_persistent(MctsArgs a, PolicyDev p, const int32_t* __restrict__ live, const int32_t* __restrict__ n_live) {
+    extern __shared__ __align__(16) unsigned char pm_smem[];
+    const PmLayout L = pm_layout(p.E, p.H, p.obs_size);
+    float* w1s = reinterpret_cast<float*>(pm_smem + L.w1s);
+    float* tab = reinterpret_cast<float*>(pm_smem + L.tab);
+    float* h1 = reinterpret_cast<float*>(pm_smem + L.h1);
+    float* b1s = reinterpret_cast<float*>(pm_smem + L.b1s);
+    float* embb = reinterpret_cast<float*>(pm_smem + L.embb);
+    float* headw = reinterpret_cast<float*>(pm_smem + L.headw);
+    float* part = reinterpret_cast<float*>(pm_smem + L.part);
+    uint4* leaf_cells = reinterpret_cast<uint4*>(pm_smem + L.cells);
+    int* leaf_flag = reinterpret_cast<int*>(pm_smem + L.flag);
+    const int tid = threadIdx.x;
+    const uint32_t rank = pm_rank();
+    const int E = L.E, EC = L.EC, HC = L.HC;
+    const MctsPool& m = a.pool;
+
+    // ---- stationary operands: this CTA's column slices (fp32)
+    for (int i = tid; i < E * HC; i += PM_THREADS) { const int k = i / HC, c = i % HC; w1s[i] = p.w1[(size_t)k * p.H + rank * HC + c]; }
+    for (int i = tid; i < p.obs_size * EC; i += PM_THREADS) { const int r = i / EC, f = i % EC; tab[i] = p.emb[(size_t)r * E + rank * EC + f]; }
+    for (int i = tid; i < HC; i += PM_THREADS) {
+        const int col = rank * HC + i;
+        b1s[i] = p.b1[col];
+        for (int o = 0; o < 4; ++o) headw[i * 8 + o] = o < p.A ? p.wa[(size_t)col * p.A + o] : 0.0f;
+        headw[i * 8 + 4] = p.wv[col]; headw[i * 8 + 5] = 0.f; headw[i * 8 + 6] = 0.f; headw[i * 8 + 7] = 0.f;
+    }
+    for (int i = tid; i < EC; i += PM_THREADS) embb[i] = p.emb_b[rank * EC + i];
+
+    // ---- trees of this cluster: live positions [first, first + nt); tree j is owned by thread j / PM_CS of CTA j % PM_CS
+    const int n = *n_live;
+    const int ncl = (int)pm_nclusters();
+    const int per = (n + ncl - 1) / ncl;
+    const int first = (int)pm_cluster_id() * per;
+    const int nt = max(0, min(per, n - first));            // host guarantees per <= PM_TPC
+    const int j_own = tid * PM_CS + (int)rank;             // the tree this thread owns (if tid < PM_TPC / PM_CS and j_own < nt)
+    const bool owner = tid < PM_TPC / PM_CS && j_own < nt;
+    int e = 0, node = 0, len = 1;
+    int64_t base = 0;
+    bool need = false;
+    if (owner) { e = live[first + j_own]; base = (int64_t)e * m.P; }
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    __syncthreads();
+    pm_cluster_sync();
+
+    for (int sim = -1; sim < a.n_sims; ++sim) {
+        // ================= A: descent (owner threads) =================
+        if (owner) {
+            need = false;
+            if (sim < 0) {                                  // k_mcts_begin: the root (search.rs:112-128), always evaluated
+                m.cells[base] = a.env_cells[e]; m.meta[base] = a.env_meta[e];
+                m.parent[base] = -1;
+                m.node[base] = make_uint4(1u, __float_as_uint(0.0f), __float_as_uint(0.0f), link_pack(0, 0, 0xFF));
+                m.n_nodes[e] = 1;
+                m.path[e] = 0; m.path_len[e] = 1;
+                node = 0; len = 1; need = true;
+            } else {                                        // select_body without the leaf-batch compaction
+                node = 0; len = 1;
+                uint4 cur = m.node[base];
+                while (link_nch(cur.w) > 0) {
+                    const int fc = link_first(cur.w), nch = link_nch(cur.w);
+                    const float sq = sqrtf((float)cur.x);
+                    uint4 ch[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (k < nch) ch[k] = m.node[base + fc + k];
+                    int best = -1;
+                    float best_ucb = -INFINITY;
+                    uint4 best_rec = cur;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k < nch) {
+                            const uint32_t nv = ch[k].x;
+                            const float q = nv == 0u ? 0.0f : __fdiv_rn(__uint_as_float(ch[k].y), (float)nv);
+                            const float ucb = __fadd_rn(q, __fmul_rn(__fmul_rn(a.C, __fdiv_rn(sq, __fadd_rn((float)nv, 1.0f))), __uint_as_float(ch[k].z)));
+                            if (ucb > best_ucb) { best = fc + k; best_ucb = ucb; best_rec = ch[k]; }
+                        }
+                    }
+                    if (best < 0) break;
+                    node = best; cur = best_rec;
+                    if (len >= 0) { if (len < TWR_MCTS_PATH) { m.path[(int64_t)len * m.B + e] = node; ++len; } else len = -1; }
+                }
+                if (a.trace) { a.trace[((int64_t)sim * m.B + e) * 2] = node; a.trace[((int64_t)sim * m.B + e) * 2 + 1] = node; }
+                const EnvState s = node_state(m, base + node);
+                if (env_is_final(a.env, s) || m.n_nodes[e] + m.A > m.P) backprop(m, e, base, node, len, env_reward(a.env, s));
+                else need = true;
+            }
+            const uint4 cells = need ? m.cells[base + node] : make_uint4(0, 0, 0, 0);
+            for (uint32_t r = 0; r < PM_CS; ++r) {          // the leaf's state to every CTA of the cluster
+                *pm_remote(leaf_cells + j_own, r) = cells;
+                *pm_remote(leaf_flag + j_own, r) = need ? 1 : 0;
+            }
+        }
+        pm_cluster_sync();
+        // ================= B: embedding slice, h1[j][rank*EC + f] into every CTA =================
+        for (int idx = tid; idx < nt * (EC / 4); idx += PM_THREADS) {
+            const int j = idx / (EC / 4), f4 = (idx % (EC / 4)) * 4;
+            if (!leaf_flag[j]) continue;
+            const uint4 c = leaf_cells[j];
+            EnvState s; s.blank = 0; s.depth = 0;
+            s.lo = (uint64_t)c.x | ((uint64_t)c.y << 32); s.hi = (uint64_t)c.z | ((uint64_t)c.w << 32);
+            float4 acc = *reinterpret_cast<const float4*>(embb + f4);                       // bias first, then the rows in
+            for (int i = 0; i < a.env.N; ++i) {                                              // observation order (layers.rs:58-62)
+                const int r = i * a.env.N + (int)env_board(a.env, s, i);
+                const float4 t4 = *reinterpret_cast<const float4*>(tab + (size_t)r * EC + f4);
+                acc.x = __fadd_rn(acc.x, t4.x); acc.y = __fadd_rn(acc.y, t4.y); acc.z = __fadd_rn(acc.z, t4.z); acc.w = __fadd_rn(acc.w, t4.w);
+            }
+            acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+            float* dst = h1 + (size_t)j * E + rank * EC + f4;
+            for (uint32_t r = 0; r < PM_CS; ++r) *reinterpret_cast<float4*>(pm_remote(dst, r)) = acc;
+        }
+        pm_cluster_sync();
+        // ================= C: common Linear slice + head partial sums =================
+        {
+            const int c = tid % HC, g = tid / HC, ng = PM_THREADS / HC;        // HC in {16, 32}: a group never straddles a warp
+            for (int jb = 0; jb < nt; jb += 4 * ng) {                          // same trip count for every thread: shuffles below
+                const int j0 = jb + g;
+                int js[4]; bool on[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { js[u] = j0 + u * ng; on[u] = js[u] < nt && leaf_flag[js[u]]; }
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                if (on[0] || on[1] || on[2] || on[3]) {
+                    for (int k = 0; k < E; k += 4) {
+                        const float w0 = w1s[(k + 0) * HC + c], w1v = w1s[(k + 1) * HC + c], w2 = w1s[(k + 2) * HC + c], w3 = w1s[(k + 3) * HC + c];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (on[u]) {
+                                const float4 x = *reinterpret_cast<const float4*>(h1 + (size_t)js[u] * E + k);
+                                acc[u] = fmaf(w0, x.x, acc[u]); acc[u] = fmaf(w1v, x.y, acc[u]);
+                                acc[u] = fmaf(w2, x.z, acc[u]); acc[u] = fmaf(w3, x.w, acc[u]);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float h = on[u] ? fmaxf(acc[u] + b1s[c], 0.f) : 0.f;
+                    float pr[5];
+#pragma unroll
+                    for (int o = 0; o < 5; ++o) pr[o] = h * headw[c * 8 + o];
+                    for (int d = HC / 2; d > 0; d >>= 1) {
+#pragma unroll
+                        for (int o = 0; o < 5; ++o) pr[o] += __shfl_xor_sync(0xffffffffu, pr[o], d);
+                    }
+                    if (c == 0 && on[u]) {
+                        float* dst = pm_remote(part + ((size_t)js[u] * PM_CS + rank) * 8, (uint32_t)(js[u] % PM_CS));
+#pragma unroll
+                        for (int o = 0; o < 5; ++o) dst[o] = pr[o];
+                    }
+                }
+            }
+        }
+        pm_cluster_sync();
+        // ================= D: predict epilogue, expand, child draw, backup (owner threads) =================
+        if (owner && need) {
+            float l[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int r = 0; r < PM_CS; ++r) {
+#pragma unroll
+                for (int o = 0; o < 5; ++o) l[o] += part[((size_t)j_own * PM_CS + r) * 8 + o];
+            }
+            const float4 raw = make_float4(l[0] + (p.A > 0 ? p.ba[0] : 0.f), l[1] + (p.A > 1 ? p.ba[1] : 0.f), l[2] + (p.A > 2 ? p.ba[2] : 0.f),
+                                           l[3] + (p.A > 3 ? p.ba[3] : 0.f));
+            const float v = l[4] + p.bv[0];
+            const EnvState s = node_state(m, base + node);
+            float pr[4], cp[4];
+            masked_probs(raw, env_masks(a.env, s), m.A, pr);
+            int nch;
+            const int fc = expand(m, a.env, e, base, node, pr, cp, nch);
+            if (sim >= 0) {                                 // next_sample + backup (search.rs:94-100, 45-53)
+                uint32_t w[4];
+                philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)(a.t * (a.n_sims + 1) + sim), TWR_RNG_MCTS, a.cid, k0, k1, w);
+                const int child = nch > 0 ? fc + weighted_index(cp, nch, u32_to_unit_f32(w[0])) : node;
+                if (a.trace) a.trace[((int64_t)sim * m.B + e) * 2 + 1] = child;
+                if (child != node && len >= 0) { if (len < TWR_MCTS_PATH) { m.path[(int64_t)len * m.B + e] = child; ++len; } else len = -1; }
+                backprop(m, e, base, child, len, v);
+            }
+        }
+        // the owner's global writes of D are read by the same thread in the next A: no barrier needed in between
+    }
+    if (owner) m.path_len[e] = len;
+    pm_cluster_sync();                                      // no CTA may exit while a peer can still write into its shared memory
+}
+
 }  // namespace
 
 void launch_mcts_begin(cudaStream_t st, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int64_t max_n) {
@@ -429,4 +664,35 @@ void launch_az_finish(cudaStream_t st, const MctsArgs& a, const CollectBuffers& 
 void launch_az_remaining(cudaStream_t st, const CollectBuffers& b) {
     k_az_remaining<<<grid_for(b.B, 256), 256, 0, st>>>(b);
     TWR_COUNT_LAUNCH();
+}
+
+// Whole-search persistent kernel (small batches, max_expand_depth == 1).  Returns false when it does not apply: the caller
+// then runs the lockstep path.
+bool launch_mcts_persistent(cudaStream_t st, const MctsArgs& a, const PolicyDev& p, const int32_t* live, const int32_t* n_live, int64_t max_n) {
+    if (p.generic || a.max_expand_depth != 1 || p.n_perms > 0 || max_n < 1) return false;
+    if (p.E % (PM_CS * 4) || p.E > 1024 || (p.H != 128 && p.H != 256) || p.A > 4) return false;
+    const PmLayout L = pm_layout(p.E, p.H, p.obs_size);
+    if (L.total > 227 * 1024) return false;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = PM_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(PM_THREADS); cfg.dynamicSmemBytes = L.total; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+    if (cudaFuncSetAttribute(k_mcts_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) { cudaGetLastError(); return false; }
+    int sms = 0, nc = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cfg.gridDim = dim3((unsigned)((sms / PM_CS) * PM_CS));
+    // clusters of this size and shared-memory footprint the device holds at once (a host-side computation): all of a
+    // launch's clusters are then resident, although nothing here waits on another cluster
+    if (cudaOccupancyMaxActiveClusters(&nc, k_mcts_persistent, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
+    if (nc > sms / PM_CS) nc = sms / PM_CS;
+    if (nc < 1) return false;
+    int ncl = (int)(max_n < nc ? max_n : nc);
+    if ((max_n + ncl - 1) / ncl > PM_TPC) return false;      // too many trees for the clusters that fit: lockstep path
+    cfg.gridDim = dim3((unsigned)(ncl * PM_CS));
+    if (cudaLaunchKernelEx(&cfg, k_mcts_persistent, a, p, live, n_live) != cudaSuccess) { cudaGetLastError(); return false; }
+    TWR_COUNT_LAUNCH();
+    return true;
 }

@@ -19,8 +19,12 @@ eng = tw.Engine(device=0, precision=prec, seed=7)
 env = tw.env.Puzzle(3, 3, diff, 2, 256)
 col = tw.collector.AZCollector(E, sims, 1.41, 1, 32, engine=eng)
 col.collect(env, pol)
-t0 = time.perf_counter(); d = col.collect(env, pol); dt = time.perf_counter() - t0
-R = len(d.obs_array)
+times = []
+for _ in range(int(os.environ.get("REPEATS", "5"))):
+    t0 = time.perf_counter(); d = col.collect_device(env, pol); times.append(time.perf_counter() - t0)
+dt = min(times)
+R = int(d.n_records)
+print("collect seconds:", " ".join(f"{t:.3f}" for t in times))
 print(f"GPU  {prec}: {E} episodes x {sims} sims, difficulty {diff}: {R} records in {dt:.3f}s -> {R/dt:.1f} records/s, "
       f"{R*(sims+1)/dt:.3e} leaf evals/s, launches {eng.launch_count()}")
 Ec = max(8, E // 32)

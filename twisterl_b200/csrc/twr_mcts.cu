@@ -19,6 +19,8 @@
 #include "twr_kernels.cuh"
 
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 extern std::atomic<long long> g_twr_launches;
 #define TWR_COUNT_LAUNCH() g_twr_launches.fetch_add(1, std::memory_order_relaxed)
 
@@ -400,34 +402,37 @@ __global__ void __launch_bounds__(256) k_az_remaining(CollectBuffers b) {
 // ------------------------------------------------------------------------------------------------------------------
 // Persistent whole-search kernel for SMALL batches (the reference's AlphaZero default is 512 episodes x 1000 simulations,
 // src/twisterl/defaults.py:82-90).  The lockstep path above costs two dependent launches per simulation, and its forward
-// keeps 2-4 SMs busy on a 512-leaf batch: ~115 us per simulation, below the host.  Here ONE launch runs all simulations of
-// a search: a cluster of PM_CS CTAs owns up to PM_TPC trees and holds the policy STATIONARY in shared memory, split by
-// columns -- CTA r keeps features [r*EC, (r+1)*EC) of the embedding table and columns [r*HC, (r+1)*HC) of the common
-// Linear (fp32, the oracle's arithmetic) -- so a simulation is four short phases separated by cluster barriers, with no
+// keeps 2-4 SMs busy on a 512-leaf batch: ~30 us per simulation, below the host.  Here ONE launch runs all simulations of
+// a search: a cluster of PM_CS CTAs owns up to PM_TPC trees and holds the policy STATIONARY in shared memory (fp32, the
+// oracle's arithmetic), split along the embedding features: CTA r keeps features [r*EC, (r+1)*EC) of the embedding table
+// and the matching ROWS of the common Linear.  A simulation is four short phases separated by cluster barriers, with no
 // launch, no global operand traffic and no inter-cluster dependency:
 //   A  owner thread of each tree (tree j -> CTA j % PM_CS): UCB descent; the leaf's 16-byte state goes to every CTA (DSMEM)
-//   B  every CTA: its EC features of h1 = relu(bias + sum of table rows) for every leaf, stored into EVERY CTA's h1 (DSMEM)
-//   C  every CTA: its HC columns of h2 = relu(W1.h1 + b1) (k ascending, layers.rs:31-37) and their share of the five head
-//      dot products, warp-reduced and sent to the owner CTA
-//   D  owner thread: logits / value = sum of the PM_CS partial sums (+ bias), then Policy::predict's epilogue, expand,
-//      child draw and backup exactly as expand_body does
+//   B  every CTA: its EC features of h1 = relu(bias + sum of table rows) for every leaf (local), then its K-slice of
+//      W1.h1 for ALL H columns (the weights of a column cached in registers), sent to the CTA that OWNS the leaf's tree
+//      (distributed shared memory moves 17-21 B/clk: the partial sums are half the bytes an all-gather of h1 would be)
+//   C  owner CTA, local: h2 = relu(sum of the PM_CS partial sums + b1) and the five head dot products of its trees
+//   D  owner thread: Policy::predict's epilogue, expand, child draw and backup exactly as expand_body does
+// -- two cluster barriers per simulation (after A and after B).
 // Trees stay in the global node pool (L2-resident: 512 trees x 160 KB), touched by one thread each.
 constexpr int PM_CS = 8;
 constexpr int PM_THREADS = 256;
-constexpr int PM_TPC = 32;
+constexpr int PM_TPC = 40;
+constexpr int PM_MAX_EC = 64;        // E <= 512
 
-struct PmLayout { int E, H, EC, HC, obs; size_t w1s, tab, h1, b1s, embb, headw, part, cells, flag, total; };
+struct PmLayout { int E, H, EC, obs; size_t w1s, tab, h1s, b1s, embb, headw, part2, red, cells, flag, total; };
 __host__ __device__ inline PmLayout pm_layout(int E, int H, int obs) {
     PmLayout l;
-    l.E = E; l.H = H; l.obs = obs; l.EC = E / PM_CS; l.HC = H / PM_CS;
+    l.E = E; l.H = H; l.obs = obs; l.EC = E / PM_CS;
     size_t o = 0;
-    l.w1s = o; o += sizeof(float) * (size_t)E * l.HC;
-    l.tab = o; o += sizeof(float) * (size_t)obs * l.EC;
-    l.h1 = o; o += sizeof(float) * (size_t)PM_TPC * E;
-    l.b1s = o; o += sizeof(float) * (size_t)l.HC;
+    l.w1s = o; o += sizeof(float) * (size_t)l.EC * H;                    // W1 rows [r*EC, (r+1)*EC) x all H columns
+    l.tab = o; o += sizeof(float) * (size_t)obs * l.EC;                  // table features [r*EC, (r+1)*EC)
+    l.h1s = o; o += sizeof(float) * (size_t)PM_TPC * l.EC;               // this CTA's h1 slice of every leaf
+    l.b1s = o; o += sizeof(float) * (size_t)H;
     l.embb = o; o += sizeof(float) * (size_t)l.EC;
-    l.headw = o; o += sizeof(float) * (size_t)l.HC * 8;
-    l.part = o; o += sizeof(float) * (size_t)PM_TPC * PM_CS * 8;
+    l.headw = o; o += sizeof(float) * (size_t)H * 8;
+    l.part2 = o; o += sizeof(float) * (size_t)(PM_TPC / PM_CS) * PM_CS * H;   // partial h2 of MY trees (all H columns) from every rank
+    l.red = o; o += sizeof(float) * (size_t)(PM_TPC / PM_CS) * 8 * 8;         // head sums of my trees per warp
     l.cells = o; o += sizeof(uint4) * (size_t)PM_TPC;
     l.flag = o; o += sizeof(int) * (size_t)PM_TPC;
     l.total = (o + 15) & ~(size_t)15;
@@ -450,48 +455,54 @@ __device__ __forceinline__ T* pm_remote(T* p, uint32_t rank) {
 }
 
 __global__ void __launch_bounds__(PM_THREADS, 1)
-k_mcts_persistent(MctsArgs a, PolicyDev p, const int32_t* __restrict__ live, const int32_t* __restrict__ n_live) {
+k_mcts_persistent(MctsArgs a, PolicyDev p, const int32_t* __restrict__ live, const int32_t* __restrict__ n_live, int pos0, int cap) {
     extern __shared__ __align__(16) unsigned char pm_smem[];
     const PmLayout L = pm_layout(p.E, p.H, p.obs_size);
     float* w1s = reinterpret_cast<float*>(pm_smem + L.w1s);
     float* tab = reinterpret_cast<float*>(pm_smem + L.tab);
-    float* h1 = reinterpret_cast<float*>(pm_smem + L.h1);
+    float* h1s = reinterpret_cast<float*>(pm_smem + L.h1s);
     float* b1s = reinterpret_cast<float*>(pm_smem + L.b1s);
     float* embb = reinterpret_cast<float*>(pm_smem + L.embb);
     float* headw = reinterpret_cast<float*>(pm_smem + L.headw);
-    float* part = reinterpret_cast<float*>(pm_smem + L.part);
+    float* part2 = reinterpret_cast<float*>(pm_smem + L.part2);
+    float* red = reinterpret_cast<float*>(pm_smem + L.red);
     uint4* leaf_cells = reinterpret_cast<uint4*>(pm_smem + L.cells);
     int* leaf_flag = reinterpret_cast<int*>(pm_smem + L.flag);
     const int tid = threadIdx.x;
     const uint32_t rank = pm_rank();
-    const int E = L.E, EC = L.EC, HC = L.HC;
+    const int E = L.E, H = L.H, EC = L.EC;
     const MctsPool& m = a.pool;
 
-    // ---- stationary operands: this CTA's column slices (fp32)
-    for (int i = tid; i < E * HC; i += PM_THREADS) { const int k = i / HC, c = i % HC; w1s[i] = p.w1[(size_t)k * p.H + rank * HC + c]; }
+    // ---- stationary operands (fp32): this CTA's feature slice of the table and the matching rows of W1
+    for (int i = tid; i < EC * H; i += PM_THREADS) w1s[i] = p.w1[(size_t)rank * EC * H + i];
     for (int i = tid; i < p.obs_size * EC; i += PM_THREADS) { const int r = i / EC, f = i % EC; tab[i] = p.emb[(size_t)r * E + rank * EC + f]; }
-    for (int i = tid; i < HC; i += PM_THREADS) {
-        const int col = rank * HC + i;
-        b1s[i] = p.b1[col];
-        for (int o = 0; o < 4; ++o) headw[i * 8 + o] = o < p.A ? p.wa[(size_t)col * p.A + o] : 0.0f;
-        headw[i * 8 + 4] = p.wv[col]; headw[i * 8 + 5] = 0.f; headw[i * 8 + 6] = 0.f; headw[i * 8 + 7] = 0.f;
+    for (int i = tid; i < H; i += PM_THREADS) {
+        b1s[i] = p.b1[i];
+        for (int o = 0; o < 4; ++o) headw[i * 8 + o] = o < p.A ? p.wa[(size_t)i * p.A + o] : 0.0f;
+        headw[i * 8 + 4] = p.wv[i]; headw[i * 8 + 5] = 0.f; headw[i * 8 + 6] = 0.f; headw[i * 8 + 7] = 0.f;
     }
     for (int i = tid; i < EC; i += PM_THREADS) embb[i] = p.emb_b[rank * EC + i];
+    __syncthreads();
+    // the W1 column of this thread, its EC rows cached in registers for the whole search (phase B)
+    const int col = tid % H, lg = tid / H, nlg = PM_THREADS / H;          // H = 256: one leaf group; H = 128: two
+    float wreg[PM_MAX_EC];
+#pragma unroll
+    for (int k = 0; k < PM_MAX_EC; ++k) wreg[k] = k < EC ? w1s[k * H + col] : 0.0f;
 
-    // ---- trees of this cluster: live positions [first, first + nt); tree j is owned by thread j / PM_CS of CTA j % PM_CS
-    const int n = *n_live;
+    // ---- trees of this launch: live positions [pos0, pos0 + cap) (a batch larger than the resident clusters can hold is cut
+    // into several launches; trees are independent); tree j of the cluster is owned by thread j / PM_CS of CTA j % PM_CS
+    const int n = max(0, min(*n_live - pos0, cap));
     const int ncl = (int)pm_nclusters();
     const int per = (n + ncl - 1) / ncl;
-    const int first = (int)pm_cluster_id() * per;
-    const int nt = max(0, min(per, n - first));            // host guarantees per <= PM_TPC
-    const int j_own = tid * PM_CS + (int)rank;             // the tree this thread owns (if tid < PM_TPC / PM_CS and j_own < nt)
+    const int first = pos0 + (int)pm_cluster_id() * per;
+    const int nt = max(0, min(per, pos0 + n - first));     // host guarantees per <= PM_TPC
+    const int j_own = tid * PM_CS + (int)rank;
     const bool owner = tid < PM_TPC / PM_CS && j_own < nt;
     int e = 0, node = 0, len = 1;
     int64_t base = 0;
     bool need = false;
     if (owner) { e = live[first + j_own]; base = (int64_t)e * m.P; }
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-    __syncthreads();
     pm_cluster_sync();
 
     for (int sim = -1; sim < a.n_sims; ++sim) {
@@ -542,7 +553,7 @@ k_mcts_persistent(MctsArgs a, PolicyDev p, const int32_t* __restrict__ live, con
             }
         }
         pm_cluster_sync();
-        // ================= B: embedding slice, h1[j][rank*EC + f] into every CTA =================
+        // ================= B: embedding slice (local), then this K-slice of W1.h1 for every column =================
         for (int idx = tid; idx < nt * (EC / 4); idx += PM_THREADS) {
             const int j = idx / (EC / 4), f4 = (idx % (EC / 4)) * 4;
             if (!leaf_flag[j]) continue;
@@ -556,76 +567,83 @@ k_mcts_persistent(MctsArgs a, PolicyDev p, const int32_t* __restrict__ live, con
                 acc.x = __fadd_rn(acc.x, t4.x); acc.y = __fadd_rn(acc.y, t4.y); acc.z = __fadd_rn(acc.z, t4.z); acc.w = __fadd_rn(acc.w, t4.w);
             }
             acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-            float* dst = h1 + (size_t)j * E + rank * EC + f4;
-            for (uint32_t r = 0; r < PM_CS; ++r) *reinterpret_cast<float4*>(pm_remote(dst, r)) = acc;
+            *reinterpret_cast<float4*>(h1s + (size_t)j * EC + f4) = acc;
+        }
+        __syncthreads();
+        for (int i = lg; i < nt; i += nlg) {
+            // leaf order rotated by the CTA rank: at any moment the PM_CS senders address PM_CS different owner CTAs
+            // (all of them sending leaf j at once would queue on one shared-memory port: measured 2x on the whole search)
+            const int j = (i + (int)rank) % nt;
+            if (!leaf_flag[j]) continue;
+            const float4* x = reinterpret_cast<const float4*>(h1s + (size_t)j * EC);
+            float acc = 0.0f;
+#pragma unroll
+            for (int k4 = 0; k4 < PM_MAX_EC / 4; ++k4) {
+                if (4 * k4 < EC) {
+                    const float4 v = x[k4];
+                    acc = fmaf(wreg[4 * k4 + 0], v.x, acc); acc = fmaf(wreg[4 * k4 + 1], v.y, acc);
+                    acc = fmaf(wreg[4 * k4 + 2], v.z, acc); acc = fmaf(wreg[4 * k4 + 3], v.w, acc);
+                }
+            }
+            // to the tree's owner CTA: part2[tree slot j / PM_CS][this rank][col]
+            pm_remote(part2, (uint32_t)(j % PM_CS))[((size_t)(j / PM_CS) * PM_CS + rank) * H + col] = acc;
         }
         pm_cluster_sync();
-        // ================= C: common Linear slice + head partial sums =================
+        // ================= C: h2 and the heads of MY trees (local) =================
         {
-            const int c = tid % HC, g = tid / HC, ng = PM_THREADS / HC;        // HC in {16, 32}: a group never straddles a warp
-            for (int jb = 0; jb < nt; jb += 4 * ng) {                          // same trip count for every thread: shuffles below
-                const int j0 = jb + g;
-                int js[4]; bool on[4];
+            const int wpt = H / 32;                                             // warps per tree: 8 (H = 256) or 4 (H = 128)
+            const int my_slots = (nt - (int)rank + PM_CS - 1) / PM_CS;          // trees this CTA owns (slot jl <-> tree jl*PM_CS + rank)
+            for (int jb = 0; jb < my_slots; jb += nlg) {                        // same trip count for every thread: shuffles below
+                const int jl = jb + lg;
+                const bool on = jl < my_slots && leaf_flag[jl * PM_CS + rank];
+                float h = 0.0f;
+                if (on) {
+                    const float* q = part2 + (size_t)jl * PM_CS * H + col;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { js[u] = j0 + u * ng; on[u] = js[u] < nt && leaf_flag[js[u]]; }
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                if (on[0] || on[1] || on[2] || on[3]) {
-                    for (int k = 0; k < E; k += 4) {
-                        const float w0 = w1s[(k + 0) * HC + c], w1v = w1s[(k + 1) * HC + c], w2 = w1s[(k + 2) * HC + c], w3 = w1s[(k + 3) * HC + c];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (on[u]) {
-                                const float4 x = *reinterpret_cast<const float4*>(h1 + (size_t)js[u] * E + k);
-                                acc[u] = fmaf(w0, x.x, acc[u]); acc[u] = fmaf(w1v, x.y, acc[u]);
-                                acc[u] = fmaf(w2, x.z, acc[u]); acc[u] = fmaf(w3, x.w, acc[u]);
-                            }
-                        }
-                    }
+                    for (int r = 0; r < PM_CS; ++r) h += q[r * H];               // the K-slices in ascending order
+                    h = fmaxf(h + b1s[col], 0.f);
                 }
+                float pr[5];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float h = on[u] ? fmaxf(acc[u] + b1s[c], 0.f) : 0.f;
-                    float pr[5];
+                for (int o = 0; o < 5; ++o) pr[o] = h * headw[col * 8 + o];
+                for (int d = 16; d > 0; d >>= 1) {
 #pragma unroll
-                    for (int o = 0; o < 5; ++o) pr[o] = h * headw[c * 8 + o];
-                    for (int d = HC / 2; d > 0; d >>= 1) {
+                    for (int o = 0; o < 5; ++o) pr[o] += __shfl_xor_sync(0xffffffffu, pr[o], d);
+                }
+                if ((tid & 31) == 0 && jl < my_slots) {
 #pragma unroll
-                        for (int o = 0; o < 5; ++o) pr[o] += __shfl_xor_sync(0xffffffffu, pr[o], d);
-                    }
-                    if (c == 0 && on[u]) {
-                        float* dst = pm_remote(part + ((size_t)js[u] * PM_CS + rank) * 8, (uint32_t)(js[u] % PM_CS));
+                    for (int o = 0; o < 5; ++o) red[((size_t)jl * 8 + (col >> 5)) * 8 + o] = pr[o];
+                }
+            }
+            __syncthreads();
+            // ================= D: predict epilogue, expand, child draw, backup (owner threads) =================
+            if (owner && need) {
+                float l[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int w = 0; w < wpt; ++w) {
 #pragma unroll
-                        for (int o = 0; o < 5; ++o) dst[o] = pr[o];
-                    }
+                    for (int o = 0; o < 5; ++o) l[o] += red[((size_t)tid * 8 + w) * 8 + o];
+                }
+                const float4 raw = make_float4(l[0] + (p.A > 0 ? p.ba[0] : 0.f), l[1] + (p.A > 1 ? p.ba[1] : 0.f), l[2] + (p.A > 2 ? p.ba[2] : 0.f),
+                                               l[3] + (p.A > 3 ? p.ba[3] : 0.f));
+                const float v = l[4] + p.bv[0];
+                const EnvState s = node_state(m, base + node);
+                float pr[4], cp[4];
+                masked_probs(raw, env_masks(a.env, s), m.A, pr);
+                int nch;
+                const int fc = expand(m, a.env, e, base, node, pr, cp, nch);
+                if (sim >= 0) {                                 // next_sample + backup (search.rs:94-100, 45-53)
+                    uint32_t w[4];
+                    philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)(a.t * (a.n_sims + 1) + sim), TWR_RNG_MCTS, a.cid, k0, k1, w);
+                    const int child = nch > 0 ? fc + weighted_index(cp, nch, u32_to_unit_f32(w[0])) : node;
+                    if (a.trace) a.trace[((int64_t)sim * m.B + e) * 2 + 1] = child;
+                    if (child != node && len >= 0) { if (len < TWR_MCTS_PATH) { m.path[(int64_t)len * m.B + e] = child; ++len; } else len = -1; }
+                    backprop(m, e, base, child, len, v);
                 }
             }
         }
-        pm_cluster_sync();
-        // ================= D: predict epilogue, expand, child draw, backup (owner threads) =================
-        if (owner && need) {
-            float l[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int r = 0; r < PM_CS; ++r) {
-#pragma unroll
-                for (int o = 0; o < 5; ++o) l[o] += part[((size_t)j_own * PM_CS + r) * 8 + o];
-            }
-            const float4 raw = make_float4(l[0] + (p.A > 0 ? p.ba[0] : 0.f), l[1] + (p.A > 1 ? p.ba[1] : 0.f), l[2] + (p.A > 2 ? p.ba[2] : 0.f),
-                                           l[3] + (p.A > 3 ? p.ba[3] : 0.f));
-            const float v = l[4] + p.bv[0];
-            const EnvState s = node_state(m, base + node);
-            float pr[4], cp[4];
-            masked_probs(raw, env_masks(a.env, s), m.A, pr);
-            int nch;
-            const int fc = expand(m, a.env, e, base, node, pr, cp, nch);
-            if (sim >= 0) {                                 // next_sample + backup (search.rs:94-100, 45-53)
-                uint32_t w[4];
-                philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)(a.t * (a.n_sims + 1) + sim), TWR_RNG_MCTS, a.cid, k0, k1, w);
-                const int child = nch > 0 ? fc + weighted_index(cp, nch, u32_to_unit_f32(w[0])) : node;
-                if (a.trace) a.trace[((int64_t)sim * m.B + e) * 2 + 1] = child;
-                if (child != node && len >= 0) { if (len < TWR_MCTS_PATH) { m.path[(int64_t)len * m.B + e] = child; ++len; } else len = -1; }
-                backprop(m, e, base, child, len, v);
-            }
-        }
-        // the owner's global writes of D are read by the same thread in the next A: no barrier needed in between
+        // The owner's global writes of D are read by the same thread in the next A.  Shared-memory reuse needs no third
+        // barrier: the next A overwrites (remotely) only the leaf slots of the WRITER's own trees, which no other CTA reads
+        // after barrier 2 (C reads the flags of its own trees only); h1s / part2 are rewritten after the next barrier 1.
     }
     if (owner) m.path_len[e] = len;
     pm_cluster_sync();                                      // no CTA may exit while a peer can still write into its shared memory
@@ -670,7 +688,7 @@ void launch_az_remaining(cudaStream_t st, const CollectBuffers& b) {
 // then runs the lockstep path.
 bool launch_mcts_persistent(cudaStream_t st, const MctsArgs& a, const PolicyDev& p, const int32_t* live, const int32_t* n_live, int64_t max_n) {
     if (p.generic || a.max_expand_depth != 1 || p.n_perms > 0 || max_n < 1) return false;
-    if (p.E % (PM_CS * 4) || p.E > 1024 || (p.H != 128 && p.H != 256) || p.A > 4) return false;
+    if (p.E % (PM_CS * 4) || p.E > PM_CS * PM_MAX_EC || (p.H != 128 && p.H != 256) || p.A > 4) return false;
     const PmLayout L = pm_layout(p.E, p.H, p.obs_size);
     if (L.total > 227 * 1024) return false;
     int dev = 0;
@@ -689,10 +707,21 @@ bool launch_mcts_persistent(cudaStream_t st, const MctsArgs& a, const PolicyDev&
     if (cudaOccupancyMaxActiveClusters(&nc, k_mcts_persistent, &cfg) != cudaSuccess) { cudaGetLastError(); nc = 0; }
     if (nc > sms / PM_CS) nc = sms / PM_CS;
     if (nc < 1) return false;
-    int ncl = (int)(max_n < nc ? max_n : nc);
-    if ((max_n + ncl - 1) / ncl > PM_TPC) return false;      // too many trees for the clusters that fit: lockstep path
-    cfg.gridDim = dim3((unsigned)(ncl * PM_CS));
-    if (cudaLaunchKernelEx(&cfg, k_mcts_persistent, a, p, live, n_live) != cudaSuccess) { cudaGetLastError(); return false; }
-    TWR_COUNT_LAUNCH();
+    // Searches cost the same whether a cluster holds 1 or PM_TPC trees (latency bound), so the batch is cut into as few
+    // launches as the resident clusters allow; beyond a few thousand trees the lockstep path's batched forward wins.
+    const int64_t room = (int64_t)nc * PM_TPC;
+    const int n_launch = (int)((max_n + room - 1) / room);
+    if (n_launch > 4) return false;
+    const int slice = (int)((max_n + n_launch - 1) / n_launch);
+    if (getenv("TWISTERL_B200_MCTS_DEBUG"))
+        fprintf(stderr, "[mcts] persistent: %lld trees, %d resident clusters of %d CTAs (%zu B shared memory), %d launch(es) of <= %d trees\n",
+                (long long)max_n, nc, PM_CS, L.total, n_launch, slice);
+    for (int i = 0; i < n_launch; ++i) {
+        const int pos0 = i * slice;
+        const int ncl = slice < nc ? slice : nc;
+        cfg.gridDim = dim3((unsigned)(ncl * PM_CS));
+        if (cudaLaunchKernelEx(&cfg, k_mcts_persistent, a, p, live, n_live, pos0, slice) != cudaSuccess) { cudaGetLastError(); return false; }
+        TWR_COUNT_LAUNCH();
+    }
     return true;
 }

@@ -168,6 +168,7 @@ struct MctsArgs {
     const float4* logits; const float* values;           // forward outputs, indexed by leaf-batch position
     int32_t* cur_node; float* cur_value; uint8_t* active; // per env, current simulation
     int32_t* trace;   // optional [n_sims][B][2] (parity API): leaf of the descent, node the value was backed up from
+    long long* dbg;   // optional [8] cycle counters of cluster 0 / CTA 0 / thread 0 of k_mcts_persistent (TWISTERL_B200_MCTS_DEBUG)
 };
 void launch_mcts_begin(cudaStream_t s, const MctsArgs& a, const int32_t* live, const int32_t* n_live, int64_t max_n);
 void launch_mcts_expand(cudaStream_t s, const MctsArgs& a, int mode, int sim, int d, int which, int64_t max_n);

@@ -74,6 +74,16 @@ __device__ __forceinline__ void backprop(const MctsPool& m, int e, int64_t base,
     }
 }
 
+// the same with the lanes of a warp taking one path node each (the nodes of a path are distinct); every lane of the warp
+// calls it with the same arguments
+__device__ __forceinline__ void backprop_warp(const MctsPool& m, int e, int64_t base, int node, int len, float v, int lane) {
+    if (len < 0) {
+        if (lane == 0) for (int b = node; b >= 0; b = m.parent[base + b]) bump(m, base + b, v);
+        return;
+    }
+    for (int k = lane; k < len; k += 32) bump(m, base + m.path[(int64_t)k * m.B + e], v);
+}
+
 // Policy::predict's epilogue (nn/policy.rs:43-47) on raw logits
 __device__ __forceinline__ void masked_probs(const float4 raw, uint32_t mask, int A, float pr[4]) {
     const float l[4] = {raw.x, raw.y, raw.z, raw.w};
@@ -407,12 +417,15 @@ __global__ void __launch_bounds__(256) k_az_remaining(CollectBuffers b) {
 // oracle's arithmetic), split along the embedding features: CTA r keeps features [r*EC, (r+1)*EC) of the embedding table
 // and the matching ROWS of the common Linear.  A simulation is four short phases separated by cluster barriers, with no
 // launch, no global operand traffic and no inter-cluster dependency:
-//   A  owner thread of each tree (tree j -> CTA j % PM_CS): UCB descent; the leaf's 16-byte state goes to every CTA (DSMEM)
+//   A  owner WARP of each tree (tree j -> warp j / PM_CS of CTA j % PM_CS): UCB descent, one lane per child (the
+//      divisions of the UCB expression cost as much as the L2 round trip of a level when one thread does all four);
+//      the leaf's 16-byte state goes to every CTA (DSMEM)
 //   B  every CTA: its EC features of h1 = relu(bias + sum of table rows) for every leaf (local), then its K-slice of
 //      W1.h1 for ALL H columns (the weights of a column cached in registers), sent to the CTA that OWNS the leaf's tree
 //      (distributed shared memory moves 17-21 B/clk: the partial sums are half the bytes an all-gather of h1 would be)
 //   C  owner CTA, local: h2 = relu(sum of the PM_CS partial sums + b1) and the five head dot products of its trees
-//   D  owner thread: Policy::predict's epilogue, expand, child draw and backup exactly as expand_body does
+//   D  owner warp: Policy::predict's epilogue, expand, child draw (lane 0) and the backup, one lane per path node,
+//      exactly as expand_body does
 // -- two cluster barriers per simulation (after A and after B).
 // Trees stay in the global node pool (L2-resident: 512 trees x 160 KB), touched by one thread each.
 constexpr int PM_CS = 8;
@@ -420,7 +433,7 @@ constexpr int PM_THREADS = 256;
 constexpr int PM_TPC = 40;
 constexpr int PM_MAX_EC = 64;        // E <= 512
 
-struct PmLayout { int E, H, EC, obs; size_t w1s, tab, h1s, b1s, embb, headw, part2, red, cells, flag, total; };
+struct PmLayout { int E, H, EC, obs; size_t w1s, tab, h1s, b1s, embb, headw, part2, hbuf, red, cells, flag, total; };
 __host__ __device__ inline PmLayout pm_layout(int E, int H, int obs) {
     PmLayout l;
     l.E = E; l.H = H; l.obs = obs; l.EC = E / PM_CS;
@@ -430,9 +443,10 @@ __host__ __device__ inline PmLayout pm_layout(int E, int H, int obs) {
     l.h1s = o; o += sizeof(float) * (size_t)PM_TPC * l.EC;               // this CTA's h1 slice of every leaf
     l.b1s = o; o += sizeof(float) * (size_t)H;
     l.embb = o; o += sizeof(float) * (size_t)l.EC;
-    l.headw = o; o += sizeof(float) * (size_t)H * 8;
+    l.headw = o; o += sizeof(float) * (size_t)5 * (H + 8);                   // [output][column], rows padded by 8 floats
     l.part2 = o; o += sizeof(float) * (size_t)(PM_TPC / PM_CS) * PM_CS * H;   // partial h2 of MY trees (all H columns) from every rank
-    l.red = o; o += sizeof(float) * (size_t)(PM_TPC / PM_CS) * 8 * 8;         // head sums of my trees per warp
+    l.hbuf = o; o += sizeof(float) * (size_t)(PM_TPC / PM_CS) * H;            // h2 of my trees
+    l.red = o; o += sizeof(float) * (size_t)(PM_TPC / PM_CS) * 8;             // logits / value of my trees
     l.cells = o; o += sizeof(uint4) * (size_t)PM_TPC;
     l.flag = o; o += sizeof(int) * (size_t)PM_TPC;
     l.total = (o + 15) & ~(size_t)15;
@@ -466,6 +480,7 @@ k_mcts_persistent(MctsArgs a, PolicyDev p, const int32_t* __restrict__ live, con
     float* headw = reinterpret_cast<float*>(pm_smem + L.headw);
     float* part2 = reinterpret_cast<float*>(pm_smem + L.part2);
     float* red = reinterpret_cast<float*>(pm_smem + L.red);
+    float* hbuf = reinterpret_cast<float*>(pm_smem + L.hbuf);
     uint4* leaf_cells = reinterpret_cast<uint4*>(pm_smem + L.cells);
     int* leaf_flag = reinterpret_cast<int*>(pm_smem + L.flag);
     const int tid = threadIdx.x;
@@ -478,8 +493,8 @@ k_mcts_persistent(MctsArgs a, PolicyDev p, const int32_t* __restrict__ live, con
     for (int i = tid; i < p.obs_size * EC; i += PM_THREADS) { const int r = i / EC, f = i % EC; tab[i] = p.emb[(size_t)r * E + rank * EC + f]; }
     for (int i = tid; i < H; i += PM_THREADS) {
         b1s[i] = p.b1[i];
-        for (int o = 0; o < 4; ++o) headw[i * 8 + o] = o < p.A ? p.wa[(size_t)i * p.A + o] : 0.0f;
-        headw[i * 8 + 4] = p.wv[i]; headw[i * 8 + 5] = 0.f; headw[i * 8 + 6] = 0.f; headw[i * 8 + 7] = 0.f;
+        for (int o = 0; o < 4; ++o) headw[o * (H + 8) + i] = o < p.A ? p.wa[(size_t)i * p.A + o] : 0.0f;
+        headw[4 * (H + 8) + i] = p.wv[i];
     }
     for (int i = tid; i < EC; i += PM_THREADS) embb[i] = p.emb_b[rank * EC + i];
     __syncthreads();
@@ -496,8 +511,9 @@ k_mcts_persistent(MctsArgs a, PolicyDev p, const int32_t* __restrict__ live, con
     const int per = (n + ncl - 1) / ncl;
     const int first = pos0 + (int)pm_cluster_id() * per;
     const int nt = max(0, min(per, pos0 + n - first));     // host guarantees per <= PM_TPC
-    const int j_own = tid * PM_CS + (int)rank;
-    const bool owner = tid < PM_TPC / PM_CS && j_own < nt;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int j_own = warp * PM_CS + (int)rank;            // the tree this WARP owns (slot `warp` of this CTA)
+    const bool owner = warp < PM_TPC / PM_CS && j_own < nt;    // warp-uniform
     int e = 0, node = 0, len = 1;
     int64_t base = 0;
     bool need = false;
@@ -505,54 +521,70 @@ k_mcts_persistent(MctsArgs a, PolicyDev p, const int32_t* __restrict__ live, con
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     pm_cluster_sync();
 
+    const bool prof = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;   // warp 0 / lane 0: an owner warp's view of every phase
+    long long tA = 0, tS1 = 0, tB = 0, tS2 = 0, tC = 0, tD = 0, t0 = 0;
     for (int sim = -1; sim < a.n_sims; ++sim) {
-        // ================= A: descent (owner threads) =================
+        if (prof) t0 = clock64();
+        // ================= A: descent (owner warps; lane k evaluates child k) =================
         if (owner) {
             need = false;
             if (sim < 0) {                                  // k_mcts_begin: the root (search.rs:112-128), always evaluated
-                m.cells[base] = a.env_cells[e]; m.meta[base] = a.env_meta[e];
-                m.parent[base] = -1;
-                m.node[base] = make_uint4(1u, __float_as_uint(0.0f), __float_as_uint(0.0f), link_pack(0, 0, 0xFF));
-                m.n_nodes[e] = 1;
-                m.path[e] = 0; m.path_len[e] = 1;
+                if (lane == 0) {
+                    m.cells[base] = a.env_cells[e]; m.meta[base] = a.env_meta[e];
+                    m.parent[base] = -1;
+                    m.node[base] = make_uint4(1u, __float_as_uint(0.0f), __float_as_uint(0.0f), link_pack(0, 0, 0xFF));
+                    m.n_nodes[e] = 1;
+                    m.path[e] = 0; m.path_len[e] = 1;
+                }
                 node = 0; len = 1; need = true;
-            } else {                                        // select_body without the leaf-batch compaction
+            } else {                                        // select_body: next() = argmax UCB, strict '>', first child wins a tie
                 node = 0; len = 1;
-                uint4 cur = m.node[base];
+                uint4 cur = m.node[base];                   // every lane reads the root record (one broadcast load)
                 while (link_nch(cur.w) > 0) {
                     const int fc = link_first(cur.w), nch = link_nch(cur.w);
                     const float sq = sqrtf((float)cur.x);
-                    uint4 ch[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (k < nch) ch[k] = m.node[base + fc + k];
-                    int best = -1;
-                    float best_ucb = -INFINITY;
-                    uint4 best_rec = cur;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (k < nch) {
-                            const uint32_t nv = ch[k].x;
-                            const float q = nv == 0u ? 0.0f : __fdiv_rn(__uint_as_float(ch[k].y), (float)nv);
-                            const float ucb = __fadd_rn(q, __fmul_rn(__fmul_rn(a.C, __fdiv_rn(sq, __fadd_rn((float)nv, 1.0f))), __uint_as_float(ch[k].z)));
-                            if (ucb > best_ucb) { best = fc + k; best_ucb = ucb; best_rec = ch[k]; }
-                        }
+                    uint4 ch = cur;
+                    float ucb = -INFINITY;
+                    if (lane < nch) {
+                        ch = m.node[base + fc + lane];
+                        const uint32_t nv = ch.x;
+                        const float q = nv == 0u ? 0.0f : __fdiv_rn(__uint_as_float(ch.y), (float)nv);
+                        ucb = __fadd_rn(q, __fmul_rn(__fmul_rn(a.C, __fdiv_rn(sq, __fadd_rn((float)nv, 1.0f))), __uint_as_float(ch.z)));
+                        if (!(ucb > -INFINITY)) ucb = -INFINITY;           // NaN / -inf never wins (search.rs:85: `>` is false)
                     }
-                    if (best < 0) break;
-                    node = best; cur = best_rec;
-                    if (len >= 0) { if (len < TWR_MCTS_PATH) { m.path[(int64_t)len * m.B + e] = node; ++len; } else len = -1; }
+                    int bk = lane < nch ? lane : 99;
+                    float bu = ucb;
+#pragma unroll
+                    for (int d = 1; d < 4; d <<= 1) {       // max over lanes 0..3, smallest index on equal values
+                        const float ou = __shfl_xor_sync(0xffffffffu, bu, d);
+                        const int ok = __shfl_xor_sync(0xffffffffu, bk, d);
+                        if (ou > bu || (ou == bu && ok < bk)) { bu = ou; bk = ok; }
+                    }
+                    bk = __shfl_sync(0xffffffffu, bk, 0);
+                    bu = __shfl_sync(0xffffffffu, bu, 0);
+                    if (bk >= nch || !(bu > -INFINITY)) break;             // no child with a comparable UCB: stay (search.rs:89)
+                    cur.x = __shfl_sync(0xffffffffu, ch.x, bk); cur.y = __shfl_sync(0xffffffffu, ch.y, bk);
+                    cur.z = __shfl_sync(0xffffffffu, ch.z, bk); cur.w = __shfl_sync(0xffffffffu, ch.w, bk);
+                    node = fc + bk;
+                    if (len >= 0) {
+                        if (len < TWR_MCTS_PATH) { if (lane == 0) m.path[(int64_t)len * m.B + e] = node; ++len; } else len = -1;
+                    }
                 }
-                if (a.trace) { a.trace[((int64_t)sim * m.B + e) * 2] = node; a.trace[((int64_t)sim * m.B + e) * 2 + 1] = node; }
+                if (a.trace && lane == 0) { a.trace[((int64_t)sim * m.B + e) * 2] = node; a.trace[((int64_t)sim * m.B + e) * 2 + 1] = node; }
                 const EnvState s = node_state(m, base + node);
-                if (env_is_final(a.env, s) || m.n_nodes[e] + m.A > m.P) backprop(m, e, base, node, len, env_reward(a.env, s));
+                __syncwarp();                               // lane 0's path stores are read by the other lanes in the backup
+                if (env_is_final(a.env, s) || m.n_nodes[e] + m.A > m.P) backprop_warp(m, e, base, node, len, env_reward(a.env, s), lane);
                 else need = true;
             }
-            const uint4 cells = need ? m.cells[base + node] : make_uint4(0, 0, 0, 0);
-            for (uint32_t r = 0; r < PM_CS; ++r) {          // the leaf's state to every CTA of the cluster
-                *pm_remote(leaf_cells + j_own, r) = cells;
-                *pm_remote(leaf_flag + j_own, r) = need ? 1 : 0;
+            if (lane < PM_CS) {                             // the leaf's state to every CTA of the cluster: lane r -> CTA r
+                const uint4 cells = need ? m.cells[base + node] : make_uint4(0, 0, 0, 0);
+                *pm_remote(leaf_cells + j_own, (uint32_t)lane) = cells;
+                *pm_remote(leaf_flag + j_own, (uint32_t)lane) = need ? 1 : 0;
             }
         }
+        if (prof) { const long long t = clock64(); tA += t - t0; t0 = t; }
         pm_cluster_sync();
+        if (prof) { const long long t = clock64(); tS1 += t - t0; t0 = t; }
         // ================= B: embedding slice (local), then this K-slice of W1.h1 for every column =================
         for (int idx = tid; idx < nt * (EC / 4); idx += PM_THREADS) {
             const int j = idx / (EC / 4), f4 = (idx % (EC / 4)) * 4;
@@ -588,64 +620,82 @@ k_mcts_persistent(MctsArgs a, PolicyDev p, const int32_t* __restrict__ live, con
             // to the tree's owner CTA: part2[tree slot j / PM_CS][this rank][col]
             pm_remote(part2, (uint32_t)(j % PM_CS))[((size_t)(j / PM_CS) * PM_CS + rank) * H + col] = acc;
         }
+        if (prof) { const long long t = clock64(); tB += t - t0; t0 = t; }
         pm_cluster_sync();
+        if (prof) { const long long t = clock64(); tS2 += t - t0; t0 = t; }
         // ================= C: h2 and the heads of MY trees (local) =================
         {
-            const int wpt = H / 32;                                             // warps per tree: 8 (H = 256) or 4 (H = 128)
             const int my_slots = (nt - (int)rank + PM_CS - 1) / PM_CS;          // trees this CTA owns (slot jl <-> tree jl*PM_CS + rank)
-            for (int jb = 0; jb < my_slots; jb += nlg) {                        // same trip count for every thread: shuffles below
-                const int jl = jb + lg;
-                const bool on = jl < my_slots && leaf_flag[jl * PM_CS + rank];
+            // C1: h2 of my trees, thread = column (independent loads per slot)
+            for (int jl = lg; jl < my_slots; jl += nlg) {
                 float h = 0.0f;
-                if (on) {
+                if (leaf_flag[jl * PM_CS + rank]) {
                     const float* q = part2 + (size_t)jl * PM_CS * H + col;
 #pragma unroll
                     for (int r = 0; r < PM_CS; ++r) h += q[r * H];               // the K-slices in ascending order
                     h = fmaxf(h + b1s[col], 0.f);
                 }
-                float pr[5];
-#pragma unroll
-                for (int o = 0; o < 5; ++o) pr[o] = h * headw[col * 8 + o];
-                for (int d = 16; d > 0; d >>= 1) {
-#pragma unroll
-                    for (int o = 0; o < 5; ++o) pr[o] += __shfl_xor_sync(0xffffffffu, pr[o], d);
-                }
-                if ((tid & 31) == 0 && jl < my_slots) {
-#pragma unroll
-                    for (int o = 0; o < 5; ++o) red[((size_t)jl * 8 + (col >> 5)) * 8 + o] = pr[o];
-                }
+                hbuf[jl * H + col] = h;
             }
             __syncthreads();
-            // ================= D: predict epilogue, expand, child draw, backup (owner threads) =================
+            // C2: the 5 head dot products of every slot: 8 lanes per dot product, 3 shuffle steps
+            {
+                const int dsel = tid >> 3, part = tid & 7;                      // dot product (slot, output) and its eighth of the columns
+                const int slot = dsel / 5, o = dsel % 5;
+                float acc = 0.0f;
+                if (slot < my_slots) {                                           // columns part, part + 8, ..: conflict-free rows of
+                    const float* hb = hbuf + slot * H;                           // hbuf and of the padded, transposed head weights
+                    const float* hw = headw + o * (H + 8);
+                    for (int c = part; c < H; c += 8) acc = fmaf(hb[c], hw[c], acc);
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (part == 0 && slot < my_slots) red[slot * 8 + o] = acc;
+            }
+            __syncthreads();
+            if (prof) { const long long t = clock64(); tC += t - t0; t0 = t; }
+            // ================= D: predict epilogue, expand, child draw (lane 0), backup (owner warps) =================
             if (owner && need) {
-                float l[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int w = 0; w < wpt; ++w) {
+                int child = node;
+                float v = 0.0f;
+                if (lane == 0) {
+                    float l[5];
 #pragma unroll
-                    for (int o = 0; o < 5; ++o) l[o] += red[((size_t)tid * 8 + w) * 8 + o];
+                    for (int o = 0; o < 5; ++o) l[o] = red[warp * 8 + o];
+                    const float4 raw = make_float4(l[0] + (p.A > 0 ? p.ba[0] : 0.f), l[1] + (p.A > 1 ? p.ba[1] : 0.f), l[2] + (p.A > 2 ? p.ba[2] : 0.f),
+                                                   l[3] + (p.A > 3 ? p.ba[3] : 0.f));
+                    v = l[4] + p.bv[0];
+                    const EnvState s = node_state(m, base + node);
+                    float pr[4], cp[4];
+                    masked_probs(raw, env_masks(a.env, s), m.A, pr);
+                    int nch;
+                    const int fc = expand(m, a.env, e, base, node, pr, cp, nch);
+                    if (sim >= 0) {                             // next_sample (search.rs:94-100)
+                        uint32_t w[4];
+                        philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)(a.t * (a.n_sims + 1) + sim), TWR_RNG_MCTS, a.cid, k0, k1, w);
+                        child = nch > 0 ? fc + weighted_index(cp, nch, u32_to_unit_f32(w[0])) : node;
+                        if (a.trace) a.trace[((int64_t)sim * m.B + e) * 2 + 1] = child;
+                        if (child != node && len >= 0 && len < TWR_MCTS_PATH) m.path[(int64_t)len * m.B + e] = child;
+                    }
                 }
-                const float4 raw = make_float4(l[0] + (p.A > 0 ? p.ba[0] : 0.f), l[1] + (p.A > 1 ? p.ba[1] : 0.f), l[2] + (p.A > 2 ? p.ba[2] : 0.f),
-                                               l[3] + (p.A > 3 ? p.ba[3] : 0.f));
-                const float v = l[4] + p.bv[0];
-                const EnvState s = node_state(m, base + node);
-                float pr[4], cp[4];
-                masked_probs(raw, env_masks(a.env, s), m.A, pr);
-                int nch;
-                const int fc = expand(m, a.env, e, base, node, pr, cp, nch);
-                if (sim >= 0) {                                 // next_sample + backup (search.rs:94-100, 45-53)
-                    uint32_t w[4];
-                    philox4x32_10(a.ids.gid((uint32_t)e), (uint32_t)(a.t * (a.n_sims + 1) + sim), TWR_RNG_MCTS, a.cid, k0, k1, w);
-                    const int child = nch > 0 ? fc + weighted_index(cp, nch, u32_to_unit_f32(w[0])) : node;
-                    if (a.trace) a.trace[((int64_t)sim * m.B + e) * 2 + 1] = child;
-                    if (child != node && len >= 0) { if (len < TWR_MCTS_PATH) { m.path[(int64_t)len * m.B + e] = child; ++len; } else len = -1; }
-                    backprop(m, e, base, child, len, v);
+                if (sim >= 0) {                                 // backup (search.rs:45-53), one lane per path node
+                    child = __shfl_sync(0xffffffffu, child, 0);
+                    v = __shfl_sync(0xffffffffu, v, 0);
+                    if (child != node && len >= 0) { if (len < TWR_MCTS_PATH) ++len; else len = -1; }
+                    __syncwarp();
+                    backprop_warp(m, e, base, child, len, v, lane);
                 }
+                __syncwarp();                                   // lane 0's expansion and every lane's backup are read by the whole warp in the next A
             }
         }
+        if (prof) { const long long t = clock64(); tD += t - t0; t0 = t; }
         // The owner's global writes of D are read by the same thread in the next A.  Shared-memory reuse needs no third
         // barrier: the next A overwrites (remotely) only the leaf slots of the WRITER's own trees, which no other CTA reads
         // after barrier 2 (C reads the flags of its own trees only); h1s / part2 are rewritten after the next barrier 1.
     }
-    if (owner) m.path_len[e] = len;
+    if (owner && lane == 0) m.path_len[e] = len;
+    if (prof) { a.dbg[0] = tA; a.dbg[1] = tS1; a.dbg[2] = tB; a.dbg[3] = tS2; a.dbg[4] = tC; a.dbg[5] = tD; a.dbg[6] = nt; a.dbg[7] = a.n_sims + 1; }
     pm_cluster_sync();                                      // no CTA may exit while a peer can still write into its shared memory
 }
 
@@ -716,12 +766,26 @@ bool launch_mcts_persistent(cudaStream_t st, const MctsArgs& a, const PolicyDev&
     if (getenv("TWISTERL_B200_MCTS_DEBUG"))
         fprintf(stderr, "[mcts] persistent: %lld trees, %d resident clusters of %d CTAs (%zu B shared memory), %d launch(es) of <= %d trees\n",
                 (long long)max_n, nc, PM_CS, L.total, n_launch, slice);
+    MctsArgs args = a;
+    static long long* d_dbg = nullptr;
+    if (getenv("TWISTERL_B200_MCTS_DEBUG")) {
+        if (!d_dbg) cudaMalloc(reinterpret_cast<void**>(&d_dbg), 8 * sizeof(long long));
+        args.dbg = d_dbg;
+    }
     for (int i = 0; i < n_launch; ++i) {
         const int pos0 = i * slice;
         const int ncl = slice < nc ? slice : nc;
         cfg.gridDim = dim3((unsigned)(ncl * PM_CS));
-        if (cudaLaunchKernelEx(&cfg, k_mcts_persistent, a, p, live, n_live, pos0, slice) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (cudaLaunchKernelEx(&cfg, k_mcts_persistent, args, p, live, n_live, pos0, slice) != cudaSuccess) { cudaGetLastError(); return false; }
         TWR_COUNT_LAUNCH();
+    }
+    if (args.dbg) {
+        long long h[8];
+        cudaMemcpyAsync(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        const double n = h[7] > 0 ? (double)h[7] : 1.0;
+        fprintf(stderr, "[mcts] cycles per simulation (cluster 0, %lld trees): A descent %.0f | barrier %.0f | B embed+K-slice %.0f | barrier %.0f | C heads %.0f | D expand/backup %.0f\n",
+                h[6], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n);
     }
     return true;
 }

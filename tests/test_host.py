@@ -1,6 +1,7 @@
 """CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the host
 mirror keeps the reference's names / argument meaning / error behaviour, and the product fails loudly
 without a CUDA device.  No compute calls are made here."""
+import ctypes as C
 import re
 import sys
 from pathlib import Path
@@ -256,3 +257,38 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.split() == ["3", "30"], (r.stdout, r.stderr)   # 10 episodes x (2*1 + 1) records
+
+
+def test_safetensors_reader_rejects_corrupt_headers(tmp_path):
+    """The native checkpoint reader treats the header as untrusted file content: negative / overflowing dimensions,
+    offsets outside the file and shape/offset mismatches come back as TWR_ERR_INVALID (never an exception or a wild
+    allocation across the C boundary).  Parsing happens before the engine is touched, so a placeholder handle is enough."""
+    import json
+    import struct
+    from twisterl_b200 import _lib
+    L = _lib.load()
+    fake_engine = C.create_string_buffer(64)
+
+    def write(name, header, payload=b"\0" * 64):
+        js = json.dumps(header).encode()
+        p = tmp_path / name
+        p.write_bytes(struct.pack("<Q", len(js)) + js + payload)
+        return str(p).encode()
+
+    cases = {
+        "neg.safetensors": {"embeddings.weight": {"dtype": "F32", "shape": [-4, -4], "data_offsets": [0, 64]}},
+        "huge.safetensors": {"embeddings.weight": {"dtype": "F32", "shape": [2 ** 31, 2 ** 31], "data_offsets": [0, 64]}},
+        "overflow.safetensors": {"embeddings.weight": {"dtype": "F32", "shape": [2 ** 30, 2 ** 30, 2 ** 30], "data_offsets": [0, 64]}},
+        "past_end.safetensors": {"embeddings.weight": {"dtype": "F32", "shape": [4, 4], "data_offsets": [1 << 40, (1 << 40) + 64]}},
+        "reversed.safetensors": {"embeddings.weight": {"dtype": "F32", "shape": [4, 4], "data_offsets": [64, 0]}},
+        "mismatch.safetensors": {"embeddings.weight": {"dtype": "F32", "shape": [4, 5], "data_offsets": [0, 64]}},
+        "f16.safetensors": {"embeddings.weight": {"dtype": "F16", "shape": [4, 8], "data_offsets": [0, 64]}},
+    }
+    for name, hdr in cases.items():
+        h = C.c_void_p()
+        rc = L.twr_policy_create_from_safetensors(fake_engine, write(name, hdr), None, 0, 0, None, None, 0, C.byref(h))
+        assert rc in (-1, -2) and not h.value, (name, rc)
+        assert L.twr_last_error(), name
+    (tmp_path / "short.safetensors").write_bytes(b"\x10\0\0\0\0\0\0\0{")
+    h = C.c_void_p()
+    assert L.twr_policy_create_from_safetensors(fake_engine, str(tmp_path / "short.safetensors").encode(), None, 0, 0, None, None, 0, C.byref(h)) == -1

@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <string>
 #include <vector>
@@ -110,12 +111,24 @@ int load_file(const char* path, std::map<std::string, Tensor>* out) {
     std::map<std::string, Entry> hdr;
     if (!parse_header(js, &hdr)) { std::fclose(f); return twr_set_error(TWR_ERR_INVALID, "malformed safetensors header"); }
     const long data0 = 8 + (long)hlen;
+    // the header is file content, not trusted input: every dimension, product and offset is range-checked before it sizes
+    // an allocation or a read
+    std::fseek(f, 0, SEEK_END);
+    const int64_t data_bytes = (int64_t)std::ftell(f) - data0;
     for (const auto& kv : hdr) {
         const Entry& e = kv.second;
         if (e.dtype != "F32") { std::fclose(f); return twr_set_error(TWR_ERR_UNSUPPORTED, ("tensor " + kv.first + " is " + e.dtype + ": only F32 checkpoints are read").c_str()); }
         int64_t n = 1;
-        for (int64_t d : e.shape) n *= d;
-        if (e.end - e.begin != n * 4 || n < 0) { std::fclose(f); return twr_set_error(TWR_ERR_INVALID, ("tensor " + kv.first + ": data_offsets do not match the shape").c_str()); }
+        bool ok = e.shape.size() <= 8;
+        for (int64_t d : e.shape) {
+            if (d < 0 || d >= (1ll << 31) || (d > 0 && n > (1ll << 40) / d)) { ok = false; break; }
+            n *= d;
+        }
+        if (!ok || n > (1ll << 32)) { std::fclose(f); return twr_set_error(TWR_ERR_INVALID, ("tensor " + kv.first + ": shape out of range").c_str()); }
+        if (e.begin < 0 || e.end < e.begin || e.end > data_bytes || e.end - e.begin != n * 4) {
+            std::fclose(f);
+            return twr_set_error(TWR_ERR_INVALID, ("tensor " + kv.first + ": data_offsets do not match the shape / file size").c_str());
+        }
         Tensor t;
         t.shape = e.shape;
         t.data.resize((size_t)n);
@@ -140,10 +153,26 @@ std::vector<float> transpose(const Tensor& t) {
 
 }  // namespace
 
+static int create_from_safetensors(twr_engine* e, const char* path, const int32_t* obs_shape, int32_t obs_shape_len,
+                                   int32_t conv_dim, const int32_t* obs_perms, const int32_t* act_perms, int32_t n_perms,
+                                   twr_policy** out);
+
 extern "C" int twr_policy_create_from_safetensors(twr_engine* e, const char* path, const int32_t* obs_shape, int32_t obs_shape_len,
                                                   int32_t conv_dim, const int32_t* obs_perms, const int32_t* act_perms, int32_t n_perms,
                                                   twr_policy** out) {
     if (!e || !path || !out) return twr_set_error(TWR_ERR_INVALID, "NULL argument");
+    try {                                                 // no C++ exception may cross the C boundary
+        return create_from_safetensors(e, path, obs_shape, obs_shape_len, conv_dim, obs_perms, act_perms, n_perms, out);
+    } catch (const std::exception& ex) {
+        return twr_set_error(TWR_ERR_INVALID, (std::string("safetensors checkpoint: ") + ex.what()).c_str());
+    } catch (...) {
+        return twr_set_error(TWR_ERR_INVALID, "safetensors checkpoint: unexpected error");
+    }
+}
+
+static int create_from_safetensors(twr_engine* e, const char* path, const int32_t* obs_shape, int32_t obs_shape_len,
+                                   int32_t conv_dim, const int32_t* obs_perms, const int32_t* act_perms, int32_t n_perms,
+                                   twr_policy** out) {
     std::map<std::string, Tensor> sd;
     int rc = load_file(path, &sd);
     if (rc) return rc;
@@ -179,6 +208,8 @@ extern "C" int twr_policy_create_from_safetensors(twr_engine* e, const char* pat
         if (W.shape.size() != 3 || W.shape[2] != 1 || obs_shape_len != 2 || !obs_shape || (conv_dim != 0 && conv_dim != 1))
             return twr_set_error(TWR_ERR_INVALID, "Conv1d checkpoint needs a 2-D obs_shape and conv_dim 0 or 1");
         const int64_t v = W.shape[0], n_in = W.shape[1];
+        if (obs_shape[0] < 1 || obs_shape[1] < 1 || obs_shape[0] > 65535 || obs_shape[1] > 65535 || v < 1 || n_in < 1 || v * obs_shape[1 - conv_dim] > (1 << 20))
+            return twr_set_error(TWR_ERR_INVALID, "Conv1d checkpoint: obs_shape / kernel sizes out of range");
         vectors.resize((size_t)(v * n_in));
         for (int64_t r = 0; r < n_in; ++r)
             for (int64_t k = 0; k < v; ++k) vectors[(size_t)(r * v + k)] = W.data[(size_t)(k * n_in + r)];
@@ -191,6 +222,8 @@ extern "C" int twr_policy_create_from_safetensors(twr_engine* e, const char* pat
         const Tensor& W = sd["embeddings.weight"];        // torch Linear [E][obs_size] -> vec_vectors[obs][E] = W.T
         vectors = transpose(W);
         bias = has("embeddings.bias") ? sd["embeddings.bias"].data : std::vector<float>((size_t)W.shape[0], 0.0f);
+        if ((int64_t)bias.size() != W.shape[0] || W.shape[0] < 1 || W.shape[1] < 1 || W.shape[1] >= 65536)
+            return twr_set_error(TWR_ERR_INVALID, "checkpoint: embeddings.weight / embeddings.bias sizes do not match");
         d.obs_size = (int32_t)W.shape[1]; d.emb_size = (int32_t)W.shape[0];
         d.obs_shape[0] = d.obs_size; d.obs_shape_len = 1; d.conv_dim = 0;
     }

@@ -19,6 +19,7 @@
 
 #include <cstdint>
 #include <map>
+#include <array>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -59,6 +60,18 @@ public:
     void synchronize() { check(twr_engine_synchronize(h_)); }
     void set_collect_id(uint32_t id) { check(twr_engine_set_collect_id(h_, id)); }   // pins the Philox streams of the next collect
     int64_t launch_count() const { return twr_engine_launch_count(h_); }
+
+    // ---- multi-GPU plumbing (one Engine per GPU, rank / world from the constructor): NCCL through the C ABI
+    static std::array<uint8_t, TWR_COMM_ID_BYTES> comm_unique_id() {      // rank 0 creates it; the host ships the bytes to every rank
+        std::array<uint8_t, TWR_COMM_ID_BYTES> id{};
+        check(twr_comm_unique_id(id.data()));
+        return id;
+    }
+    void comm_init(const std::array<uint8_t, TWR_COMM_ID_BYTES>& id) { check(twr_comm_init(h_, id.data())); }   // collective
+    // in-place sum / max over the ranks of a few host doubles (episodes, successes, reward sum, records, ...)
+    void allreduce_stats(std::vector<double>& stats, twr_reduce_op op = TWR_REDUCE_SUM) {
+        check(twr_allreduce_stats(h_, stats.data(), (int32_t)stats.size(), (int32_t)op));
+    }
 
 private:
     twr_engine* h_ = nullptr;
@@ -106,6 +119,8 @@ public:
     Policy& operator=(const Policy&) = delete;
     // in-place weight refresh (what sync_rs_policy rebuilds from scratch in the reference, rl/algorithm.py:91-93)
     void update(const PolicyWeights& w) { with_desc(w, [&](const twr_policy_desc& d) { check(twr_policy_update(h_, &d)); }); }
+    // rank `root`'s parameters into this policy on every rank (ncclBroadcast on the engine stream) + operand refresh
+    void broadcast_from(int root = 0) { check(twr_broadcast_weights(eng_->handle(), h_, root)); }
     twr_policy* handle() const { return h_; }
     Engine& engine() const { return *eng_; }
 

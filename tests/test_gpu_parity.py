@@ -717,3 +717,30 @@ def test_collect_host_large_uses_round_sized_sub_batches(eng):
     assert np.array_equal(arr["ep_len"], ref.ep_len)
     assert np.array_equal(arr["obs"][:R], ref.obs_array.astype(np.uint8)) and np.array_equal(arr["actions"][:R], ref.actions_array)
     assert np.array_equal(arr["logits"][:R], ref.logits_array) and np.array_equal(arr["rets"][:R], ref.additional_array("rets"))
+
+
+def test_two_engines_on_two_devices_in_one_process():
+    """Launch state (SM count, cluster residency, tensor maps of the operand images) is kept per device: two engines on two
+    GPUs of one process, used alternately, must each produce exactly what a lone engine produces."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import twisterl_b200 as tw
+    from parity import check_collect_against_oracle, make_policies
+    _, sd = trained15()
+    ospec = orc.puzzle_spec(4, 4, 6, 2, 256)
+    env = tw.env.Puzzle(4, 4, 6, 2, 256)
+    engs = [tw.Engine(device=d, precision=PRECISION, seed=77) for d in (0, 1)]
+    pols = [make_policies(sd, 256) for _ in engs]
+    outs = []
+    for rnd in range(2):                                             # alternate between the devices
+        for eng, (pol, opol) in zip(engs, pols):
+            eng.set_collect_id(5)
+            d = tw.collector.PPOCollector(3000, 0.995, 0.995, 1, engine=eng).collect(env, pol)
+            check_collect_against_oracle(d, ospec, opol, seed=77, collect_id=5, gamma=0.995, lam=0.995, tol=TOL, stride=37)
+            outs.append(d)
+    for d in outs[1:]:
+        assert np.array_equal(d.obs_array, outs[0].obs_array) and np.array_equal(d.logits_array, outs[0].logits_array)
+        assert np.array_equal(d.actions_array, outs[0].actions_array)
+    for (pol, _), eng in zip(pols, engs):
+        pol.release(); eng.close()

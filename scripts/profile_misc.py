@@ -33,6 +33,11 @@ acol = twc.AZCollector(4096, 50, 1.41, 1, 32, engine=eng)
 c = acol.collect_device(aenv, apol)
 print("az records", c.n_records)
 
+# the reference's AZ shape class (small batch): the persistent whole-search kernel
+pcol = twc.AZCollector(512, 200, 1.41, 1, 32, engine=eng)
+c = pcol.collect_device(aenv, apol)
+print("az (persistent search) records", c.n_records)
+
 # evaluate (single_solve loop) and MCTS-guided evaluate
 print("evaluate", tw.collector.evaluate(aenv, apol, 4096, False, 4, 0, 0, 1.41, 1, 32))
 

@@ -179,6 +179,7 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
     return TWR_OK;
 }
 
+static void mcts_release_fwd(twr_engine* e);
 static void free_collect_buffers(twr_engine* e) {
     CollectBuffers& b = e->buf;
     dev_free(b.cells); dev_free(b.meta); dev_free(b.live_a); dev_free(b.live_b); dev_free(b.n_live);
@@ -198,6 +199,7 @@ void twr_engine_destroy(twr_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     twr_comm_destroy(e);
+    mcts_release_fwd(e);
     free_collect_buffers(e);
     for (auto ev : e->ev) cudaEventDestroy(ev);
     dev_free(e->ep_len_id);
@@ -1257,25 +1259,40 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
 
 
 // ------------------------------------------------ batched MCTS driver (K6; also used by solve/evaluate) ---
-struct MctsMem {
-    Staging<uint4> cells, node; Staging<uint32_t> meta; Staging<int32_t> parent, n_nodes, fwd_list, fwd_env, fwd_count, cur_node, path, path_len, leaf_pos;
-    Staging<uint8_t> active; Staging<float> cur_value;
-    int alloc(int64_t B, int P, MctsPool* pool, MctsArgs* a) {
-        const size_t n = (size_t)B * (size_t)P;
+static void mcts_release(twr_engine* e);
+static void mcts_release_fwd(twr_engine* e) { mcts_release(e); }
+static void mcts_release(twr_engine* e) {
+    MctsCache& c = e->mcts;
+    dev_free(c.cells); dev_free(c.node); dev_free(c.meta); dev_free(c.parent); dev_free(c.n_nodes); dev_free(c.fwd_list);
+    dev_free(c.fwd_env); dev_free(c.fwd_count); dev_free(c.cur_node); dev_free(c.path); dev_free(c.path_len); dev_free(c.leaf_pos);
+    dev_free(c.active); dev_free(c.cur_value);
+    c.cap_nodes = 0; c.cap_B = 0;
+}
+
+// node pool of B trees x P nodes (+ per-env scratch) from the engine's cache, grown when a call needs more
+static int mcts_acquire(twr_engine* e, int64_t B, int P, MctsPool* pool, MctsArgs* a) {
+    if (P >= (1 << 20)) return fail(TWR_ERR_INVALID, "MCTS tree too large (num_mcts_searches * max_expand_depth must stay below 2^18)");
+    MctsCache& c = e->mcts;
+    const size_t n = (size_t)B * (size_t)P;
+    if (n > c.cap_nodes || B > c.cap_B) {
+        CU_TRY(cudaStreamSynchronize(e->stream));
+        const size_t nn = n > c.cap_nodes ? n : c.cap_nodes;
+        const int64_t nb = B > c.cap_B ? B : c.cap_B;
+        mcts_release(e);
         int rc;
-        if (P >= (1 << 20)) return fail(TWR_ERR_INVALID, "MCTS tree too large (num_mcts_searches * max_expand_depth must stay below 2^18)");
-        if ((rc = cells.alloc(n)) || (rc = meta.alloc(n)) || (rc = parent.alloc(n)) || (rc = node.alloc(n)) ||
-            (rc = n_nodes.alloc((size_t)B)) || (rc = fwd_list.alloc((size_t)B)) ||
-            (rc = fwd_env.alloc((size_t)B)) || (rc = fwd_count.alloc(2)) || (rc = cur_node.alloc((size_t)B)) ||
-            (rc = cur_value.alloc((size_t)B)) || (rc = active.alloc((size_t)B)) ||
-            (rc = path.alloc((size_t)B * TWR_MCTS_PATH)) || (rc = path_len.alloc((size_t)B)) || (rc = leaf_pos.alloc((size_t)B))) return rc;
-        pool->B = B; pool->P = P; pool->cells = cells.d; pool->meta = meta.d; pool->parent = parent.d;
-        pool->node = node.d; pool->n_nodes = n_nodes.d; pool->path = path.d; pool->path_len = path_len.d;
-        a->fwd_list = fwd_list.d; a->fwd_env = fwd_env.d; a->fwd_count = fwd_count.d; a->cur_node = cur_node.d;
-        a->cur_value = cur_value.d; a->active = active.d; a->leaf_pos = leaf_pos.d;
-        return TWR_OK;
+        if ((rc = dev_alloc(&c.cells, nn)) || (rc = dev_alloc(&c.meta, nn)) || (rc = dev_alloc(&c.parent, nn)) || (rc = dev_alloc(&c.node, nn)) ||
+            (rc = dev_alloc(&c.n_nodes, (size_t)nb)) || (rc = dev_alloc(&c.fwd_list, (size_t)nb)) || (rc = dev_alloc(&c.fwd_env, (size_t)nb)) ||
+            (rc = dev_alloc(&c.fwd_count, 2)) || (rc = dev_alloc(&c.cur_node, (size_t)nb)) || (rc = dev_alloc(&c.cur_value, (size_t)nb)) ||
+            (rc = dev_alloc(&c.active, (size_t)nb)) || (rc = dev_alloc(&c.path, (size_t)nb * TWR_MCTS_PATH)) ||
+            (rc = dev_alloc(&c.path_len, (size_t)nb)) || (rc = dev_alloc(&c.leaf_pos, (size_t)nb))) { mcts_release(e); return rc; }
+        c.cap_nodes = nn; c.cap_B = nb;
     }
-};
+    pool->B = B; pool->P = P; pool->cells = c.cells; pool->meta = c.meta; pool->parent = c.parent;
+    pool->node = c.node; pool->n_nodes = c.n_nodes; pool->path = c.path; pool->path_len = c.path_len;
+    a->fwd_list = c.fwd_list; a->fwd_env = c.fwd_env; a->fwd_count = c.fwd_count; a->cur_node = c.cur_node;
+    a->cur_value = c.cur_value; a->active = c.active; a->leaf_pos = c.leaf_pos;
+    return TWR_OK;
+}
 
 static int mcts_pool_nodes(int A, int n_sims, int med) { return 1 + A * (n_sims * (med > 1 ? med : 1) + 1); }
 
@@ -1332,14 +1349,13 @@ static int run_solve(twr_engine* e, const EnvParams& env, const PolicyDev& dev, 
     int rc;
     // num_mcts_searches > 0: every step's action distribution is predict_probs_mcts of the current state
     MctsArgs ma{};
-    MctsMem mem;
     Staging<float> mcts_probs; Staging<int32_t> mcts_vis;
     if (mo.n_sims > 0) {
         if (dev.n_perms > 0) return fail(TWR_ERR_UNSUPPORTED, "MCTS with twists (full_predict over all perms) is not implemented; the AZ trainer clears them (rl/az.py:24-26)");
         const int P = mcts_pool_nodes(dev.A, mo.n_sims, mo.max_expand_depth);
         if ((double)B * P >= 2147483647.0) return fail(TWR_ERR_INVALID, "MCTS node pool too large");
         ma.pool.A = dev.A;
-        if ((rc = mem.alloc(B, P, &ma.pool, &ma)) || (rc = mcts_probs.alloc((size_t)B * dev.A)) || (rc = mcts_vis.alloc((size_t)B * dev.A))) return rc;
+        if ((rc = mcts_acquire(e, B, P, &ma.pool, &ma)) || (rc = mcts_probs.alloc((size_t)B * dev.A)) || (rc = mcts_vis.alloc((size_t)B * dev.A))) return rc;
     }
     if ((rc = live_a.alloc((size_t)B)) || (rc = live_b.alloc((size_t)B)) || (rc = n_live.alloc((size_t)T + 2)) ||
         (rc = logits.alloc((size_t)B)) || (rc = values.alloc((size_t)B))) return rc;
@@ -1524,9 +1540,8 @@ static int mcts_probs_impl(twr_engine* e, const twr_policy* p, twr_envs* v, int3
     const int P = mcts_pool_nodes(dev.A, n_sims, max_expand_depth);
     if ((double)B * P >= 2147483647.0) return fail(TWR_ERR_INVALID, "MCTS node pool too large");
     MctsArgs a{};
-    MctsMem mem;
     a.pool.A = dev.A;
-    if ((rc = mem.alloc(B, P, &a.pool, &a))) return rc;
+    if ((rc = mcts_acquire(e, B, P, &a.pool, &a))) return rc;
     Staging<float4> logits; Staging<float> values, d_probs; Staging<int32_t> live, n_live, d_vis;
     if ((rc = logits.alloc((size_t)B)) || (rc = values.alloc((size_t)B)) || (rc = live.alloc((size_t)B)) || (rc = n_live.alloc(1)) ||
         (rc = d_probs.alloc((size_t)B * dev.A)) || (rc = d_vis.alloc((size_t)B * dev.A))) return rc;
@@ -1571,9 +1586,8 @@ int twr_az_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p,
     if ((double)B * P >= 2147483647.0) return fail(TWR_ERR_INVALID, "MCTS node pool too large (num_episodes * (1 + A*(n_sims*depth+1)) must be < 2^31)");
     if ((rc = ensure_collect_buffers(e, B, T, plan.env.N, B))) return rc;
     MctsArgs a{};
-    MctsMem mem;
     a.pool.A = plan.dev.A;
-    if ((rc = mem.alloc(B, P, &a.pool, &a))) return rc;
+    if ((rc = mcts_acquire(e, B, P, &a.pool, &a))) return rc;
     CollectBuffers& b = e->buf;
     cudaStream_t st = e->stream;
     e->has_last = false;

@@ -7,6 +7,16 @@
 #include <map>
 #include <vector>
 
+// MCTS working set of an engine (node pool + per-env scratch), kept between calls: AZ collects / MCTS-guided evaluation
+// re-allocating ~1 GB per call cost more in cudaMalloc / cudaFree (and their implicit synchronisation) than the searches
+struct MctsCache {
+    uint4* cells = nullptr; uint4* node = nullptr; uint32_t* meta = nullptr;
+    int32_t *parent = nullptr, *n_nodes = nullptr, *fwd_list = nullptr, *fwd_env = nullptr, *fwd_count = nullptr, *cur_node = nullptr,
+            *path = nullptr, *path_len = nullptr, *leaf_pos = nullptr;
+    uint8_t* active = nullptr; float* cur_value = nullptr;
+    size_t cap_nodes = 0; int64_t cap_B = 0;
+};
+
 struct twr_engine {
     int device = 0, precision = 0, rank = 0, world = 1;
     int tc_terms = 0;            // ForwardArgs::tc_terms of every tensor-core forward of this engine (0 = all split terms)
@@ -45,6 +55,7 @@ struct twr_engine {
     // NCCL plumbing (twr_comm.cu): communicator over the `world` engines of a job, device scratch for the stats reduction
     void* comm = nullptr;
     double* d_stats = nullptr;
+    MctsCache mcts;
 };
 
 struct twr_policy {

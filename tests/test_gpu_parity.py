@@ -744,3 +744,27 @@ def test_two_engines_on_two_devices_in_one_process():
         assert np.array_equal(d.actions_array, outs[0].actions_array)
     for (pol, _), eng in zip(pols, engs):
         pol.release(); eng.close()
+
+
+@pytest.mark.parametrize("E,H", [(256, 256), (768, 256), (1024, 128), (256, 128)])
+def test_forward_and_collect_other_layer_widths(eng, E, H):
+    """Embedding widths of 2, 6 and 8 chunk pairs and both common widths of the pair kernel (the shipped configs are all
+    E = 512): forward against the oracle on scrambled states, and a collect replayed record by record."""
+    import twisterl_b200 as tw
+    from parity import check_collect_against_oracle, make_policies
+    from twisterl_b200.env import EnvBatch
+    from twisterl_b200.nn import forward_batch
+    sd = synth_state_dict(13 + E + H, 256, E, H, 4)
+    pol, opol = make_policies(sd, 256, *transpose_twists(4))
+    st = scramble_states(np.random.default_rng(E), 300, 4, 4, 60)
+    b = EnvBatch(_spec(orc.puzzle_spec(4, 4, 1, 2, 256)), len(st), eng)
+    b.set_state(st)
+    perm = np.arange(len(st)) % 3 - 1                               # -1 (no twist), 0, 1
+    logits, values = forward_batch(eng, pol, b, perm_idx=perm)
+    ref = [opol.raw_predict(o, int(p)) for o, p in zip(obs_from_states(st).tolist(), perm)]
+    assert _close(logits, np.array([r[0] for r in ref]), TOL) and _close(values, np.array([r[1] for r in ref]), TOL)
+    ospec = orc.puzzle_spec(4, 4, 10, 2, 256)
+    eng.set_collect_id(3)
+    d = tw.collector.PPOCollector(700, 0.995, 0.995, 1, engine=eng).collect(tw.env.Puzzle(4, 4, 10, 2, 256), pol)
+    rep = check_collect_against_oracle(d, ospec, opol, seed=eng.seed, collect_id=3, gamma=0.995, lam=0.995, tol=TOL, stride=7)
+    assert rep["records"] > 500

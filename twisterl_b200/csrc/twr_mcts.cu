@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256) k_az_remaining(CollectBuffers b) {
 // src/twisterl/defaults.py:82-90).  The lockstep path above costs two dependent launches per simulation, and its forward
 // keeps 2-4 SMs busy on a 512-leaf batch: ~30 us per simulation, below the host.  Here ONE launch runs all simulations of
 // a search: a cluster of PM_CS CTAs owns up to PM_TPC trees and holds the policy STATIONARY in shared memory (fp32, the
-// oracle's arithmetic), split along the embedding features: CTA r keeps features [r*EC, (r+1)*EC) of the embedding table
+// reference's arithmetic), split along the embedding features: CTA r keeps features [r*EC, (r+1)*EC) of the embedding table
 // and the matching ROWS of the common Linear.  A simulation is four short phases separated by cluster barriers, with no
 // launch, no global operand traffic and no inter-cluster dependency:
 //   A  owner WARP of each tree (tree j -> warp j / PM_CS of CTA j % PM_CS): UCB descent, one lane per child (the

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <algorithm>
 #include <string>
@@ -1160,6 +1161,7 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
     e->buf.obs_u8 = u8 ? 1 : 0;
     e->buf.pack_misc = pack ? 1 : 0;
     std::vector<std::thread> stages;                    // one per sub-batch: waits for its copy, then rebuilds the packed fields
+    std::vector<std::function<void()>> deferred;        // stages whose thread could not be started: run on this thread at the end
     // TWISTERL_B200_E2E_TRACE=1: host-clock milestones of every sub-batch on stderr (ms since the call started)
     const bool trace = getenv("TWISTERL_B200_E2E_TRACE") != nullptr;
     const auto t_call = std::chrono::steady_clock::now();
@@ -1210,7 +1212,9 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
                 const twr_host_buffers d = *dst;
                 const float* rtab = reward_of_code;
                 double* t_exp = trace ? &tr_exp[k] : nullptr;
-                stages.emplace_back([ev, dev_id, at0, R, d, rtab, workers, t_exp, t_call]() {
+                // the rebuild of one sub-batch; a thread that cannot be started (resource limits) is run inline instead --
+                // no C++ exception may leave through the C boundary
+                auto stage = [ev, dev_id, at0, R, d, rtab, workers, t_exp, t_call]() {
                     cudaSetDevice(dev_id);
                     cudaEventSynchronize(ev);
                     auto span = [&](int64_t a, int64_t b) {
@@ -1220,12 +1224,14 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
                     const int64_t per = ((int64_t)R + workers - 1) / workers;
                     for (int w = 1; w < workers; ++w) {
                         const int64_t a = at0 + w * per, b = std::min<int64_t>(at0 + (int64_t)R, a + per);
-                        if (a < b) ws.emplace_back(span, a, b);
+                        if (a >= b) continue;
+                        try { ws.emplace_back(span, a, b); } catch (...) { span(a, b); }
                     }
                     span(at0, std::min<int64_t>(at0 + (int64_t)R, at0 + per));
                     for (auto& t : ws) t.join();
                     if (t_exp) *t_exp = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
-                });
+                };
+                try { stages.emplace_back(stage); } catch (...) { deferred.push_back(stage); }
             }
             at += (int64_t)R;
             lo += B;
@@ -1238,6 +1244,7 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
     rc = body();
     const double t_copies = trace ? now_ms() : 0.0;
     for (auto& t : stages) t.join();                    // every exit path: workers done, engine flags restored
+    for (auto& f : deferred) f();
     if (trace && !rc) {
         for (size_t k = 0; k < tr_done.size(); ++k) {
             float copy_ms = 0.f;

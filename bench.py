@@ -339,7 +339,10 @@ def run_ours(args, rank, local_rank, world):
                                               f"{time.perf_counter() - t0:.1f}s), C restatement of the Rust collector"}
     pol.release()
     if not args.no_extras:
-        extra = run_extras(args, torch, tw, twc, twn, eng, comm, stream, rank, world, pk)
+        try:
+            extra = run_extras(args, torch, tw, twc, twn, eng, comm, stream, rank, world, pk)
+        except Exception as exc:                                       # noqa: BLE001 -- the headline line is printed regardless
+            extra = [{"error": f"{type(exc).__name__}: {exc}"[:300]}]
         if rank == 0:
             line["extra"] = extra
     if rank == 0:
@@ -452,16 +455,24 @@ def run_extras(args, torch, tw, twc, twn, eng, comm, stream, rank, world, pk):
         pol.release()
         out.append(e)
 
-    ppo("puzzle8_ppo", "examples/ppo_puzzle8_v1.json PPO rollout (3x3, difficulty 32 = diff_max, depth budget 64), 65536 envs per GPU",
-        tw.env.Puzzle(3, 3, 32, 2, 256), orc.puzzle_spec(3, 3, 32, 2, 256), 81, 256, "puzzle8", 81, 65536, "weak")
-    ppo("gridworld_ppo", "examples/grid_world/ppo_grid_world_5x5_v1.json PPO rollout (5x5, max_steps 64, difficulty 10 = diff_max), 65536 envs per GPU",
-        tw.env.GridWorld(5, 5, 64, 10), orc.gridworld_spec(5, 5, 64, 10), 625, 128, "gridworld", 100, 65536, "weak")
-    az("puzzle8_az_100", "AlphaZero on puzzle8 (difficulty 8), 100 MCTS simulations per record, 65536 episodes per GPU", 65536, 100, 8)
-    az("puzzle8_az_1000", "AlphaZero on puzzle8 (difficulty 8), the reference's AZ defaults: 512 episodes x 1000 MCTS simulations (src/twisterl/defaults.py)",
-       512, 1000, 8)
+    def guarded(fn, *fa):
+        # an extra that fails (e.g. out of memory on a smaller device) must not take the headline line with it; the failure
+        # is the same on every rank (same shapes), so the ranks stay in step
+        try:
+            fn(*fa)
+        except Exception as exc:                                   # noqa: BLE001
+            out.append({"workload": fa[1], "error": f"{type(exc).__name__}: {exc}"[:300]})
+
+    guarded(ppo, "puzzle8_ppo", "examples/ppo_puzzle8_v1.json PPO rollout (3x3, difficulty 32 = diff_max, depth budget 64), 65536 envs per GPU",
+            tw.env.Puzzle(3, 3, 32, 2, 256), orc.puzzle_spec(3, 3, 32, 2, 256), 81, 256, "puzzle8", 81, 65536, "weak")
+    guarded(ppo, "gridworld_ppo", "examples/grid_world/ppo_grid_world_5x5_v1.json PPO rollout (5x5, max_steps 64, difficulty 10 = diff_max), 65536 envs per GPU",
+            tw.env.GridWorld(5, 5, 64, 10), orc.gridworld_spec(5, 5, 64, 10), 625, 128, "gridworld", 100, 65536, "weak")
+    guarded(az, "puzzle8_az_100", "AlphaZero on puzzle8 (difficulty 8), 100 MCTS simulations per record, 65536 episodes per GPU", 65536, 100, 8)
+    guarded(az, "puzzle8_az_1000", "AlphaZero on puzzle8 (difficulty 8), the reference's AZ defaults: 512 episodes x 1000 MCTS simulations (src/twisterl/defaults.py)",
+            512, 1000, 8)
     per_gpu = (1 << 20) // world
-    ppo("puzzle15_twists_1M", f"puzzle15 PPO rollout with the {{identity, transpose}} twist set, 1048576 envs in total ({per_gpu} per GPU), difficulty 128",
-        tw.env.Puzzle(4, 4, 128, 2, 256), orc.puzzle_spec(4, 4, 128, 2, 256), 256, 256, "puzzle15", 256, per_gpu, "strong", puzzle15_twists())
+    guarded(ppo, "puzzle15_twists_1M", f"puzzle15 PPO rollout with the {{identity, transpose}} twist set, 1048576 envs in total ({per_gpu} per GPU), difficulty 128",
+            tw.env.Puzzle(4, 4, 128, 2, 256), orc.puzzle_spec(4, 4, 128, 2, 256), 256, 256, "puzzle15", 256, per_gpu, "strong", puzzle15_twists())
     return out
 
 

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <functional>
 #include <map>
 #include <algorithm>
@@ -29,6 +30,18 @@ int fail(int code, const std::string& msg) {
     return code;
 }
 }  // namespace
+// No C++ exception may leave through the C boundary (std::bad_alloc of a host staging vector, std::system_error of a
+// thread): the exported functions whose bodies can throw run inside this guard.
+template <typename F>
+static int twr_guard(F&& body) {
+    try {
+        return body();
+    } catch (const std::exception& ex) {
+        return fail(TWR_ERR_INVALID, std::string("host-side failure: ") + ex.what());
+    } catch (...) {
+        return fail(TWR_ERR_INVALID, "host-side failure");
+    }
+}
 // error hook for the other translation units of the library (twr_safetensors.cpp)
 extern "C" int twr_set_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }
 namespace {
@@ -131,6 +144,7 @@ int twr_device_count(void) {
 }
 
 int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
+    return twr_guard([&]() -> int {
     if (!cfg || !out) return fail(TWR_ERR_INVALID, "cfg/out is NULL");
     *out = nullptr;
     int n = 0;
@@ -178,6 +192,7 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
     e->launches0 = g_twr_launches.load();
     *out = e;
     return TWR_OK;
+    });
 }
 
 static void mcts_release_fwd(twr_engine* e);
@@ -363,6 +378,7 @@ static int upload_policy(twr_policy* p, const twr_policy_desc* d) {
 }
 
 int twr_policy_create(twr_engine* e, const twr_policy_desc* d_in, twr_policy** out) {
+    return twr_guard([&]() -> int {
     if (!e || !out) return fail(TWR_ERR_INVALID, "engine/out is NULL");
     *out = nullptr;
     if (!d_in) return fail(TWR_ERR_INVALID, "policy desc / embedding is NULL");
@@ -453,9 +469,11 @@ int twr_policy_create(twr_engine* e, const twr_policy_desc* d_in, twr_policy** o
     }
     *out = p;
     return TWR_OK;
+    });
 }
 
 int twr_policy_update(twr_policy* p, const twr_policy_desc* d_in) {
+    return twr_guard([&]() -> int {
     if (!p) return fail(TWR_ERR_INVALID, "policy is NULL");
     if (!d_in) return fail(TWR_ERR_INVALID, "policy desc / embedding is NULL");
     twr_policy_desc flat;
@@ -466,6 +484,7 @@ int twr_policy_update(twr_policy* p, const twr_policy_desc* d_in) {
     if ((rc = validate_desc(d))) return rc;
     CU_TRY(cudaSetDevice(p->eng->device));
     return upload_policy(p, d);
+    });
 }
 
 int64_t twr_policy_blob_floats(const twr_policy* p) { return p ? p->blob_floats : 0; }
@@ -536,6 +555,7 @@ int twr_envs_set_difficulty(twr_envs* v, int32_t difficulty) {
 }
 
 int twr_envs_set_state(twr_envs* v, const int64_t* states) {
+    return twr_guard([&]() -> int {
     if (!v || !states) return fail(TWR_ERR_INVALID, "envs/states is NULL");
     if (v->n == 0) return TWR_OK;
     const int N = v->p.N;
@@ -562,6 +582,7 @@ int twr_envs_set_state(twr_envs* v, const int64_t* states) {
     launch_envs_set_state(e->stream, v->p, v->cells, v->meta, v->n, st.d);
     CU_TRY(cudaStreamSynchronize(e->stream));
     return TWR_OK;
+    });
 }
 
 int twr_envs_set_cell(twr_envs* v, int64_t env, int32_t cell, int32_t value) {
@@ -644,6 +665,7 @@ static void launch_forward(twr_engine* e, const PolicyDev& dev, const ForwardArg
 
 int twr_policy_forward(twr_engine* e, const twr_policy* p, twr_envs* v, const int32_t* perm_idx, int32_t apply_masks,
                        float* logits, float* values) {
+    return twr_guard([&]() -> int {
     if (!e || !p || !v || !logits || !values) return fail(TWR_ERR_INVALID, "NULL argument");
     if (p->eng != e || v->eng != e) return fail(TWR_ERR_INVALID, "policy/envs belong to another engine");
     if (v->n == 0) return TWR_OK;
@@ -679,9 +701,11 @@ int twr_policy_forward(twr_engine* e, const twr_policy* p, twr_envs* v, const in
         for (int a2 = 0; a2 < dev.A; ++a2) logits[i * dev.A + a2] = l[a2];
     }
     return TWR_OK;
+    });
 }
 
 int twr_debug_forward_profile(twr_engine* e, const twr_policy* p, twr_envs* v, int64_t* counters, int32_t max_ctas, int32_t flags) {
+    return twr_guard([&]() -> int {
     if (!e || !p || !v || !counters) return fail(TWR_ERR_INVALID, "NULL argument");
     PolicyDev dev;
     int rc = check_policy_env(p, v->p, &dev);
@@ -700,6 +724,7 @@ int twr_debug_forward_profile(twr_engine* e, const twr_policy* p, twr_envs* v, i
     CU_TRY(cudaMemcpyAsync(counters, d_dbg.d, sizeof(long long) * ((size_t)148 * 16 + 256), cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     return TWR_OK;
+    });
 }
 
 int twr_debug_set_tc_terms(twr_engine* e, int32_t terms) {
@@ -711,6 +736,7 @@ int twr_debug_set_tc_terms(twr_engine* e, int32_t terms) {
 
 int twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* obs, int64_t n, int32_t n_obs,
                            const int32_t* perm_idx, float* logits, float* values) {
+    return twr_guard([&]() -> int {
     if (!e || !p || !obs || !logits || !values) return fail(TWR_ERR_INVALID, "NULL argument");
     if (p->eng != e) return fail(TWR_ERR_INVALID, "policy belongs to another engine");
     if (n_obs < 1 || n_obs > TWR_MAX_CELLS) return fail(TWR_ERR_UNSUPPORTED, "n_obs must be in 1..32");
@@ -756,10 +782,12 @@ int twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* ob
         for (int a2 = 0; a2 < dev.A; ++a2) logits[i * dev.A + a2] = l[a2];
     }
     return TWR_OK;
+    });
 }
 
 int twr_sample(twr_engine* e, const float* logits, int64_t n, int32_t A, uint32_t env_id_base, uint32_t step,
                uint32_t collect_id, int32_t* actions, float* uniforms_out) {
+    return twr_guard([&]() -> int {
     if (!e || !logits || !actions) return fail(TWR_ERR_INVALID, "NULL argument");
     if (A < 1 || A > TWR_MAX_ACTIONS) return fail(TWR_ERR_UNSUPPORTED, "num_actions must be 1..4");
     if (n <= 0) return TWR_OK;
@@ -774,10 +802,12 @@ int twr_sample(twr_engine* e, const float* logits, int64_t n, int32_t A, uint32_
         CU_TRY(cudaMemcpyAsync(uniforms_out, d_u.d, sizeof(float) * (size_t)n * A, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     return TWR_OK;
+    });
 }
 
 int twr_gae(twr_engine* e, const float* rewards, const float* values, const int64_t* offsets, int64_t n_ep, float gamma,
             float lambda, float* advs, float* rets) {
+    return twr_guard([&]() -> int {
     if (!e || !rewards || !values || !offsets || !advs || !rets) return fail(TWR_ERR_INVALID, "NULL argument");
     if (n_ep <= 0) return TWR_OK;
     const int64_t R = offsets[n_ep];
@@ -797,6 +827,7 @@ int twr_gae(twr_engine* e, const float* rewards, const float* values, const int6
     CU_TRY(cudaMemcpyAsync(rets, d_t.d, sizeof(float) * (size_t)R, cudaMemcpyDeviceToHost, e->stream));
     CU_TRY(cudaStreamSynchronize(e->stream));
     return TWR_OK;
+    });
 }
 
 // -------------------------------------------------------------------- collect ---
@@ -1004,6 +1035,7 @@ static void finish_timing(twr_engine* e, int n_fwd) {
 
 int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, float gamma,
                     float lambda, twr_collected* out) {
+    return twr_guard([&]() -> int {
     if (!out) return fail(TWR_ERR_INVALID, "NULL argument");
     CollectPlan plan;
     int rc = plan_collect(e, spec, p, num_episodes, &plan);
@@ -1039,6 +1071,7 @@ int twr_ppo_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p
     e->has_last = true;
     *out = c;
     return TWR_OK;
+    });
 }
 
 static int copy_out(twr_engine* e, cudaStream_t st, const twr_host_buffers* dst, int64_t at, size_t R, int n_cells, int A) {
@@ -1056,6 +1089,7 @@ static int copy_out(twr_engine* e, cudaStream_t st, const twr_host_buffers* dst,
 }
 
 int twr_collected_to_host(twr_engine* e, const twr_host_buffers* dst) {
+    return twr_guard([&]() -> int {
     if (!e || !dst) return fail(TWR_ERR_INVALID, "NULL argument");
     if (!e->has_last) return fail(TWR_ERR_STATE, "twr_collected_to_host: no collect has run on this engine");
     const twr_collected& c = e->last;
@@ -1070,6 +1104,7 @@ int twr_collected_to_host(twr_engine* e, const twr_host_buffers* dst) {
     if (dst->ep_len) CU_TRY(cudaMemcpyAsync(dst->ep_len, c.ep_len, sizeof(int32_t) * (size_t)c.num_episodes, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     return TWR_OK;
+    });
 }
 
 // End-to-end collect with host buffers.  Large collects are split into sub-batches of consecutive local episodes so
@@ -1129,6 +1164,7 @@ static std::vector<int64_t> host_collect_parts(twr_engine* e, int64_t num_episod
 
 int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p, const twr_policy_desc* desc,
                          int64_t num_episodes, float gamma, float lambda, const twr_host_buffers* dst, twr_collected* out) {
+    return twr_guard([&]() -> int {
     if (!e || !p || !dst || !out) return fail(TWR_ERR_INVALID, "NULL argument");
     int rc;
     if (desc && (rc = twr_policy_update(p, desc))) return rc;
@@ -1262,6 +1298,7 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
     c.successes = successes; c.reward_sum = reward_sum;    // device pointers stay NULL: the data now lives in `dst`
     *out = c;
     return TWR_OK;
+    });
 }
 
 
@@ -1425,6 +1462,7 @@ int twr_evaluate(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, i
 int twr_evaluate_episodes(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, int32_t deterministic,
                           int32_t num_searches, int32_t num_mcts_searches, float C, int32_t max_expand_depth,
                           float* success_rate, float* mean_reward, float* best_success, float* best_reward) {
+    return twr_guard([&]() -> int {
     if (!success_rate || !mean_reward) return fail(TWR_ERR_INVALID, "NULL argument");
     if (num_mcts_searches < 0 || max_expand_depth < 0) return fail(TWR_ERR_INVALID, "negative argument");
     const MctsOpt mo{num_mcts_searches, C, max_expand_depth};
@@ -1466,11 +1504,13 @@ int twr_evaluate_episodes(twr_engine* e, const twr_env_spec* spec, const twr_pol
     *success_rate = succ / (float)num_episodes;
     *mean_reward = rew / (float)num_episodes;
     return TWR_OK;
+    });
 }
 
 int twr_solve(twr_engine* e, twr_envs* start, const twr_policy* p, int32_t deterministic, int32_t num_searches,
               int32_t num_mcts_searches, float C, int32_t max_expand_depth,
               float* success, float* reward, int32_t* actions, int32_t max_actions, int32_t* n_actions) {
+    return twr_guard([&]() -> int {
     if (!e || !start || !p || !success || !reward || !n_actions) return fail(TWR_ERR_INVALID, "NULL argument");
     if (num_mcts_searches < 0 || max_expand_depth < 0) return fail(TWR_ERR_INVALID, "negative argument");
     const MctsOpt mo{num_mcts_searches, C, max_expand_depth};
@@ -1514,6 +1554,7 @@ int twr_solve(twr_engine* e, twr_envs* start, const twr_policy* p, int32_t deter
         }
     }
     return TWR_OK;
+    });
 }
 
 
@@ -1580,6 +1621,7 @@ static int mcts_probs_impl(twr_engine* e, const twr_policy* p, twr_envs* v, int3
 
 int twr_az_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p, int64_t num_episodes, int32_t num_mcts_searches,
                    float C, int32_t max_expand_depth, twr_collected* out) {
+    return twr_guard([&]() -> int {
     if (!out) return fail(TWR_ERR_INVALID, "NULL argument");
     CollectPlan plan;
     int rc = plan_collect(e, spec, p, num_episodes, &plan);
@@ -1640,6 +1682,7 @@ int twr_az_collect(twr_engine* e, const twr_env_spec* spec, const twr_policy* p,
     e->has_last = true;
     *out = c;
     return TWR_OK;
+    });
 }
 
 int twr_host_alloc(void** ptr, int64_t bytes) {

@@ -180,3 +180,32 @@ def test_az_errors_and_trained_policy_solves(eng):
         col.collect(env, twisted)
     with pytest.raises(RuntimeError, match="No data in collected data chunks to merge"):
         tw.collector.AZCollector(0, 4, 1.0, 1, 1, engine=eng).collect(env, pol)
+
+
+@pytest.mark.parametrize("lockstep", [False, True])
+def test_mcts_probs_gridworld(eng, monkeypatch, lockstep):
+    """The search on the other env kind (GridWorld 5x5: 625-row table, common width 128), on both device paths: the
+    persistent whole-search kernel (policy stationary in shared memory) and the lockstep kernels."""
+    from parity import make_policies
+    from twisterl_b200 import _lib
+    from twisterl_b200.env import EnvBatch
+    if lockstep:
+        monkeypatch.setenv("TWISTERL_B200_MCTS_LOCKSTEP", "1")
+    pol, opol = make_policies(synth_state_dict(6, 625, 512, 128, 4), 625)
+    n, sims = 64, 60
+    b = EnvBatch(_lib.EnvSpec(1, 5, 5, 6, 0, 64), n, eng)
+    b.reset(env_id_base=900, collect_id=4)
+    states = b.get_state()
+    probs, visits, trace = _mcts(eng, pol, b, sims, 1.41, 1, 900, 4, 0)
+    same = 0
+    for i in range(n):
+        env = orc.Env(orc.gridworld_spec(5, 5, 64, 6)); env.reset(seed=eng.seed, env_id=900 + i, collect_id=4)
+        assert env.get_state() == states[i].tolist()
+        op, ov = orc.mcts_probs(env, opol, sims, 1.41, 1, seed=eng.seed, collect_id=4, stream_id=900 + i, t=0)
+        assert visits[i].sum() == ov.sum()
+        if np.array_equal(visits[i], ov):
+            same += 1
+            continue
+        div = _first_divergence_margin(trace[:, i], env, opol, sims, 1.41, 1, eng.seed, 4, 900 + i, 0)
+        assert div is not None and div[1] < NEAR_TIE, (i, div)
+    assert same >= n // 2

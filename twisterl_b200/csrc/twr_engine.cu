@@ -216,6 +216,7 @@ void twr_engine_destroy(twr_engine* e) {
     cudaStreamSynchronize(e->stream);
     twr_comm_destroy(e);
     mcts_release_fwd(e);
+    if (e->trace_buf) { cudaFree(e->trace_buf); e->trace_buf = nullptr; }
     free_collect_buffers(e);
     for (auto ev : e->ev) cudaEventDestroy(ev);
     dev_free(e->ep_len_id);
@@ -948,7 +949,7 @@ static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev&
             }
             if (e->timing && 2 * n_fwd + 1 < (int)e->ev.size()) cudaEventRecord(e->ev[2 * n_fwd], st);
             fa.dbg = nullptr;
-            static long long* trace_buf = nullptr;           // TWISTERL_B200_TRACE=<chunk index>: pipeline counters of that launch
+            long long*& trace_buf = e->trace_buf;             // TWISTERL_B200_TRACE=<chunk index>: pipeline counters of that launch (per engine)
             static const char* trace_env = getenv("TWISTERL_B200_TRACE");
             if (trace_env && ci == atoi(trace_env)) {
                 if (!trace_buf) cudaMalloc(reinterpret_cast<void**>(&trace_buf), sizeof(long long) * (148 * 16 + 256));

@@ -56,6 +56,7 @@ struct twr_engine {
     void* comm = nullptr;
     double* d_stats = nullptr;
     MctsCache mcts;
+    long long* trace_buf = nullptr;   // device counters of a traced forward launch (TWISTERL_B200_TRACE)
 };
 
 struct twr_policy {

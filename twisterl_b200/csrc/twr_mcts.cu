@@ -767,9 +767,11 @@ bool launch_mcts_persistent(cudaStream_t st, const MctsArgs& a, const PolicyDev&
         fprintf(stderr, "[mcts] persistent: %lld trees, %d resident clusters of %d CTAs (%zu B shared memory), %d launch(es) of <= %d trees\n",
                 (long long)max_n, nc, PM_CS, L.total, n_launch, slice);
     MctsArgs args = a;
-    static long long* d_dbg = nullptr;
-    if (getenv("TWISTERL_B200_MCTS_DEBUG")) {
-        if (!d_dbg) cudaMalloc(reinterpret_cast<void**>(&d_dbg), 8 * sizeof(long long));
+    static long long* d_dbg_dev[64] = {nullptr};           // debug counters, one buffer per device
+    long long* d_dbg = nullptr;
+    if (getenv("TWISTERL_B200_MCTS_DEBUG") && dev >= 0 && dev < 64) {
+        if (!d_dbg_dev[dev]) cudaMalloc(reinterpret_cast<void**>(&d_dbg_dev[dev]), 8 * sizeof(long long));
+        d_dbg = d_dbg_dev[dev];
         args.dbg = d_dbg;
     }
     for (int i = 0; i < n_launch; ++i) {

@@ -465,8 +465,10 @@ def run_extras(args, torch, tw, twc, twn, eng, comm, stream, rank, world, pk):
 
     guarded(ppo, "puzzle8_ppo", "examples/ppo_puzzle8_v1.json PPO rollout (3x3, difficulty 32 = diff_max, depth budget 64), 65536 envs per GPU",
             tw.env.Puzzle(3, 3, 32, 2, 256), orc.puzzle_spec(3, 3, 32, 2, 256), 81, 256, "puzzle8", 81, 65536, "weak")
-    guarded(ppo, "gridworld_ppo", "examples/grid_world/ppo_grid_world_5x5_v1.json PPO rollout (5x5, max_steps 64, difficulty 10 = diff_max), 65536 envs per GPU",
-            tw.env.GridWorld(5, 5, 64, 10), orc.gridworld_spec(5, 5, 64, 10), 625, 128, "gridworld", 100, 65536, "weak")
+    # GridWorld episodes are short (random walks end on the goal / trap after a handful of steps, 64 at most), so a collect
+    # is bound by the latency of its <= 65 sequential steps unless the batch is large: 262144 envs per GPU
+    guarded(ppo, "gridworld_ppo", "examples/grid_world/ppo_grid_world_5x5_v1.json PPO rollout (5x5, max_steps 64, difficulty 10 = diff_max), 262144 envs per GPU",
+            tw.env.GridWorld(5, 5, 64, 10), orc.gridworld_spec(5, 5, 64, 10), 625, 128, "gridworld", 100, 262144, "weak")
     guarded(az, "puzzle8_az_100", "AlphaZero on puzzle8 (difficulty 8), 100 MCTS simulations per record, 65536 episodes per GPU", 65536, 100, 8)
     guarded(az, "puzzle8_az_1000", "AlphaZero on puzzle8 (difficulty 8), the reference's AZ defaults: 512 episodes x 1000 MCTS simulations (src/twisterl/defaults.py)",
             512, 1000, 8)

@@ -94,7 +94,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (!done && spins > (1u << 22)) __trap();
+        if (!done && spins > (1u << 26)) __trap();
     }
 }
 __device__ __forceinline__ void mbar_wait_cluster_t(uint32_t bar, uint32_t parity, long long& acc, bool timed) {
@@ -236,7 +236,7 @@ __device__ __forceinline__ void wait_handoff(const int32_t* flag, int target) {
         for (uint32_t spins = 0;; ++spins) {
             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
             if (v >= target) break;
-            if (spins > (1u << 22)) __trap();
+            if (spins > (1u << 26)) __trap();
             __nanosleep(100);
         }
     }

@@ -27,7 +27,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (!done && spins > (1u << 22)) __trap();
+        if (!done && spins > (1u << 26)) __trap();
     }
 }
 // timed variant for the pipeline-wait counters; `timed` is false in production launches

@@ -292,3 +292,25 @@ def test_safetensors_reader_rejects_corrupt_headers(tmp_path):
     (tmp_path / "short.safetensors").write_bytes(b"\x10\0\0\0\0\0\0\0{")
     h = C.c_void_p()
     assert L.twr_policy_create_from_safetensors(fake_engine, str(tmp_path / "short.safetensors").encode(), None, 0, 0, None, None, 0, C.byref(h)) == -1
+
+
+def test_puzzle_opt_in_twists_are_a_symmetry():
+    """`Puzzle(..., add_perms=True)` hands the policy the {identity, transpose} twist set: a pair of
+    permutations for which twist(step(s, a)) == step(twist(s), A(a)) on the oracle env, with the solved board fixed."""
+    import twisterl_b200 as tw
+    from helpers import transpose_twists
+    from oracle import orc
+    assert tw.env.Puzzle(4, 4, 1, 2, 256).twists() == ([], [])
+    assert tw.env.Puzzle(4, 3, 1, 2, 256, add_perms=True).twists() == ([], [])           # square boards only
+    obs_perms, act_perms = tw.env.Puzzle(4, 4, 1, 2, 256, add_perms=True).twists()
+    assert (obs_perms, act_perms) == tuple(transpose_twists(4))
+    assert sorted(obs_perms[1]) == list(range(256)) and obs_perms[0] == list(range(256))
+    rng = np.random.default_rng(0)
+    env, tenv = orc.Env(orc.puzzle_spec(4, 4, 1, 2, 256)), orc.Env(orc.puzzle_spec(4, 4, 1, 2, 256))
+    twist_state = lambda obs: [v % 16 for v in sorted(obs_perms[1][o] for o in obs)]      # obs index -> (cell, tile) under the twist
+    assert twist_state(env.observe()) == env.get_state()                                   # solved board is a fixed point
+    for _ in range(300):
+        a = int(rng.integers(0, 4))
+        tenv.set_state(twist_state(env.observe()))
+        env.step(a); tenv.step(act_perms[1][a])
+        assert twist_state(env.observe()) == tenv.get_state()

@@ -147,12 +147,26 @@ def spec_from_env(env) -> _lib.EnvSpec:
 class Puzzle(PyBaseEnv):
     """`env.Puzzle(width, height, difficulty, depth_slope, max_depth)` (python_interface/env.rs:117-160)."""
 
-    def __init__(self, width: int, height: int, difficulty: int, depth_slope: int, max_depth: int):
+    def __init__(self, width: int, height: int, difficulty: int, depth_slope: int, max_depth: int, add_perms: bool = False):
         for v in (width, height, difficulty, depth_slope, max_depth):
             if int(v) < 0:
                 raise OverflowError("can't convert negative int to unsigned")
         self._init_spec(_lib.EnvSpec(_lib.ENV_PUZZLE, int(width), int(height), int(difficulty), int(depth_slope),
                                      int(max_depth)))
+        # Opt-in twist set (docs/twists.md: "gate toggles through config ... an `add_perms` flag"): the reference's Puzzle
+        # declares no twists (Env::twists default, rl/env.rs:59), and neither does this one unless asked to
+        self._add_perms = bool(add_perms)
+
+    def twists(self):
+        """`Env::twists` (rl/env.rs:33,59).  With `add_perms=True` on a square board: {identity, main-diagonal transpose}
+        -- cell i and tile label v both move to their transposed index, left<->up and right<->down trade places
+        (`twist(step(s, a)) == step(twist(s), A(a))`, the solved board is a fixed point)."""
+        w, h = self._spec.width, self._spec.height
+        if not getattr(self, "_add_perms", False) or w != h:
+            return ([], [])
+        n = w * h
+        t = [(i % w) * w + (i // w) for i in range(n)]
+        return ([list(range(n * n)), [t[i] * n + t[v] for i in range(n) for v in range(n)]], [[0, 1, 2, 3], [1, 0, 3, 2]])
 
     def get_state(self) -> list[int]: return [int(x) for x in self._b().get_state()[0]]
     def solved(self) -> bool: return bool(self._b().success()[0])

@@ -23,7 +23,7 @@ E = 65536
 cap = int(L.twr_max_records(C.byref(spec), E))
 hb, arrs, keep = twc._host_buffers(cap, 16, 4, E, pinned=True, obs_u8=True)
 desc = pol.desc(); hpol = pol.device_handle(eng); out = _lib.Collected()
-for parts in ("37888,27648", "37888,18944,8704", "18944,37888,8704"):
+for parts in ("37888,27648", "37888,18944,8704", "18944,37888,8704", "18944,27648,18944", "18944,18944,18944,8704", "8704,37888,18944", "18944,46592"):
     os.environ["TWISTERL_B200_E2E_PARTS"] = parts
     os.environ.pop("TWISTERL_B200_E2E_TRACE", None)
     for _ in range(3):

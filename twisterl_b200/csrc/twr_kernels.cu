@@ -473,6 +473,15 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
     }
 }
 
+__global__ void k_publish_stats(const unsigned long long* __restrict__ stats, unsigned long long* __restrict__ mapped_host) {
+    if (threadIdx.x < 4) mapped_host[threadIdx.x] = stats[threadIdx.x];
+    __threadfence_system();
+}
+void launch_publish_stats(cudaStream_t st, const unsigned long long* stats, unsigned long long* mapped_host) {
+    k_publish_stats<<<1, 32, 0, st>>>(stats, mapped_host);
+    TWR_COUNT_LAUNCH();
+}
+
 void launch_compact(cudaStream_t st, const EnvParams& p, const CollectBuffers& b, int A) {
     dim3 grid(grid_for(b.B, 32), (unsigned)((b.Tmax + 31) / 32));
     cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompactTiles));   // per device: set on every launch

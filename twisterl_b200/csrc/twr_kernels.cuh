@@ -97,6 +97,8 @@ void launch_gae_concat(cudaStream_t s, const float* r, const float* v, const int
 // K5 episode offsets in merged order + transpose/compaction into concatenated episodes
 void launch_episode_offsets(cudaStream_t s, const CollectBuffers& b, const EnvIds& ids);
 void launch_compact(cudaStream_t s, const EnvParams& p, const CollectBuffers& b, int A);
+// the four statistics words of a collect -> mapped pinned host memory (no copy engine involved)
+void launch_publish_stats(cudaStream_t s, const unsigned long long* stats, unsigned long long* mapped_host);
 
 // K2 policy forward.  `live` may be NULL (identity); n_live_ptr may be NULL (use n).
 struct ForwardArgs {

@@ -44,7 +44,8 @@ struct twr_engine {
     int bal_delta = 3;
 #define TWR_MAX_SUBBATCH 64
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[TWR_MAX_SUBBATCH] = {}, ev_small[TWR_MAX_SUBBATCH] = {};
-    unsigned long long* h_stats = nullptr;   // pinned
+    unsigned long long* h_stats = nullptr;   // pinned, mapped
+    unsigned long long* d_hstats = nullptr;  // its device address
     bool has_last = false;
     twr_collected last{};
     // timing

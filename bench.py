@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- rollout env-steps/s including the policy forward, puzzle15 PPO (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|f16x2|f16x2w16] [--no-extras]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|f16x2|f16x2w16|f16f8c] [--no-extras]
 
 One "step" = one PPOCollector.collect of `--episodes` (default 65 536) puzzle15 episodes per GPU at
 difficulty 128 (<= 257 records each): reset, per-step policy forward + Gumbel-max sampling + env step +
@@ -39,7 +39,10 @@ EXECUTED_TENSOR_FLOP_PER_STEP = {"f16x2": 2 * (2 * 256 * 512) + 3 * (2 * 512 * 2
 DTYPE = {"fp32": "f32",
          "f16x2": "f16x2 (tcgen05; every operand split into fp16 hi+lo, f32 accumulate; 1e-5-grade)",
          "f16x2w16": "f16x2w16 (tcgen05; table and activations split into fp16 hi+lo, common-layer weight one fp16 term, f32 accumulate; "
-                     "7e-4 worst case on the shipped trained weights, bar 1e-3)"}
+                     "7e-4 worst case on the shipped trained weights, bar 1e-3)",
+         "f16f8c": "f16f8c (tcgen05; main products one-hot x table and h1 x W in fp16, their two correction products "
+                   "(table residue, activation residue) as fp8 MMAs, f32 accumulate; same 1e-3 bar as f16x2w16, "
+                   "tests/test_gpu_precision.py)"}
 METRIC = "rollout env-steps/sec incl. policy fwd (puzzle15 PPO)"
 UNIT = "env-steps/s"
 
@@ -173,6 +176,9 @@ def executed_flop(precision, obs_k, emb, hidden):
     """tensor-pipe flop per env-step of the pair kernel: dense one-hot GEMM1 over the hi and lo table (K padded to 64) and
     2 (f16x2w16) or 3 (f16x2) split products of the common layer"""
     k = ((obs_k + 63) // 64) * 64
+    if precision == "f16f8c":       # the two fp8 correction products run at twice the fp16 rate: counted at half, i.e. in
+        k8 = ((obs_k + 127) // 128) * 128      # fp16-equivalent pipe work (what the bf16 roof is comparable with)
+        return 2 * k * emb + (2 * k8 * emb) // 2 + 2 * emb * hidden + (2 * emb * hidden) // 2
     return 2 * (2 * k * emb) + (3 if precision == "f16x2" else 2) * (2 * emb * hidden)
 
 
@@ -484,7 +490,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TWISTERL_B200_PRECISION", "f16x2w16"), choices=["fp32", "f16x2", "f16x2w16"])
+    ap.add_argument("--precision", default=os.environ.get("TWISTERL_B200_PRECISION", "f16x2w16"), choices=["fp32", "f16x2", "f16x2w16", "f16f8c"])
     ap.add_argument("--episodes", type=int, default=65536)
     ap.add_argument("--difficulty", type=int, default=128)
     ap.add_argument("--ref-episodes", type=int, default=2048)

@@ -48,10 +48,13 @@ typedef enum {
                          * fp32-grade results (1e-5 measured on the shipped trained weights; bar 1e-3).
                          * Policies whose shape does not fit the tensor-core kernel and multiset observations run the
                          * fp32 SIMT kernel on the same engine. */
-    TWR_PREC_F16X2_W16 = 2 /* same kernel, the common Linear's weight held as ONE fp16 term (h1_hi*W + h1_lo*W; table and
+    TWR_PREC_F16X2_W16 = 2, /* same kernel, the common Linear's weight held as ONE fp16 term (h1_hi*W + h1_lo*W; table and
                          * activations stay split): 2/3 of the GEMM2 work, 7e-4 worst case on the shipped trained
-                         * weights -- the cheapest operand combination inside the 1e-3 bar (tests/test_gpu_precision.py
+                         * weights -- the cheapest fp16 operand combination inside the 1e-3 bar (tests/test_gpu_precision.py
                          * holds the whole ladder; plain fp16 operands measure 4e-3 and miss it). */
+    TWR_PREC_F16_F8C = 3 /* the terms of F16X2_W16 with the two CORRECTION products (one-hot * table_lo, h1_lo * W) issued as
+                         * fp8 MMAs (K = 32 per instruction): a correction is ~2^-12 of its main term, so 2-3 mantissa bits
+                         * of it keep the same 1e-3 grade at 3/4 of the tensor-core instructions.  Same bar, same tests. */
 } twr_precision;
 
 typedef struct twr_engine twr_engine;
@@ -184,7 +187,8 @@ int  twr_debug_forward_profile(twr_engine* e, const twr_policy* p, twr_envs* v, 
                                int32_t experiment_flags /* 0 = none; results are invalid when non-zero */);
 /* Debug / precision ladder: which split-operand terms the tensor-core forward of this engine accumulates on top of the
  * hi*hi products: bit 0 one-hot * table_lo, bit 1 h1_lo * W_hi, bit 2 h1_hi * W_lo (7 = TWR_PREC_F16X2, 3 = .._W16,
- * 0 = plain fp16 operands).  -1 restores the engine's precision. */
+ * 0 = plain fp16 operands; 16 | 3 = the two corrections of .._W16 as fp8 products = TWR_PREC_F16_F8C).
+ * -1 restores the engine's precision. */
 int  twr_debug_set_tc_terms(twr_engine* e, int32_t terms);
 
 /* sample_from_logits (rust/src/nn/policy.rs:169-172) for n logit rows, row i using the uniforms

@@ -13,7 +13,7 @@ from twisterl_b200.env import EnvBatch
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 sd = synth_state_dict(0, 256, 512, 256, 4)
 pol, _ = make_policies(sd, 256)
-eng = tw.Engine(device=0, precision="f16x2", seed=1)
+eng = tw.Engine(device=0, precision=sys.argv[3] if len(sys.argv) > 3 else "f16x2", seed=1)
 b = EnvBatch(_lib.EnvSpec(0, 4, 4, 64, 2, 256), n, eng)
 b.reset()
 flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0

@@ -57,7 +57,7 @@ def test_cpp_collect_matches_python_mirror(tmp_path):
     w = _weights_file(tmp_path, sd)
     seed, cid, E, diff = 0xABCDEF, 5, 300, 6
     out = tmp_path / "out.bin"
-    r = subprocess.run([str(exe), str(w), str(out), str({"fp32": 0, "f16x2": 1, "f16x2w16": 2}[PRECISION]), str(seed), str(cid), str(E), str(diff)],
+    r = subprocess.run([str(exe), str(w), str(out), str({"fp32": 0, "f16x2": 1, "f16x2w16": 2, "f16f8c": 3}[PRECISION]), str(seed), str(cid), str(E), str(diff)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     raw = out.read_bytes()

@@ -29,7 +29,7 @@ def eng():
 # is therefore traced to the FIRST simulation in which the two part ways, and the oracle's smallest decision margin of
 # that simulation (best minus second-best UCB along the descent, bin-edge distance of the child draw) must be tiny.
 # UCB = q + C*sqrt(N)/(1+n)*prior amplifies a prior difference by up to C*sqrt(N) ~ 20 at these search sizes.
-NEAR_TIE = {"fp32": 2e-4, "f16x2": 2e-3, "f16x2w16": 2e-2}[PRECISION]
+NEAR_TIE = {"fp32": 2e-4, "f16x2": 2e-3, "f16x2w16": 2e-2, "f16f8c": 2e-2}[PRECISION]
 
 
 def _mcts(eng, pol, batch, n_sims, c, med, base, cid, t):

@@ -25,7 +25,7 @@ def eng():
 # Device and oracle evaluate the same f32 expressions on the same Philox streams; their logits differ in the last bits, so
 # an episode may differ only where one of its decisions was a near-tie in the oracle (argmax gap, weighted-draw distance
 # to a bin edge, UCB gap inside MCTS; orc_evaluate_margins reports the smallest of an episode).
-NEAR_TIE = {"fp32": 2e-4, "f16x2": 2e-3, "f16x2w16": 2e-2}[PRECISION]
+NEAR_TIE = {"fp32": 2e-4, "f16x2": 2e-3, "f16x2w16": 2e-2, "f16f8c": 2e-2}[PRECISION]
 
 
 def _evaluate(eng, env, pol, n, det, searches, cid, mcts=0, c_puct=1.41, depth=1, episodes=False):

@@ -162,7 +162,7 @@ def test_forward_matches_reference_torch_golden(eng):
     assert _close(logits, z["logits"], TOL) and _close(values, z["values"], TOL)
     # the split-operand tensor-core path is held to its measured margin too (1.1e-5 on these trained weights), not only
     # to the 1e-3 bar of a bf16 path
-    if PRECISION != "f16x2w16":
+    if PRECISION not in ("f16x2w16", "f16f8c"):
         assert _close(logits, z["logits"], 1e-4) and _close(values, z["values"], 1e-4)
     assert _close(logits[0], np.array([-4.4116335, -5.16946, -2.0670972, 0.8337202], np.float32), TOL)
     # and against the oracle, element by element

@@ -9,8 +9,11 @@ to the tensor cores as one fp16 term or as a hi+lo pair; this test MEASURES each
 against the logits/values the reference's own torch BasicPolicy produced (tests/golden/policy15_trained.npz) and holds
 each to the bar it is shipped under: all three terms = TWR_PREC_F16X2 (1e-4, fp32-grade); bits 0|1 = TWR_PREC_F16X2_W16
 (1e-3, the cheapest combination inside the north-star bar); every cheaper combination -- plain fp16 operands included --
-MISSES 1e-3 on these weights, which is why none of them is offered.  scripts/precision_ladder_emul.py is the CPU
-emulation of the same table (it also shows bf16 operands an order of magnitude further out)."""
+MISSES 1e-3 on these weights, which is why none of them is offered.  One more rung keeps the terms of W16 but issues the
+two CORRECTION products (bits 0 and 1) as fp8 MMAs (16|3 = TWR_PREC_F16_F8C: a correction is ~2^-12 of its main term, so
+2-3 mantissa bits of it are enough) -- 3/4 of the tensor-core instructions of W16, held to the same 1e-3.
+scripts/precision_ladder_emul.py is the CPU emulation of the same table (it also shows bf16 operands an order of
+magnitude further out)."""
 import json
 import os
 from pathlib import Path
@@ -54,18 +57,19 @@ def test_precision_ladder_on_trained_weights():
     bg = EnvBatch(spec, len(golden), eng); bg.set_state(golden)
     bw = EnvBatch(spec, len(wide), eng); bw.set_state(wide)
     table = {}
-    for terms in range(8):
+    for terms in list(range(8)) + [16 | 3]:
         eng.set_tc_terms(terms)
         l, v = forward_batch(eng, pol, bg)
         l2, v2 = forward_batch(eng, pol, bw)
         table[terms] = dict(g1_passes=1 + (terms & 1), g2_terms=1 + ((terms >> 1) & 1) + ((terms >> 2) & 1),
-                            executed_flop_per_env_step=EXECUTED(terms),
+                            executed_flop_per_env_step=EXECUTED(terms & 7), fp8_corrections=bool(terms & 16),
+                            mma_per_256_envs=(96 if terms & 16 else EXECUTED(terms) // 8192),
                             logits_err_golden=_err(l, z["logits"]), values_err_golden=_err(v, z["values"]),
                             logits_err_8192=_err(l2, wl), values_err_8192=_err(v2, wv))
     eng.set_tc_terms(-1)
     print("\nterms  executed    logits(golden) values(golden)  logits(8192)  values(8192)")
     for t, r in table.items():
-        print(f"  {t:03b}  {r['executed_flop_per_env_step']:8d}    {r['logits_err_golden']:.2e}       {r['values_err_golden']:.2e}"
+        print(f"  {t:05b}  {r['executed_flop_per_env_step']:8d}    {r['logits_err_golden']:.2e}       {r['values_err_golden']:.2e}"
               f"      {r['logits_err_8192']:.2e}     {r['values_err_8192']:.2e}")
     out = Path(os.environ.get("GRAFT_REPO_ROOT", Path(__file__).resolve().parent.parent)) / "gpurun_out"
     if out.is_dir():
@@ -73,6 +77,8 @@ def test_precision_ladder_on_trained_weights():
     worst = lambda r: max(r["logits_err_golden"], r["values_err_golden"], r["logits_err_8192"], r["values_err_8192"])
     assert worst(table[7]) <= 1e-4, table[7]                       # TWR_PREC_F16X2: fp32-grade
     assert worst(table[3]) <= 1e-3, table[3]                       # TWR_PREC_F16X2_W16: inside the north-star bar
+    assert worst(table[16 | 3]) <= 1e-3, table[16 | 3]             # TWR_PREC_F16_F8C: same bar with fp8 correction products
+    assert worst(table[16 | 3]) <= 1.25 * worst(table[3]) + 1e-4, (table[16 | 3], table[3])   # and no worse than W16 to speak of
     for terms in (0, 1, 2, 4, 5, 6):                               # everything cheaper than / as cheap as W16 misses it
         assert max(table[terms]["logits_err_golden"], table[terms]["logits_err_8192"]) > 1e-3, (terms, table[terms])
     # the W16 engine is exactly the 0b011 rung
@@ -84,4 +90,13 @@ def test_precision_ladder_on_trained_weights():
     b16 = EnvBatch(spec, len(golden), e16); b16.set_state(golden)
     l16, v16 = forward_batch(e16, pol16, b16)
     assert np.array_equal(l16, l3) and np.array_equal(v16, v3)
-    pol.release(); pol16.release(); eng.close(); e16.close()
+    # and the F8C engine the 16|3 rung
+    eng.set_tc_terms(16 | 3)
+    l8, v8 = forward_batch(eng, pol, bg)
+    eng.set_tc_terms(-1)
+    e8 = tw.Engine(device=0, precision="f16f8c", seed=1)
+    pol8, _ = make_policies(sd, 256)
+    b8 = EnvBatch(spec, len(golden), e8); b8.set_state(golden)
+    l8e, v8e = forward_batch(e8, pol8, b8)
+    assert np.array_equal(l8e, l8) and np.array_equal(v8e, v8)
+    pol.release(); pol16.release(); pol8.release(); eng.close(); e16.close(); e8.close()

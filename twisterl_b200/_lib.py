@@ -18,9 +18,10 @@ LIB_PATH = PKG / "lib" / "libtwisterl_b200.so"
 OK = 0
 ENV_PUZZLE, ENV_GRIDWORLD = 0, 1
 ABI_VERSION = 3                      # TWR_ABI_VERSION of the header these struct layouts / prototypes were written against
-PREC_FP32, PREC_F16X2, PREC_F16X2_W16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "f16x2": PREC_F16X2, "f16x2w16": PREC_F16X2_W16}
-TC_PRECISIONS = ("f16x2", "f16x2w16")   # the tcgen05 forward: all operands split / common-layer weight as one fp16 term
+PREC_FP32, PREC_F16X2, PREC_F16X2_W16, PREC_F16_F8C = 0, 1, 2, 3
+PRECISIONS = {"fp32": PREC_FP32, "f16x2": PREC_F16X2, "f16x2w16": PREC_F16X2_W16, "f16f8c": PREC_F16_F8C}
+# the tcgen05 forward: all operands split / common-layer weight as one fp16 term / that with the correction products in fp8
+TC_PRECISIONS = ("f16x2", "f16x2w16", "f16f8c")
 MAX_ACTIONS = 4
 
 f32p, i32p, i64p, u8p, i8p, u16p = (C.POINTER(t) for t in (C.c_float, C.c_int32, C.c_int64, C.c_uint8, C.c_int8, C.c_uint16))

@@ -143,6 +143,11 @@ int twr_device_count(void) {
     return n;
 }
 
+// ForwardArgs::tc_terms of an engine precision (bit 3 marks "explicit", bit 4 = fp8 correction products)
+static int terms_of_precision(int precision) {
+    return precision == TWR_PREC_F16X2_W16 ? (8 | 1 | 2) : precision == TWR_PREC_F16_F8C ? (16 | 8 | 1 | 2) : 0;
+}
+
 int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
     return twr_guard([&]() -> int {
     if (!cfg || !out) return fail(TWR_ERR_INVALID, "cfg/out is NULL");
@@ -154,7 +159,8 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
         return fail(TWR_ERR_CUDA, "no CUDA device: the twisterl_b200 engine has no CPU fallback");
     }
     if (cfg->device < 0 || cfg->device >= n) return fail(TWR_ERR_INVALID, "device ordinal out of range");
-    if (cfg->precision != TWR_PREC_FP32 && cfg->precision != TWR_PREC_F16X2 && cfg->precision != TWR_PREC_F16X2_W16)
+    if (cfg->precision != TWR_PREC_FP32 && cfg->precision != TWR_PREC_F16X2 && cfg->precision != TWR_PREC_F16X2_W16 &&
+        cfg->precision != TWR_PREC_F16_F8C)
         return fail(TWR_ERR_INVALID, "unknown precision");
     if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(TWR_ERR_INVALID, "bad rank/world");
     CU_TRY(cudaSetDevice(cfg->device));
@@ -165,7 +171,7 @@ int twr_engine_create(const twr_engine_cfg* cfg, twr_engine** out) {
     twr_engine* e = new twr_engine();
     e->device = cfg->device; e->precision = cfg->precision; e->seed = cfg->seed;
     e->rank = cfg->rank; e->world = cfg->world;
-    e->tc_terms = cfg->precision == TWR_PREC_F16X2_W16 ? (8 | 1 | 2) : 0;
+    e->tc_terms = terms_of_precision(cfg->precision);
     if (const char* f = getenv("TWISTERL_B200_TC_FLAGS")) e->tc_flags = atoi(f);
     if (cfg->stream) {
         e->stream = reinterpret_cast<cudaStream_t>(cfg->stream);
@@ -734,8 +740,8 @@ int twr_debug_forward_profile(twr_engine* e, const twr_policy* p, twr_envs* v, i
 
 int twr_debug_set_tc_terms(twr_engine* e, int32_t terms) {
     if (!e) return fail(TWR_ERR_INVALID, "engine is NULL");
-    if (terms < -1 || terms > 7) return fail(TWR_ERR_INVALID, "terms must be -1 or a 3-bit mask");
-    e->tc_terms = terms < 0 ? (e->precision == TWR_PREC_F16X2_W16 ? (8 | 1 | 2) : 0) : (8 | terms);
+    if (terms < -1 || (terms > 7 && terms != (16 | 3))) return fail(TWR_ERR_INVALID, "terms must be -1, a 3-bit mask, or 16|3");
+    e->tc_terms = terms < 0 ? terms_of_precision(e->precision) : (8 | terms);
     return TWR_OK;
 }
 

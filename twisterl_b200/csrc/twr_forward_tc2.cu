@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <map>
 #include <mutex>
 
@@ -45,6 +46,10 @@ constexpr int NCOPIES = 1;              // replicas of the operand image (8 copi
 
 constexpr int SM_A1 = 0;
 constexpr int SM_RING = SM_A1 + MAX_KB1 * TILE_BYTES;
+// fp8 correction terms (TERMS bit 4): the first two ring slots hold the e5m2 copy of the one-hot operand (two k-blocks of
+// 128 one-byte columns), the ring keeps the other six
+constexpr int SM_A8 = SM_RING;
+constexpr int A8_TILES = 2;
 constexpr int SM_MISC = SM_RING + NSLOTS * TILE_BYTES;
 constexpr int SM_HEADW = SM_MISC;
 constexpr int SM_B1 = SM_HEADW + 8192;
@@ -123,13 +128,56 @@ __device__ __forceinline__ void tc2_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 }
 constexpr uint32_t IDESC_256x128 = (1u << 4) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 constexpr uint32_t IDESC_256x256 = (1u << 4) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+// kind::f8f6f4 (K = 32 per instruction): operand formats at [7,10) (A) and [10,13) (B), 0 = e4m3, 1 = e5m2
+// (cute::UMMA::InstrDescriptor / MXF8F6F4Format)
+__device__ __forceinline__ void tc2_mma8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc2_mma8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+constexpr uint32_t idesc8(uint32_t n, uint32_t a_fmt, uint32_t b_fmt) {
+    return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
+}
+// The two correction terms as fp8 products (TWR_PREC_F16_F8C).  Each is ~2^-12 of its main term, so 2-3 mantissa bits are
+// enough to keep the 1e-3 grade (tests/test_gpu_precision.py measures it), and an fp8 MMA covers K = 32 at the cost of an
+// fp16 K = 16 one: half the instructions for these two terms.
+//   GEMM1: one-hot value 2^-14 (e5m2 0x04)  x  e4m3((table - fp16(table)) * 2^14)
+//   GEMM2: e5m2((h1 - fp16(h1)) * 2^6)      x  e5m2(W * 2^-6)
+constexpr uint8_t  ONE8 = 0x04;
+constexpr float    TABLE8_SCALE = 16384.0f, H1LO8_SCALE = 64.0f, W8_SCALE = 1.0f / 64.0f;
+__host__ __device__ __forceinline__ uint32_t tile_off8(uint32_t row, uint32_t k) {       // [128 rows][128 one-byte k], 128B swizzle
+    return (row >> 3) * 1024u + (row & 7u) * 128u + ((((k >> 4) ^ row) & 7u) << 4) + (k & 15u);
+}
 
 // cN > 0: GEMM1 runs over the COMPACT table of a GridWorld policy -- compact row k = cell (k / 4), value (k % 4) stands
 // for table row (k / 4) * cN + (k % 4); the other obs_size - 4 * cN rows are unreachable (lib.rs:74-81: cell values 0..3)
-struct Tc2Params { int NC, NKB1, E, H, cN; };
-__host__ __device__ inline size_t slots_g1(const Tc2Params& t) { return (size_t)t.NC * t.NKB1; }
-__host__ __device__ inline size_t slots_g2(const Tc2Params& t) { return (size_t)t.NC * (t.H == 256 ? 4 : 2); }
+// f8 = 1: the operand image of the fp8-correction variant (it follows the standard image in the same buffer, row0 = its
+// first tensor-map row); NKB8 = k-blocks of 128 of the one-byte one-hot operand
+struct Tc2Params { int NC, NKB1, E, H, cN, f8, NKB8, row0; };
+__host__ __device__ inline size_t slots_g1(const Tc2Params& t) { return t.f8 ? (size_t)(t.NC / 2) * (t.NKB1 + t.NKB8) : (size_t)t.NC * t.NKB1; }
+__host__ __device__ inline size_t slots_g2(const Tc2Params& t) { return t.f8 ? (size_t)t.NC * (t.H == 256 ? 3 : 2) : (size_t)t.NC * (t.H == 256 ? 4 : 2); }
 __host__ __device__ inline size_t slots_per_rank(const Tc2Params& t) { return slots_g1(t) + slots_g2(t); }
+// fp8 variant, GEMM1 stream of one chunk pair: hi k-blocks in order, the one-byte k-block j (= hi k-blocks 2j, 2j+1) right
+// after hi k-block 2j+1; the LAST hi and the LAST one-byte k-block close the sequence (they are issued chunk by chunk as
+// N = 128 MMAs, see the kernel).  Unit u of NKB1 + NKB8 -> (is8, k-block, last).
+__host__ __device__ inline void g1_unit8(int NKB1, int NKB8, int u, int& is8, int& kb, int& last) {
+    int i = 0;
+    for (int k = 0; k < NKB1 - 1; ++k) {
+        if (i++ == u) { is8 = 0; kb = k; last = 0; return; }
+        if ((k & 1) && (k >> 1) < NKB8 - 1) { if (i++ == u) { is8 = 1; kb = k >> 1; last = 0; return; } }
+    }
+    if (i++ == u) { is8 = 0; kb = NKB1 - 1; last = 1; return; }
+    is8 = 1; kb = NKB8 - 1; last = 1;
+}
 
 // Operand image per CTA rank r (rank 0 image, then rank 1 image), in streaming order, 16 KB per ring slot:
 //   G1 slot (s,kb,part) : [128 rows x 64 k] of the hi (part 0) or lo (part 1) table, rows n = feature (2s+r)*128 + (0..127),
@@ -181,6 +229,65 @@ __global__ void __launch_bounds__(256) k_tc2_pack(PolicyDev p, Tc2Params t, __ha
         const __half v = lo_part ? __float2half_rn(x - __half2float(hi)) : hi;
         for (int cp = 0; cp < NCOPIES; ++cp)
             *reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(pack) + ((size_t)cp * 2 * spr + gslot) * TILE_BYTES + off) = v;
+    }
+}
+
+// Operand image of the fp8-correction variant, per CTA rank, in streaming order:
+//   per chunk pair sc: the units of g1_unit8 -- hi slots exactly as above (part 0), one-byte slots [128 rows x 128 k] of
+//                      e4m3((table - hi) * 2^14), rows like the hi slot of the same kind (plain / last)
+//   per chunk j      : H = 256: hi kb 0, hi kb 1 (as above), then [128 rows x 128 k] e5m2(W * 2^-6), rows n = output r*128 + ..
+//                      H = 128: the hi slot (two sub-tiles), then [64 rows x 128 k] e5m2(W * 2^-6), rows n = output r*64 + ..
+__global__ void __launch_bounds__(256) k_tc2_pack8(PolicyDev p, Tc2Params t, unsigned char* __restrict__ pack) {
+    const size_t spr = slots_per_rank(t), n1 = slots_g1(t);
+    const size_t total = 2 * spr * TILE_BYTES;                 // one thread per BYTE position (fp16 slots: even positions only)
+    const int upc = t.NKB1 + t.NKB8;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t gslot = idx / TILE_BYTES;
+        const uint32_t within = (uint32_t)(idx % TILE_BYTES);
+        const int r = (int)(gslot / spr);
+        const size_t slot = gslot % spr;
+        unsigned char* dst = pack + gslot * TILE_BYTES;
+        const uint32_t row = within >> 7;
+        if (slot < n1) {
+            const int sc = (int)(slot / upc);
+            int is8, kb, last;
+            g1_unit8(t.NKB1, t.NKB8, (int)(slot % upc), is8, kb, last);
+            if (!is8 && (within & 1u)) continue;
+            const uint32_t kk = is8 ? (within & 127u) : ((within & 127u) >> 1);
+            const int f = last ? (2 * sc + (int)(row >> 6)) * 128 + r * 64 + (int)(row & 63u) : (2 * sc + r) * 128 + (int)row;
+            int k = is8 ? kb * 128 + (int)kk : kb * 64 + (int)kk;
+            if (t.cN > 0) k = (k >> 2) < t.cN ? (k >> 2) * t.cN + (k & 3) : p.obs_size;
+            const float x = k < p.obs_size ? p.emb[(size_t)k * p.E + f] : 0.0f;
+            const __half hi = __float2half_rn(x);
+            if (is8) dst[tile_off8(row, kk)] = (unsigned char)__nv_cvt_float_to_fp8((x - __half2float(hi)) * TABLE8_SCALE, __NV_SATFINITE, __NV_E4M3);
+            else *reinterpret_cast<__half*>(dst + tile_off(row, kk)) = hi;
+        } else if (t.H == 256) {
+            const size_t q = slot - n1;
+            const int j = (int)(q / 3), u = (int)(q % 3);
+            const int o = r * 128 + (int)row;
+            if (u < 2) {
+                if (within & 1u) continue;
+                const uint32_t kk = (within & 127u) >> 1;
+                *reinterpret_cast<__half*>(dst + tile_off(row, kk)) = __float2half_rn(p.w1[(size_t)(j * 128 + u * 64 + (int)kk) * p.H + o]);
+            } else {
+                const uint32_t kk = within & 127u;
+                dst[tile_off8(row, kk)] = (unsigned char)__nv_cvt_float_to_fp8(p.w1[(size_t)(j * 128 + (int)kk) * p.H + o] * W8_SCALE, __NV_SATFINITE, __NV_E5M2);
+            }
+        } else {
+            const size_t q = slot - n1;
+            const int j = (int)(q / 2), u = (int)(q % 2);
+            if (u == 0) {
+                if (within & 1u) continue;
+                const uint32_t kk = (within & 127u) >> 1;
+                const int kb = (int)(row >> 6);
+                const int o = r * 64 + (int)(row & 63u);
+                *reinterpret_cast<__half*>(dst + (uint32_t)kb * 8192u + tile_off(row & 63u, kk)) = __float2half_rn(p.w1[(size_t)(j * 128 + kb * 64 + (int)kk) * p.H + o]);
+            } else {
+                const uint32_t kk = within & 127u;
+                const float w = row < 64 ? p.w1[(size_t)(j * 128 + (int)kk) * p.H + (r * 64 + (int)row)] * W8_SCALE : 0.0f;
+                dst[tile_off8(row, kk)] = (unsigned char)__nv_cvt_float_to_fp8(w, __NV_SATFINITE, __NV_E5M2);
+            }
+        }
     }
 }
 
@@ -285,8 +392,15 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     // Split-operand terms of this launch (ForwardArgs::tc_terms; 0 = all): GEMM1 always has one-hot x table_hi and GEMM2
     // h1_hi x W_hi; bit 0 adds one-hot x table_lo, bit 1 h1_lo x W_hi, bit 2 h1_hi x W_lo.  Skipped terms are neither
     // streamed nor issued.
-    const int terms = TERMS >= 0 ? TERMS : (a.tc_terms ? a.tc_terms : 7);
+    // TERMS = 16 | 3: the two correction terms of f16x2w16 as fp8 products (see ONE8 above) -- own operand image, own
+    // one-hot copy, six ring slots.
+    constexpr bool F8 = TERMS >= 16;
+    static_assert(!F8 || TERMS == 19, "fp8 corrections replace exactly the terms of f16x2w16");
+    constexpr int NS = F8 ? NSLOTS - A8_TILES : NSLOTS;                  // ring slots
+    constexpr int RING = F8 ? SM_RING + A8_TILES * TILE_BYTES : SM_RING;
+    const int terms = TERMS >= 0 ? (TERMS & 7) : (a.tc_terms ? (a.tc_terms & 7) : 7);
     const bool g1_lo = (terms & 1) != 0, g2_alo = (terms & 2) != 0, g2_wlo = (terms & 4) != 0;
+    const int NKB8 = t.NKB8;
     constexpr uint32_t idesc2 = H == 256 ? IDESC_256x256 : IDESC_256x128;   // GEMM2: N = H
     constexpr int g2_units = H == 256 ? 4 : 2;                               // ring slots of one chunk's GEMM2 (see k_tc2_pack)
 
@@ -298,7 +412,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         mbar_init(bar(B_D2_FULL), 1); mbar_init(bar(B_D2_EMPTY), 2 * NEPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < MAX_KB1 * TILE_BYTES / 16; i += NTHREADS)
+    for (int i = threadIdx.x; i < (MAX_KB1 + (F8 ? A8_TILES : 0)) * TILE_BYTES / 16; i += NTHREADS)   // A8 follows A1
         reinterpret_cast<uint4*>(smem + SM_A1)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < H; i += NTHREADS) {
         float* w = headw + i * 8;
@@ -330,18 +444,18 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         // Each CTA fetches ITS half of every operand tile into its own ring; both halves credit the
         // leader's `full` barrier, so the MMA issuer waits on one local barrier per ring slot.
         if (lane == 0) {
-            const int img_row0 = ((pair_id % NCOPIES) * 2 + crank) * (int)slots_per_rank(t) * (TILE_BYTES / 128);   // tensor-map row of this pair's copy, this rank's image
+            const int img_row0 = t.row0 + ((pair_id % NCOPIES) * 2 + crank) * (int)slots_per_rank(t) * (TILE_BYTES / 128);   // tensor-map row of this pair's copy, this rank's image
             const int g1_row0 = img_row0, g2_row0 = img_row0 + (int)slots_g1(t) * (TILE_BYTES / 128);
             uint32_t use = 0;
             long long w_empty = 0;
             auto push = [&](int row) {
-                const uint32_t slot = use % NSLOTS, round = use / NSLOTS;
+                const uint32_t slot = use % NS, round = use / NS;
                 mbar_wait_t(bar(B_EMPTY0 + slot), (round & 1u) ^ 1u, w_empty, timed);
                 if (a.dbg_flags & 2) {                      // ablation: no operand traffic, the slot is "full" at once
                     if (crank == 0) mbar_arrive(bar(B_FULL0 + slot));
                 } else {
                     if (crank == 0) mbar_expect_tx(bar(B_FULL0 + slot), 2 * TILE_BYTES);
-                    tma_load_2sm(sbase + SM_RING + slot * TILE_BYTES, &tmap, 0, row, bar(B_FULL0 + slot));
+                    tma_load_2sm(sbase + RING + slot * TILE_BYTES, &tmap, 0, row, bar(B_FULL0 + slot));
                 }
                 ++use;
             };
@@ -353,8 +467,18 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 for (int u = 0; u < g2_units; ++u)
                     if (!(u & 1) || g2_wlo) push(g2_row0 + (j * g2_units + u) * (TILE_BYTES / 128));
             };
-            for (int it = 0; it < n_items; ++it)
-                for (int sc = 0; sc < NC / 2; ++sc) { push_g1(sc); push_g2(2 * sc); push_g2(2 * sc + 1); }
+            if constexpr (F8) {
+                // the image holds exactly the slots this variant streams, in order
+                const int n1 = NKB1 + NKB8, n2 = 2 * (H == 256 ? 3 : 2);
+                for (int it = 0; it < n_items; ++it)
+                    for (int sc = 0; sc < NC / 2; ++sc) {
+                        for (int u = 0; u < n1; ++u) push(g1_row0 + (sc * n1 + u) * (TILE_BYTES / 128));
+                        for (int u = 0; u < n2; ++u) push(g2_row0 + (sc * n2 + u) * (TILE_BYTES / 128));
+                    }
+            } else {
+                for (int it = 0; it < n_items; ++it)
+                    for (int sc = 0; sc < NC / 2; ++sc) { push_g1(sc); push_g2(2 * sc); push_g2(2 * sc + 1); }
+            }
             if (a.dbg) a.dbg[blockIdx.x * 16 + 8] = w_empty;
         }
         __syncwarp();
@@ -365,7 +489,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             long long w_slot = 0, w_a1 = 0, w_a2 = 0, w_d2 = 0, w_slot_g1 = 0, w_slot_first = 0;
             const long long t_begin = clock64();
             auto wait_slot = [&]() -> uint32_t {
-                const uint32_t slot = use % NSLOTS, round = use / NSLOTS;
+                const uint32_t slot = use % NS, round = use / NS;
                 mbar_wait_cluster_t(bar(B_FULL0 + slot), round & 1u, w_slot, timed);
                 tc_fence_after();
                 ++use;
@@ -380,6 +504,67 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 auto g1 = [&](int sc) {
                     stamp(it, 1 + 2 * sc);
                     const uint32_t d = tmem + D1_COL;
+                    if constexpr (F8) {
+                        constexpr uint32_t I8_256 = idesc8(256, 1, 0), I8_128 = idesc8(128, 1, 0);
+                        const bool on = !(a.dbg_flags & 8);
+                        for (int kb = 0; kb < NKB1 - 1; ++kb) {
+                            const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
+                            const long long w0 = w_slot;
+                            const uint32_t slot = wait_slot();
+                            w_slot_g1 += w_slot - w0;
+                            if (kb == 0) w_slot_first += w_slot - w0;
+                            const uint64_t bh = make_desc(sbase + RING + slot * TILE_BYTES);
+                            if (on) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) tc2_mma(d, ad + 2u * ks, bh + 2u * ks, IDESC_256x256, (kb | ks) != 0);
+                            }
+                            tc2_commit(bar(B_EMPTY0 + slot));
+                            if ((kb & 1) && (kb >> 1) < NKB8 - 1) {
+                                const uint64_t a8 = make_desc(sbase + SM_A8 + (kb >> 1) * TILE_BYTES);
+                                const long long w1 = w_slot;
+                                const uint32_t slot8 = wait_slot();
+                                w_slot_g1 += w_slot - w1;
+                                const uint64_t b8 = make_desc(sbase + RING + slot8 * TILE_BYTES);
+                                if (on) {
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) tc2_mma8(d, a8 + 2u * ks, b8 + 2u * ks, I8_256, 1u);
+                                }
+                                tc2_commit(bar(B_EMPTY0 + slot8));
+                            }
+                        }
+                        {   // last hi k-block + last one-byte k-block, chunk 2sc first (rows 0..63 of both slots), then chunk 2sc+1
+                            const int kb = NKB1 - 1;
+                            const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
+                            const uint64_t a8 = make_desc(sbase + SM_A8 + (NKB8 - 1) * TILE_BYTES);
+                            const long long w0 = w_slot;
+                            const uint32_t slot_h = wait_slot();
+                            const uint32_t slot_l = wait_slot();
+                            w_slot_g1 += w_slot - w0;
+                            if (kb == 0) w_slot_first += w_slot - w0;
+                            const uint64_t bh = make_desc(sbase + RING + slot_h * TILE_BYTES);
+                            const uint64_t bl = make_desc(sbase + RING + slot_l * TILE_BYTES);
+                            const uint64_t half = (uint64_t)((64 * 128) >> 4);
+                            if (on) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) tc2_mma(d, ad + 2u * ks, bh + 2u * ks, IDESC_256x128, (kb | ks) != 0);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) tc2_mma8(d, a8 + 2u * ks, bl + 2u * ks, I8_128, 1u);
+                            }
+                            tc2_commit(bar(B_D1_FULL0));
+                            if (on) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) tc2_mma(d + 128u, ad + 2u * ks, bh + half + 2u * ks, IDESC_256x128, (kb | ks) != 0);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) tc2_mma8(d + 128u, a8 + 2u * ks, bl + half + 2u * ks, I8_128, 1u);
+                            }
+                            tc2_commit(bar(B_EMPTY0 + slot_h));
+                            tc2_commit(bar(B_EMPTY0 + slot_l));
+                            tc2_commit(bar(B_D1_FULL1));
+                        }
+                        if (sc == NC / 2 - 1) tc2_commit(bar(B_A1_EMPTY));
+                        d1use += 2;
+                        return;
+                    }
                     for (int kb = 0; kb < NKB1 - 1; ++kb) {
                         const uint64_t ad = make_desc(sbase + SM_A1 + kb * TILE_BYTES);
                         const long long w0 = w_slot;
@@ -387,8 +572,8 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                         const uint32_t slot_l = g1_lo ? wait_slot() : slot_h;
                         w_slot_g1 += w_slot - w0;
                         if (kb == 0) w_slot_first += w_slot - w0;
-                        const uint64_t bh = make_desc(sbase + SM_RING + slot_h * TILE_BYTES);
-                        const uint64_t bl = make_desc(sbase + SM_RING + slot_l * TILE_BYTES);
+                        const uint64_t bh = make_desc(sbase + RING + slot_h * TILE_BYTES);
+                        const uint64_t bl = make_desc(sbase + RING + slot_l * TILE_BYTES);
                         if (!(a.dbg_flags & 8)) {
                             // per k-step: table_hi then table_lo against the SAME one-hot A tile -- back-to-back MMAs that share
                             // their shared-memory A operand issue faster than the (all hi, then all lo) order: +4 % on the whole
@@ -412,8 +597,8 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                         const uint32_t slot_h = wait_slot();
                         const uint32_t slot_l = g1_lo ? wait_slot() : slot_h;
                         w_slot_g1 += w_slot - w0;
-                        const uint64_t bh = make_desc(sbase + SM_RING + slot_h * TILE_BYTES);
-                        const uint64_t bl = make_desc(sbase + SM_RING + slot_l * TILE_BYTES);
+                        const uint64_t bh = make_desc(sbase + RING + slot_h * TILE_BYTES);
+                        const uint64_t bl = make_desc(sbase + RING + slot_l * TILE_BYTES);
                         const uint64_t half = (uint64_t)((64 * 128) >> 4);          // 64 rows further into the slot (descriptor address units of 16 B)
                         if (!(a.dbg_flags & 8)) {
 #pragma unroll
@@ -445,6 +630,40 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     stamp(it, 5 + j);
                     const uint32_t a_base = tmem + D1_COL + buf * 128u;
                     const uint32_t d = tmem + D2_COL;
+                    if constexpr (F8) {
+                        // hi slots (H = 256: k-blocks 0, 1; H = 128: one slot with both), then the one-byte slot: the chunk's
+                        // 128 features as 4 MMAs of K = 32, A = the e5m2 residues at columns +16..+23 of every 32-feature group
+                        constexpr uint32_t I8 = idesc8((uint32_t)H, 1, 1);
+                        const bool on = !(a.dbg_flags & 4);
+#pragma unroll
+                        for (int u = 0; u < (H == 256 ? 2 : 1); ++u) {
+                            const uint32_t slot = wait_slot();
+                            const uint64_t bd = make_desc(sbase + RING + slot * TILE_BYTES);
+                            constexpr int nks = H == 256 ? 4 : 8;
+                            if (on) {
+#pragma unroll
+                                for (int ks = 0; ks < nks; ++ks) {
+                                    const uint32_t sidx = H == 256 ? (uint32_t)(u * 4 + ks) : (uint32_t)ks;
+                                    const uint32_t ah = a_base + 32u * (sidx >> 1) + 8u * (sidx & 1u);
+                                    const uint64_t bk = H == 256 ? bd + 2u * ks : bd + (uint64_t)((ks >> 2) * (8192 >> 4)) + 2u * (ks & 3);
+                                    tc2_mma_ts(d, ah, bk, idesc2, !(j == 0 && u == 0 && ks == 0));
+                                }
+                            }
+                            tc2_commit(bar(B_EMPTY0 + slot));
+                        }
+                        {
+                            const uint32_t slot = wait_slot();
+                            const uint64_t bd = make_desc(sbase + RING + slot * TILE_BYTES);
+                            if (on) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) tc2_mma8_ts(d, a_base + 32u * ks + 16u, bd + 2u * ks, I8, 1u);
+                            }
+                            tc2_commit(bar(B_EMPTY0 + slot));
+                        }
+                        ++a2use;
+                        if (j == NC - 1) tc2_commit(bar(B_D2_FULL));
+                        return;
+                    }
                     // unit u = one ring slot: H = 256 -> (kb, part) = (u >> 1, u & 1), 4 k-steps of 16 features;
                     // H = 128 -> part = u, both k-blocks (two 64-row sub-tiles), 8 k-steps
 #pragma unroll
@@ -452,7 +671,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                         const int part = u & 1;
                         if (part && !g2_wlo) continue;
                         const uint32_t slot = wait_slot();
-                        const uint64_t bd = make_desc(sbase + SM_RING + slot * TILE_BYTES);
+                        const uint64_t bd = make_desc(sbase + RING + slot * TILE_BYTES);
                         const bool first = (j == 0 && u == 0);
                         if (!(a.dbg_flags & 4)) {
                             constexpr int nks = H == 256 ? 4 : 8;
@@ -542,7 +761,21 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[j * 32] = make_uint4(0, 0, 0, 0);
             }
+            if constexpr (F8) {
+                for (int kb = 0; kb < NKB8; ++kb) {
+                    uint4* dst = reinterpret_cast<uint4*>(smem + SM_A8 + kb * TILE_BYTES + quarter * 4096) + lane;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j * 32] = make_uint4(0, 0, 0, 0);
+                }
+            }
             __syncwarp();
+            // the same index in the one-byte copy of the operand (k-blocks of 128)
+            auto set8 = [&](uint32_t r) {
+                if constexpr (F8) {
+                    const uint32_t k8 = r & 127u;
+                    smem[SM_A8 + (r >> 7) * TILE_BYTES + row_base + ((((k8 >> 4) ^ rx) & 7u) << 4) + (k8 & 15u)] = ONE8;
+                }
+            };
             if (fast) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
@@ -552,6 +785,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                         const uint32_t k = r & 63u;
                         *reinterpret_cast<__half*>(smem + SM_A1 + (r >> 6) * TILE_BYTES + row_base + ((((k >> 3) ^ rx) & 7u) << 4) + (k & 7u) * 2u) =
                             __ushort_as_half(0x3C00);
+                        set8(r);
                     }
                 }
             } else {
@@ -566,6 +800,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     const uint32_t k = r & 63u;
                     *reinterpret_cast<__half*>(smem + SM_A1 + (r >> 6) * TILE_BYTES + row_base + ((((k >> 3) ^ rx) & 7u) << 4) + (k & 7u) * 2u) =
                         __ushort_as_half(0x3C00);
+                    set8(r);
                 }
             }
             perm_s[(it & 3) * TM + row] = (int8_t)perm;
@@ -582,6 +817,19 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
             hi = *reinterpret_cast<const uint32_t*>(&h);
             lo = *reinterpret_cast<const uint32_t*>(&l);
+        };
+
+        // fp8 variant: four features -> two fp16 pairs and ONE word of four e5m2 residues (feature k at byte k, the K order
+        // of an 8-bit A operand in tensor memory)
+        auto split4 = [](float x0, float x1, float x2, float x3, uint32_t& hi01, uint32_t& hi23, uint32_t& lo) {
+            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+            const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const uint32_t l01 = __nv_cvt_float2_to_fp8x2(make_float2((x0 - f01.x) * H1LO8_SCALE, (x1 - f01.y) * H1LO8_SCALE), __NV_SATFINITE, __NV_E5M2);
+            const uint32_t l23 = __nv_cvt_float2_to_fp8x2(make_float2((x2 - f23.x) * H1LO8_SCALE, (x3 - f23.y) * H1LO8_SCALE), __NV_SATFINITE, __NV_E5M2);
+            hi01 = *reinterpret_cast<const uint32_t*>(&h01);
+            hi23 = *reinterpret_cast<const uint32_t*>(&h23);
+            lo = l01 | (l23 << 16);
         };
 
         // the next item's one-hot operand is normally built BEFORE this item's heads (so its GEMM1 overlaps
@@ -603,14 +851,31 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 tc_wait_ld();
                 const float* bias = embb + c * 128 + chalf * 64;
                 uint32_t w[32];
+                if constexpr (F8) {
 #pragma unroll
-                for (int e2 = 0; e2 < 16; ++e2)
-                    split2(__uint_as_float(v0[2 * e2]) + bias[2 * e2], __uint_as_float(v0[2 * e2 + 1]) + bias[2 * e2 + 1], w[e2], w[16 + e2]);
-                tc_st32(taddr, w);
+                    for (int e4 = 0; e4 < 8; ++e4)
+                        split4(__uint_as_float(v0[4 * e4]) + bias[4 * e4], __uint_as_float(v0[4 * e4 + 1]) + bias[4 * e4 + 1],
+                               __uint_as_float(v0[4 * e4 + 2]) + bias[4 * e4 + 2], __uint_as_float(v0[4 * e4 + 3]) + bias[4 * e4 + 3],
+                               w[2 * e4], w[2 * e4 + 1], w[16 + e4]);
 #pragma unroll
-                for (int e2 = 0; e2 < 16; ++e2)
-                    split2(__uint_as_float(v1[2 * e2]) + bias[32 + 2 * e2], __uint_as_float(v1[2 * e2 + 1]) + bias[32 + 2 * e2 + 1], w[e2], w[16 + e2]);
-                tc_st32(taddr + 32u, w);
+                    for (int e4 = 24; e4 < 32; ++e4) w[e4] = 0u;
+                    tc_st32(taddr, w);
+#pragma unroll
+                    for (int e4 = 0; e4 < 8; ++e4)
+                        split4(__uint_as_float(v1[4 * e4]) + bias[32 + 4 * e4], __uint_as_float(v1[4 * e4 + 1]) + bias[32 + 4 * e4 + 1],
+                               __uint_as_float(v1[4 * e4 + 2]) + bias[32 + 4 * e4 + 2], __uint_as_float(v1[4 * e4 + 3]) + bias[32 + 4 * e4 + 3],
+                               w[2 * e4], w[2 * e4 + 1], w[16 + e4]);
+                    tc_st32(taddr + 32u, w);
+                } else {
+#pragma unroll
+                    for (int e2 = 0; e2 < 16; ++e2)
+                        split2(__uint_as_float(v0[2 * e2]) + bias[2 * e2], __uint_as_float(v0[2 * e2 + 1]) + bias[2 * e2 + 1], w[e2], w[16 + e2]);
+                    tc_st32(taddr, w);
+#pragma unroll
+                    for (int e2 = 0; e2 < 16; ++e2)
+                        split2(__uint_as_float(v1[2 * e2]) + bias[32 + 2 * e2], __uint_as_float(v1[2 * e2 + 1]) + bias[32 + 2 * e2 + 1], w[e2], w[16 + e2]);
+                    tc_st32(taddr + 32u, w);
+                }
                 tc_wait_st();
             }
             tc_fence_before();
@@ -654,16 +919,27 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             Pre pre_next; pre_next.pos = 0; pre_next.e = 0; pre_next.c = make_uint4(0, 0, 0, 0); pre_next.step = 0;
             int c_done = 0;
             if (defer) {
+                // Item it+1's env state was last written by the step of an earlier item of the same group (same-group
+                // items are >= 2 apart).  Steps of items <= it-2 finished before the previous iteration's bar.sync 1; only
+                // when item it-1 IS that earlier item do the upper-half threads have to wait (barrier 3) for the step the
+                // lower half runs right now -- otherwise their loads go out at once and the one-hot build of item it+1 does
+                // not queue behind a 5k-cycle step it does not depend on.
+                bool dep = false;
+                if (it >= 1 && it + 1 < n_items) {
+                    int g0, g1, s0, s1, x0, x1;
+                    sched_item(sch, pair_id, it - 1, g0, s0, x0);
+                    sched_item(sch, pair_id, it + 1, g1, s1, x1);
+                    dep = g0 == g1;
+                }
                 for (; c_done < 2 && c_done < NC; ++c_done) epi1(it, c_done);
+                if (chalf == 1 && it + 1 < n_items && !dep) pre_next = prefetch(it + 1);
                 if (chalf == 0 && sv.valid) {                          // step of item it-1
                     run_step(sv);
                     sv.valid = false;
-                    if (it + 1 < n_items) asm volatile("bar.arrive 3, %0;" ::"n"(NEPI) : "memory");
+                    if (dep) asm volatile("bar.arrive 3, %0;" ::"n"(NEPI) : "memory");
                 }
-                if (chalf == 1 && it + 1 < n_items) {
-                    // item it+1's env state was last written by the step of an item <= it-1 (same-group items are >= 2
-                    // apart), which the lower-half threads have just finished: barrier 3 orders it before these loads
-                    if (it >= 1) asm volatile("bar.sync 3, %0;" ::"n"(NEPI) : "memory");
+                if (chalf == 1 && dep) {
+                    asm volatile("bar.sync 3, %0;" ::"n"(NEPI) : "memory");
                     pre_next = prefetch(it + 1);
                 }
             } else if (build_early && chalf == 1 && it + 1 < n_items) {
@@ -771,10 +1047,16 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     }
 }
 
-Tc2Params make_params2(const PolicyDev& p) {
+Tc2Params make_params2(const PolicyDev& p, bool f8 = false) {
     Tc2Params t;
     t.E = p.E; t.H = p.H; t.NC = p.E / 128; t.cN = p.tc_compact_n;
     t.NKB1 = ((p.tc_compact_n > 0 ? 4 * p.tc_compact_n : p.obs_size) + 63) / 64;
+    t.NKB8 = (t.NKB1 + 1) / 2;
+    t.f8 = 0; t.row0 = 0;
+    if (f8) {                                   // the fp8-correction image follows the standard one
+        t.row0 = (int)((size_t)NCOPIES * 2 * slots_per_rank(t) * (TILE_BYTES / 128));
+        t.f8 = 1;
+    }
     return t;
 }
 
@@ -834,12 +1116,16 @@ int forward_tc2_supported(const PolicyDev& p) {
 
 size_t forward_tc2_pack_bytes(const PolicyDev& p) {
     if (!forward_tc2_supported(p)) return 0;
-    return (size_t)NCOPIES * 2 * slots_per_rank(make_params2(p)) * TILE_BYTES;
+    return (size_t)NCOPIES * 2 * (slots_per_rank(make_params2(p)) + slots_per_rank(make_params2(p, true))) * TILE_BYTES;
 }
 
 void launch_forward_tc2_pack(cudaStream_t st, const PolicyDev& p, void* pack) {
     k_tc2_pack<<<1024, 256, 0, st>>>(p, make_params2(p), reinterpret_cast<__half*>(pack));
-    g_twr_launches.fetch_add(1, std::memory_order_relaxed);
+    const Tc2Params t8 = make_params2(p, true);
+    unsigned char* img8 = reinterpret_cast<unsigned char*>(pack) + (size_t)t8.row0 * 128;
+    for (int cp = 0; cp < NCOPIES; ++cp)
+        k_tc2_pack8<<<1024, 256, 0, st>>>(p, t8, img8 + (size_t)cp * 2 * slots_per_rank(t8) * TILE_BYTES);
+    g_twr_launches.fetch_add(1 + NCOPIES, std::memory_order_relaxed);
 }
 
 // Everything a launch needs besides the arguments, resolved once (at policy creation) so that a launch cannot fail for
@@ -852,7 +1138,7 @@ bool forward_tc2_prepare(const PolicyDev& p, const void* pack) {
     if (!get_tmap(*d, pack, forward_tc2_pack_bytes(p), &tmap)) return false;
     if (!d->attr_set) {
         for (auto k : {k_forward_tc2<256, 7>, k_forward_tc2<256, 3>, k_forward_tc2<256, -1>, k_forward_tc2<128, 7>, k_forward_tc2<128, 3>,
-                       k_forward_tc2<128, -1>})
+                       k_forward_tc2<128, -1>, k_forward_tc2<256, 19>, k_forward_tc2<128, 19>})
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) != cudaSuccess) return false;
         d->attr_set = true;
     }
@@ -896,10 +1182,11 @@ bool launch_forward_tc2(cudaStream_t st, const PolicyDev& p, const ForwardArgs& 
     ForwardArgs args = a;
     if (a.bal_flags && max_clusters < grid / 2) { args.bal_flags = nullptr; args.bal_delta = 0; }
     const int terms = a.tc_terms ? (a.tc_terms & 7) : 7;
-    const Tc2Params t = make_params2(p);
+    const bool f8 = (a.tc_terms & 16) != 0 && terms == 3;                     // fp8 corrections: only defined for the f16x2w16 terms
+    const Tc2Params t = make_params2(p, f8);
     auto go = [&](auto kern) { kern<<<grid, NTHREADS, SM_TOTAL, st>>>(p, args, t, tmap); };
-    if (p.H == 256) { if (terms == 7) go(k_forward_tc2<256, 7>); else if (terms == 3) go(k_forward_tc2<256, 3>); else go(k_forward_tc2<256, -1>); }
-    else            { if (terms == 7) go(k_forward_tc2<128, 7>); else if (terms == 3) go(k_forward_tc2<128, 3>); else go(k_forward_tc2<128, -1>); }
+    if (p.H == 256) { if (f8) go(k_forward_tc2<256, 19>); else if (terms == 7) go(k_forward_tc2<256, 7>); else if (terms == 3) go(k_forward_tc2<256, 3>); else go(k_forward_tc2<256, -1>); }
+    else            { if (f8) go(k_forward_tc2<128, 19>); else if (terms == 7) go(k_forward_tc2<128, 7>); else if (terms == 3) go(k_forward_tc2<128, 3>); else go(k_forward_tc2<128, -1>); }
     g_twr_launches.fetch_add(1, std::memory_order_relaxed);
     return true;
 }

@@ -934,7 +934,9 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 for (; c_done < 2 && c_done < NC; ++c_done) epi1(it, c_done);
                 if (chalf == 1 && it + 1 < n_items && !dep) pre_next = prefetch(it + 1);
                 if (chalf == 0 && sv.valid) {                          // step of item it-1
+                    if (threadIdx.x == 64) stamp(it, 23);
                     run_step(sv);
+                    if (threadIdx.x == 64) stamp(it, 24);
                     sv.valid = false;
                     if (dep) asm volatile("bar.arrive 3, %0;" ::"n"(NEPI) : "memory");
                 }
@@ -988,7 +990,9 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 *reinterpret_cast<float4*>(ps) = make_float4(acc[0], acc[1], acc[2], acc[3]);
                 ps[4] = acc[4];
             }
+            if (threadIdx.x == 64) stamp(it, 25);
             asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");     // the 8 epilogue warps only
+            if (threadIdx.x == 64) stamp(it, 26);
             if (chalf == 0) {                                          // warp-uniform: whole warps take this branch
                 Saved cur;
                 sched_item(sch, pair_id, it, cur.group, cur.step, cur.extra);

@@ -439,7 +439,15 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
             if (x < nt) {
                 const uint4 q = tl.q[1][x][ey];
                 const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                if (b.obs_u8) {
+                if (b.obs_u8 == 2) {
+                    uint32_t h[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {          // bytes (b0 b1 b2 b3), all < 16 -> (b0 | b1 << 4), (b2 | b3 << 4)
+                        const uint32_t t = (w[k] | (w[k] >> 4)) & 0x00FF00FFu;
+                        h[k] = (t | (t >> 8)) & 0xFFFFu;
+                    }
+                    reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(b.out_obs) + r0 * 8)[x] = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+                } else if (b.obs_u8) {
                     uint32_t o[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k)            // cell i = 4k+j holds tile byte j of word k; index = i*16 + tile

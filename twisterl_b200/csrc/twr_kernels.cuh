@@ -51,7 +51,9 @@ struct CollectBuffers {
     int64_t* ep_off;      // [B] record offset of local episode e (plain local order; the id rotation gives merge order)
     int32_t* ep_len_id;   // [total episodes] episode length by episode id (filled by k_episode_offsets)
     int64_t out_base;     // records of earlier sub-batches (pipelined host collect)
-    int obs_u8;           // compaction writes one byte per observation index (twr_host_buffers.obs_u8)
+    int obs_u8;           // compaction writes one byte per observation index (twr_host_buffers.obs_u8); 2: 16-cell puzzles,
+                          // the 16 tile values as nibbles (8 bytes per record, cell 2j in the low half of byte j) -- the wire
+                          // format of twr_ppo_collect_host, expanded to indices by its host threads
     int pack_misc;        // compaction writes ONE byte per record into out_actions -- action | reward code << 2 | (perm + 1) << 4 --
                           // and skips out_perms / out_rewards / out_advs: the pipelined host collect rebuilds those on the host
                           // (Puzzle rewards take three values, puzzle.rs:171-177; advs = rets - values, ppo.rs:87-91)

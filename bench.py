@@ -279,10 +279,10 @@ def run_ours(args, rank, local_rank, world):
     rec_per_step = e2e_records / e2e_steps / world
     d2h = int(rec_per_step * sum(a.dtype.itemsize * int(np.prod(a.shape[1:])) for k, a in arrs.items() if k != "ep_len")
               + arrs["ep_len"].nbytes)
-    # bytes that actually cross PCIe: the 16 tiles as nibbles (8 B), action / twist / reward as one byte, and the advantages
-    # not at all -- rebuilt on the host from rets - values (twr_ppo_collect_host); d2h_bytes_per_step counts what lands in
+    # bytes that actually cross PCIe: the observation indices (or, opt-in, the 16 tiles as nibbles: 8 B), action / twist /
+    # reward as one byte, and the advantages not at all -- rebuilt on the host from rets - values (twr_ppo_collect_host); d2h_bytes_per_step counts what lands in
     # the caller's buffers
-    nib = 16 if os.environ.get("TWISTERL_B200_E2E_NONIB") else 8
+    nib = 8 if int(os.environ.get("TWISTERL_B200_E2E_NIB", "0") or 0) > 0 else 16      # opt-in wire format, see twr_ppo_collect_host
     pcie = int(rec_per_step * (nib + 16 + 4 + 4 + 1) + arrs["ep_len"].nbytes)
     h2d = nblob * 4
     # the host-memory ceiling of this box for the same bytes: one plain pinned cudaMemcpyAsync stream per rank, all ranks at once

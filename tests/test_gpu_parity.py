@@ -471,14 +471,14 @@ def test_collect_host_pipelined_matches_plain(eng, monkeypatch, twists):
     L = _lib.load()
     spec = tw.env.spec_from_env(env)
     cap = int(L.twr_max_records(C.byref(spec), E))
-    # nonib: the observation indices cross PCIe as they are instead of as 8 bytes of tile nibbles expanded on the host
-    for split, parts, u8, nonib in (("3", None, False, False), ("7", None, True, False), ("1", None, True, False),
-                                    (None, "600,300,100", True, False), ("3", None, True, True), ("2", None, False, True)):
+    # nib: the observations cross PCIe as 8 bytes of tile nibbles that host threads expand (opt-in wire format)
+    for split, parts, u8, nib in (("3", None, False, False), ("7", None, True, False), ("1", None, True, False),
+                                  (None, "600,300,100", True, False), ("3", None, True, True), ("2", None, False, True)):
         monkeypatch.delenv("TWISTERL_B200_E2E_SPLIT", raising=False)
         monkeypatch.delenv("TWISTERL_B200_E2E_PARTS", raising=False)
-        monkeypatch.delenv("TWISTERL_B200_E2E_NONIB", raising=False)
-        if nonib:
-            monkeypatch.setenv("TWISTERL_B200_E2E_NONIB", "1")
+        monkeypatch.delenv("TWISTERL_B200_E2E_NIB", raising=False)
+        if nib:
+            monkeypatch.setenv("TWISTERL_B200_E2E_NIB", "1")
         if split:
             monkeypatch.setenv("TWISTERL_B200_E2E_SPLIT", split)
         if parts:

@@ -1231,9 +1231,13 @@ int twr_ppo_collect_host(twr_engine* e, const twr_env_spec* spec, twr_policy* p,
     const bool pack = plan.env.kind == TWR_ENV_PUZZLE && plan.dev.n_perms <= 14 && dst->actions && (!dst->advs || (dst->rets && dst->values)) &&
                       !getenv("TWISTERL_B200_E2E_NOPACK");
     const float reward_of_code[4] = {-0.5f / (float)plan.env.max_depth, -0.5f, 1.0f, 0.0f};     // puzzle.rs:171-177
-    // 16-cell puzzles: the observation crosses PCIe as 8 bytes of tile nibbles instead of 16 index bytes (the indices are
-    // i * 16 + tile(i)); host threads expand them while the logits of the same sub-batch are still in flight
-    const bool nib = pack && plan.env.N == 16 && (dst->obs || dst->obs_u8) && !getenv("TWISTERL_B200_E2E_NONIB");
+    // 16-cell puzzles, opt-in (TWISTERL_B200_E2E_NIB=1): the observation crosses PCIe as 8 bytes of tile nibbles instead of
+    // 16 index bytes (the indices are i * 16 + tile(i)) and host threads expand them while the logits of the same
+    // sub-batch are still in flight.  33 instead of 41 B/record on the wire, but the expansion writes 16 B/record from
+    // the CPU: on the 16-vCPU benchmark hosts that costs more than the 2.4 ms of PCIe time it saves (measured: 22.9 vs
+    // 20.2 ms per 65 536-env call), so it is for hosts with cores to spare.
+    const char* nib_env = getenv("TWISTERL_B200_E2E_NIB");
+    const bool nib = pack && plan.env.N == 16 && (dst->obs || dst->obs_u8) && nib_env && atoi(nib_env) > 0;
     if (nib && e->h_obs_nib_bytes < (size_t)dst->capacity * 8) {
         if (e->h_obs_nib) { cudaFreeHost(e->h_obs_nib); e->h_obs_nib = nullptr; e->h_obs_nib_bytes = 0; }
         CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&e->h_obs_nib), (size_t)dst->capacity * 8, cudaHostAllocDefault));

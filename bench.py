@@ -359,7 +359,7 @@ def run_ours(args, rank, local_rank, world):
 
 
 # dram bytes (read + write) of one steady-state forward launch, from the committed ncu capture of the same command
-TRAFFIC = {("f16x2w16", 65536): 3_088_896 + 296_557_568}   # profiles/r2_tc2_summary.md, launch 0 (128 steps x 65 536 envs)
+TRAFFIC = {("f16x2w16", 65536): 3_088_896 + 296_557_568, ("f16f8c", 65536): 3_088_896 + 296_557_568}   # profiles/r2_tc2_summary.md, launch 0 (128 steps x 65 536 envs)
 
 
 # ------------------------------------------------------------- the other BASELINE configs ---
@@ -492,7 +492,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TWISTERL_B200_PRECISION", "f16x2w16"), choices=["fp32", "f16x2", "f16x2w16", "f16f8c"])
+    ap.add_argument("--precision", default=os.environ.get("TWISTERL_B200_PRECISION", "f16f8c"), choices=["fp32", "f16x2", "f16x2w16", "f16f8c"])
     ap.add_argument("--episodes", type=int, default=65536)
     ap.add_argument("--difficulty", type=int, default=128)
     ap.add_argument("--ref-episodes", type=int, default=2048)

@@ -501,6 +501,32 @@ def test_collect_host_pipelined_matches_plain(eng, monkeypatch, twists):
     assert len(set(np.unique(ref.rewards_array))) >= 2            # step reward and solved (and, for some seeds, out-of-budget) all cross as codes
 
 
+@pytest.mark.parametrize("E,difficulty", [(5000, 40), (33, 3), (20000, 128)])
+def test_collect_fused_gae_matches_stand_alone_kernels(eng, monkeypatch, E, difficulty):
+    """The PPO collect computes advantages and returns inside the compaction pass (k_compact<true>: reverse walk over the
+    time tiles, collector/ppo.rs:82-92 per episode); TWISTERL_B200_SPLIT_GAE=1 runs the stand-alone GAE kernel and the
+    plain compaction instead.  Every array must be identical, bit for bit (both are held to the oracle by the replays)."""
+    import twisterl_b200 as tw
+    from parity import make_policies
+    pol, _ = make_policies(synth_state_dict(5, 256, 512, 256, 4), 256)
+    env = tw.env.Puzzle(4, 4, difficulty, 2, 256)
+    col = tw.collector.PPOCollector(E, 0.97, 0.9, 32, engine=eng)
+    out = []
+    for split in (False, True):
+        monkeypatch.delenv("TWISTERL_B200_SPLIT_GAE", raising=False)
+        if split:
+            monkeypatch.setenv("TWISTERL_B200_SPLIT_GAE", "1")
+        eng.set_collect_id(4)
+        out.append(col.collect(env, pol))
+    a, b = out
+    assert len(a.values_array) == len(b.values_array) and len(a.values_array) > E
+    for f in ("obs_array", "logits_array", "values_array", "rewards_array", "actions_array", "perms_array", "ep_len"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    for k in ("advs", "rets"):
+        assert np.array_equal(a.additional_array(k), b.additional_array(k)), k
+    pol.release()
+
+
 @pytest.mark.parametrize("E,difficulty,chunk,trained", [(65536, 128, None, False), (60000, 6, "8", True), (57100, 20, "5", False),
                                                         (45000, 40, None, False), (38400, 24, "6", True)])     # the last two: two own groups per pair
 def test_collect_balanced_schedule_matches_plain(eng, monkeypatch, E, difficulty, chunk, trained):

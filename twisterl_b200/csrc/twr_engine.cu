@@ -1015,12 +1015,14 @@ static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev&
         }
     }
     *n_fwd_out = n_fwd;
-    launch_gae_time_major(st, b, gamma, lambda);
+    // GAE rides on the compaction (one pass over the records); TWISTERL_B200_SPLIT_GAE=1 keeps the two stand-alone kernels
+    const bool split_gae = getenv("TWISTERL_B200_SPLIT_GAE") != nullptr;
+    if (split_gae) launch_gae_time_major(st, b, gamma, lambda);
     launch_episode_offsets(st, b, ids);
     // only the compaction writes the output set: a pipelined caller's "its previous copy is done" event is awaited here,
     // not in front of the rollout
     if (outset_free) CU_TRY(cudaStreamWaitEvent(st, outset_free, 0));
-    launch_compact(st, env, b, dev.A);
+    if (split_gae) launch_compact(st, env, b, dev.A); else launch_compact_gae(st, env, b, dev.A, gamma, lambda);
     CU_TRY(cudaGetLastError());
     FWD_CHECK(e);
     return TWR_OK;

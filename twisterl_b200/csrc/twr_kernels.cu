@@ -352,13 +352,17 @@ struct CompactTiles {
     uint8_t b[2][32][33];
     uint4 q[2][32][33];
 };
-__global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, int A) {
+// FUSE_GAE (the PPO collect): the block walks its 32 episodes' tiles from the LAST time tile to the first and computes
+// advantages and returns on the way (K4b's reverse recursion, one lane of warp 0 per episode, carried across tiles in
+// registers) -- the records are read once, and the time-major adv / ret arrays are neither written nor read: 42 B R + 66 B W
+// per record instead of 16 + 16 (GAE) + 50 + 66.  Same f32 operations in the same order as k_gae_time_major.
+template <bool FUSE_GAE>
+__global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, int A, float gamma, float lambda) {
     extern __shared__ __align__(16) unsigned char compact_smem[];
     CompactTiles& tl = *reinterpret_cast<CompactTiles*>(compact_smem);
     __shared__ int lens[32];
     __shared__ long long offs[32];
     const int64_t e0 = (int64_t)blockIdx.x * 32;
-    const int t0 = blockIdx.y * 32;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     if (tid < 32) {
         const int64_t e = e0 + tid;
@@ -368,7 +372,9 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
     __syncthreads();
     int maxlen = 0;
     for (int i = 0; i < 32; ++i) maxlen = max(maxlen, lens[i]);
-    if (t0 >= maxlen) return;
+    if (maxlen == 0 || (!FUSE_GAE && (int)blockIdx.y * 32 >= maxlen)) return;
+    float g_adv = 0.f, g_vnext = 0.f;          // GAE state of episode threadIdx.x (warp 0), carried from tile to tile
+    for (int t0 = FUSE_GAE ? ((maxlen - 1) / 32) * 32 : (int)blockIdx.y * 32; t0 >= 0; t0 -= 32) {
 
     // ---- load phase: row t of the time-major records, 32 consecutive envs per warp (coalesced)
     {
@@ -384,7 +390,8 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
             ok[it] = e < b.B && t < len;
             if (ok[it]) {
                 const int64_t r = (int64_t)t * b.B + e;
-                vf[it][0] = b.rec_value[r]; vf[it][1] = b.rec_reward[r]; vf[it][2] = b.rec_adv[r]; vf[it][3] = b.rec_ret[r];
+                vf[it][0] = b.rec_value[r]; vf[it][1] = b.rec_reward[r];
+                if (!FUSE_GAE) { vf[it][2] = b.rec_adv[r]; vf[it][3] = b.rec_ret[r]; }
                 vb[it][0] = b.rec_action[r]; vb[it][1] = (uint8_t)b.rec_perm[r];
                 vq[it][0] = reinterpret_cast<const uint4*>(b.rec_logits)[r]; vq[it][1] = b.rec_state[r];
             }
@@ -394,13 +401,27 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
             if (ok[it]) {
                 const int ty = threadIdx.y + 8 * it;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) tl.f[k][ty][threadIdx.x] = vf[it][k];
+                for (int k = 0; k < (FUSE_GAE ? 2 : 4); ++k) tl.f[k][ty][threadIdx.x] = vf[it][k];
                 tl.b[0][ty][threadIdx.x] = vb[it][0]; tl.b[1][ty][threadIdx.x] = vb[it][1];
                 tl.q[0][ty][threadIdx.x] = vq[it][0]; tl.q[1][ty][threadIdx.x] = vq[it][1];
             }
         }
     }
     __syncthreads();
+    if (FUSE_GAE) {
+        if (threadIdx.y == 0) {                  // collector/ppo.rs:82-92, steps t0+nt-1 .. t0 of episode threadIdx.x
+            const int ey = threadIdx.x, len = lens[ey];
+            for (int x = min(32, len - t0) - 1; x >= 0; --x) {
+                const float v = tl.f[0][x][ey], r = tl.f[1][x][ey];
+                float ret;
+                if (t0 + x == len - 1) { g_adv = __fsub_rn(r, v); ret = r; }
+                else gae_step(r, v, g_vnext, g_adv, gamma, lambda, g_adv, ret);
+                tl.f[2][x][ey] = g_adv; tl.f[3][x][ey] = ret;
+                g_vnext = v;
+            }
+        }
+        __syncthreads();
+    }
 
     // ---- store phase: warp `ey` walks episodes ey, ey+8, ..; lane = step inside the tile
     for (int ey = threadIdx.y; ey < 32; ey += blockDim.y) {
@@ -479,6 +500,9 @@ __global__ void __launch_bounds__(256) k_compact(EnvParams p, CollectBuffers b, 
             if (b.obs_u8) dst8[j] = (uint8_t)idx; else dst[j] = (uint16_t)idx;
         }
     }
+    if (!FUSE_GAE) break;
+    __syncthreads();                             // the next (earlier) tile's loads overwrite the tiles
+    }
 }
 
 __global__ void k_publish_stats(const unsigned long long* __restrict__ stats, unsigned long long* __restrict__ mapped_host) {
@@ -492,8 +516,14 @@ void launch_publish_stats(cudaStream_t st, const unsigned long long* stats, unsi
 
 void launch_compact(cudaStream_t st, const EnvParams& p, const CollectBuffers& b, int A) {
     dim3 grid(grid_for(b.B, 32), (unsigned)((b.Tmax + 31) / 32));
-    cudaFuncSetAttribute(k_compact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompactTiles));   // per device: set on every launch
-    k_compact<<<grid, dim3(32, 8), sizeof(CompactTiles), st>>>(p, b, A);
+    cudaFuncSetAttribute(k_compact<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompactTiles));   // per device: set on every launch
+    k_compact<false><<<grid, dim3(32, 8), sizeof(CompactTiles), st>>>(p, b, A, 0.f, 0.f);
+    TWR_COUNT_LAUNCH();
+}
+// K4b + K5 in one pass (see k_compact<true>): the caller does not run launch_gae_time_major
+void launch_compact_gae(cudaStream_t st, const EnvParams& p, const CollectBuffers& b, int A, float gamma, float lambda) {
+    cudaFuncSetAttribute(k_compact<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CompactTiles));
+    k_compact<true><<<dim3(grid_for(b.B, 32)), dim3(32, 8), sizeof(CompactTiles), st>>>(p, b, A, gamma, lambda);
     TWR_COUNT_LAUNCH();
 }
 

@@ -99,6 +99,7 @@ void launch_gae_concat(cudaStream_t s, const float* r, const float* v, const int
 // K5 episode offsets in merged order + transpose/compaction into concatenated episodes
 void launch_episode_offsets(cudaStream_t s, const CollectBuffers& b, const EnvIds& ids);
 void launch_compact(cudaStream_t s, const EnvParams& p, const CollectBuffers& b, int A);
+void launch_compact_gae(cudaStream_t s, const EnvParams& p, const CollectBuffers& b, int A, float gamma, float lambda);   // GAE fused into the compaction
 // the four statistics words of a collect -> mapped pinned host memory (no copy engine involved)
 void launch_publish_stats(cudaStream_t s, const unsigned long long* stats, unsigned long long* mapped_host);
 

@@ -64,7 +64,7 @@ static_assert(SM_TOTAL <= 227 * 1024, "shared memory budget");
 
 enum Bar { B_FULL0 = 0, B_EMPTY0 = NSLOTS, B_A1_FULL = 2 * NSLOTS, B_A1_EMPTY, B_D1_FULL0, B_D1_FULL1,
            B_A2_FULL0, B_A2_FULL1, B_D2_FULL, B_D2_EMPTY, B_COUNT };
-static_assert(B_COUNT * 8 + 8 <= 512, "barrier area");
+static_assert(B_COUNT * 8 + 8 <= 384, "barrier area (the last 128 bytes hold the action twists)");
 
 // ---- cluster / cta_group::2 PTX ----
 // TMA tile load (tensor map over the packed operand image, one box = one 16 KB ring slot) whose completion
@@ -423,6 +423,11 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     for (int i = threadIdx.x; i < t.E; i += NTHREADS) embb[i] = p.emb_b[i];
     if (operm_smem)
         for (int i = threadIdx.x; i < p.n_perms * p.obs_size; i += NTHREADS) operm_s[i] = (uint8_t)p.obs_perms[i];
+    // action twists next to the barriers (the heads look one row up per item)
+    uint8_t* aperm_s = smem + SM_BARS + 384;
+    const bool aperm_smem = p.n_perms > 0 && p.n_perms * p.A <= 128;
+    if (aperm_smem)
+        for (int i = threadIdx.x; i < p.n_perms * p.A; i += NTHREADS) aperm_s[i] = (uint8_t)p.act_perms[i];
     if (warp == 1) {   // both CTAs, same warp id: allocates the same 512 columns in both SMs
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
@@ -713,6 +718,10 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         const long long t_begin = clock64();
         const uint32_t l_a1_full = lbar(B_A1_FULL), l_d2_empty = lbar(B_D2_EMPTY);
         const uint32_t l_a2_full0 = lbar(B_A2_FULL0), l_a2_full1 = lbar(B_A2_FULL1);
+        float ba_r[4];                         // head biases: read once, not once per item
+#pragma unroll
+        for (int o = 0; o < 4; ++o) ba_r[o] = o < p.A ? p.ba[o] : 0.0f;
+        const float bv_r = p.bv[0];
 
         // Global loads of the env state for item `it`, issued early (at the start of the previous item) so
         // their latency is off the critical path of the one-hot build.
@@ -1007,19 +1016,19 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                     acc[0] += o4.x; acc[1] += o4.y; acc[2] += o4.z; acc[3] += o4.w; acc[4] += ps[4];
                     float l[4];
 #pragma unroll
-                    for (int o = 0; o < 4; ++o) l[o] = o < p.A ? acc[o] + p.ba[o] : 0.0f;
+                    for (int o = 0; o < 4; ++o) l[o] = o < p.A ? acc[o] + ba_r[o] : 0.0f;
 #pragma unroll
                     for (int o = 0; o < 4; ++o) cur.out[o] = l[o];
                     if (perm_cur >= 0) {                               // twist-out, nn/policy.rs:95-97
 #pragma unroll
                         for (int o = 0; o < 4; ++o) {
                             if (o < p.A) {
-                                const int src = p.act_perms[perm_cur * p.A + o];
+                                const int src = aperm_smem ? (int)aperm_s[perm_cur * p.A + o] : p.act_perms[perm_cur * p.A + o];
                                 cur.out[o] = src == 0 ? l[0] : src == 1 ? l[1] : src == 2 ? l[2] : l[3];
                             }
                         }
                     }
-                    cur.value = acc[4] + p.bv[0];
+                    cur.value = acc[4] + bv_r;
                 }
                 if (defer && it + 1 < n_items) {
                     sv = cur;                                          // runs inside the next iteration

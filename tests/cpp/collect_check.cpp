@@ -1,6 +1,6 @@
 // Runs one PPO collect and one evaluate through the C++ host side (include/twisterl_b200.hpp) and dumps the result;
 // tests/test_cpp_host.py compares the dump with the Python mirror's collect on the same Philox streams.
-//   collect_check <weights.bin> <out.bin> <precision 0|1> <seed> <collect_id> <episodes> <difficulty>
+//   collect_check <weights.bin> <out.bin> <precision 0..3 = twr_precision> <seed> <collect_id> <episodes> <difficulty>
 // weights.bin: float32 [256*512 emb rows][512 emb bias][512*256 W1.T][256 b1][256*4 Wa.T][4 ba][256 Wv.T][1 bv]
 #include "twisterl_b200.hpp"
 
@@ -23,7 +23,7 @@ int main(int argc, char** argv) {
         w.value_net.push_back(twisterl::Linear{rd(256), rd(1), false});
         std::fclose(f);
 
-        twisterl::Engine eng(0, std::atoi(argv[3]) ? TWR_PREC_F16X2 : TWR_PREC_FP32, std::strtoull(argv[4], nullptr, 0));
+        twisterl::Engine eng(0, static_cast<twr_precision>(std::atoi(argv[3])), std::strtoull(argv[4], nullptr, 0));
         twisterl::Policy policy(eng, w);
         const twr_env_spec env = twisterl::Puzzle(4, 4, std::atoi(argv[7]), 2, 256);
         twisterl::PPOCollector collector((size_t)std::atoll(argv[6]), 0.995f, 0.995f, 32);

@@ -829,16 +829,17 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         };
 
         // fp8 variant: four features -> two fp16 pairs and ONE word of four e5m2 residues (feature k at byte k, the K order
-        // of an 8-bit A operand in tensor memory)
+        // of an 8-bit A operand in tensor memory).  ReLU costs nothing here: hi = fp16(relu(x)) rounded TOWARD ZERO
+        // (cvt.rz.relu), so the residue x - hi is >= 0 wherever x >= 0, and the relu of the residue's own conversion
+        // (cvt.rn.satfinite.relu.e5m2x2) zeroes exactly the lanes with x < 0 (hi = 0, residue = x < 0).
         auto split4 = [](float x0, float x1, float x2, float x3, uint32_t& hi01, uint32_t& hi23, uint32_t& lo) {
-            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
-            const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
-            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            const uint32_t l01 = __nv_cvt_float2_to_fp8x2(make_float2((x0 - f01.x) * H1LO8_SCALE, (x1 - f01.y) * H1LO8_SCALE), __NV_SATFINITE, __NV_E5M2);
-            const uint32_t l23 = __nv_cvt_float2_to_fp8x2(make_float2((x2 - f23.x) * H1LO8_SCALE, (x3 - f23.y) * H1LO8_SCALE), __NV_SATFINITE, __NV_E5M2);
-            hi01 = *reinterpret_cast<const uint32_t*>(&h01);
-            hi23 = *reinterpret_cast<const uint32_t*>(&h23);
-            lo = l01 | (l23 << 16);
+            asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi01) : "f"(x1), "f"(x0));     // first source -> upper half
+            asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi23) : "f"(x3), "f"(x2));
+            const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&hi01)), f23 = __half22float2(*reinterpret_cast<const __half2*>(&hi23));
+            uint16_t l01, l23;
+            asm("cvt.rn.satfinite.relu.e5m2x2.f32 %0, %1, %2;" : "=h"(l01) : "f"((x1 - f01.y) * H1LO8_SCALE), "f"((x0 - f01.x) * H1LO8_SCALE));
+            asm("cvt.rn.satfinite.relu.e5m2x2.f32 %0, %1, %2;" : "=h"(l23) : "f"((x3 - f23.y) * H1LO8_SCALE), "f"((x2 - f23.x) * H1LO8_SCALE));
+            lo = (uint32_t)l01 | ((uint32_t)l23 << 16);
         };
 
         // the next item's one-hot operand is normally built BEFORE this item's heads (so its GEMM1 overlaps

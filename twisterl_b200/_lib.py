@@ -98,10 +98,11 @@ def load():
             import warnings
             warnings.warn(f"twisterl_b200: sources are newer than {LIB_PATH.name} and the rebuild failed ({exc}); "
                           "loading the existing library (its ABI version is checked)", RuntimeWarning)
+        path = os.environ.get("TWISTERL_B200_LIB") or str(LIB_PATH)      # a specific build (A/B runs of kernel variants)
         try:
-            L = C.CDLL(str(LIB_PATH))
+            L = C.CDLL(path)
         except OSError as exc:
-            raise ImportError(f"twisterl_b200: cannot load {LIB_PATH}: {exc} (there is no CPU fallback)") from exc
+            raise ImportError(f"twisterl_b200: cannot load {path}: {exc} (there is no CPU fallback)") from exc
         if int(L.twr_abi_version()) != ABI_VERSION:
             raise ImportError(f"twisterl_b200: {LIB_PATH} has ABI version {int(L.twr_abi_version())}, this package binds "
                               f"version {ABI_VERSION}: rebuild with `python -m twisterl_b200.build --force`")

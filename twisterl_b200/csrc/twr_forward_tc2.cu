@@ -726,9 +726,14 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         // Global loads of the env state for item `it`, issued early (at the start of the previous item) so
         // their latency is off the critical path of the one-hot build.
         struct Pre { int64_t pos; int64_t e; uint4 c; int step; };
-        auto prefetch = [&](int it) -> Pre {
-            int group, step, extra;
-            sched_item(sch, pair_id, it, group, step, extra);
+        // (group, step, extra) of items it-1, it, it+1: sched_item divides by run-time values, so every item is resolved ONCE
+        // per thread (at the end of the iteration two before it) instead of once per use
+        struct Ent { int group, step, extra; };
+        Ent e_prev{0, 0, 0}, e_cur{0, 0, 0}, e_next{0, 0, 0};
+        sched_item(sch, pair_id, 0, e_cur.group, e_cur.step, e_cur.extra);
+        if (n_items > 1) sched_item(sch, pair_id, 1, e_next.group, e_next.step, e_next.extra);
+        auto prefetch = [&](const Ent& en) -> Pre {
+            const int group = en.group, step = en.step, extra = en.extra;
             // first step of a piece whose earlier steps ran on another pair: wait until both of its CTAs published them
             if (extra == 1 && step == sch.sA0 && sch.sA0 > 0) wait_handoff(a.bal_flags + sch.gA, 2 * sch.sA0);
             Pre q; q.pos = ((int64_t)group * 2 + crank) * TM + row; q.e = 0; q.c = make_uint4(0, 0, 0, 0); q.step = step;
@@ -924,7 +929,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         sv.valid = false; sv.pos = 0; sv.step = 0; sv.group = 0; sv.extra = 0; sv.perm = -1; sv.value = 0.f;
         sv.out[0] = sv.out[1] = sv.out[2] = sv.out[3] = 0.f;
 
-        if (chalf == 1) perm_next = build_a1(0, prefetch(0));          // the upper-half warps own the one-hot operand
+        if (chalf == 1) perm_next = build_a1(0, prefetch(e_cur));      // the upper-half warps own the one-hot operand
         for (int it = 0; it < n_items; ++it) {
             Pre pre_next; pre_next.pos = 0; pre_next.e = 0; pre_next.c = make_uint4(0, 0, 0, 0); pre_next.step = 0;
             int c_done = 0;
@@ -934,15 +939,9 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 // when item it-1 IS that earlier item do the upper-half threads have to wait (barrier 3) for the step the
                 // lower half runs right now -- otherwise their loads go out at once and the one-hot build of item it+1 does
                 // not queue behind a 5k-cycle step it does not depend on.
-                bool dep = false;
-                if (it >= 1 && it + 1 < n_items) {
-                    int g0, g1, s0, s1, x0, x1;
-                    sched_item(sch, pair_id, it - 1, g0, s0, x0);
-                    sched_item(sch, pair_id, it + 1, g1, s1, x1);
-                    dep = g0 == g1;
-                }
+                const bool dep = it >= 1 && it + 1 < n_items && e_prev.group == e_next.group;
                 for (; c_done < 2 && c_done < NC; ++c_done) epi1(it, c_done);
-                if (chalf == 1 && it + 1 < n_items && !dep) pre_next = prefetch(it + 1);
+                if (chalf == 1 && it + 1 < n_items && !dep) pre_next = prefetch(e_next);
                 if (chalf == 0 && sv.valid) {                          // step of item it-1
                     if (threadIdx.x == 64) stamp(it, 23);
                     run_step(sv);
@@ -952,13 +951,13 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 }
                 if (chalf == 1 && dep) {
                     asm volatile("bar.sync 3, %0;" ::"n"(NEPI) : "memory");
-                    pre_next = prefetch(it + 1);
+                    pre_next = prefetch(e_next);
                 }
             } else if (build_early && chalf == 1 && it + 1 < n_items) {
                 // with >= 2 tiles per pair, item it+1's env state was last written by the fused step of item
                 // it+1-my_tiles <= it-1 (lower-half threads); barrier 3 orders that step before these loads
                 if (t_count > 1 && it >= 1) asm volatile("bar.sync 3, %0;" ::"n"(NEPI) : "memory");
-                pre_next = prefetch(it + 1);
+                pre_next = prefetch(e_next);
             }
             for (; c_done < NC; ++c_done) epi1(it, c_done);
             // ---- next tile's one-hot operand, so its GEMM1 overlaps this tile's heads
@@ -1005,7 +1004,7 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             if (threadIdx.x == 64) stamp(it, 26);
             if (chalf == 0) {                                          // warp-uniform: whole warps take this branch
                 Saved cur;
-                sched_item(sch, pair_id, it, cur.group, cur.step, cur.extra);
+                cur.group = e_cur.group; cur.step = e_cur.step; cur.extra = e_cur.extra;
                 cur.pos = ((int64_t)cur.group * 2 + crank) * TM + row;
                 cur.valid = true;
                 cur.out[0] = cur.out[1] = cur.out[2] = cur.out[3] = 0.f;
@@ -1041,8 +1040,10 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             }
             if (!build_early && it + 1 < n_items) {                    // single tile per pair: the next item is these envs one step later
                 asm volatile("bar.sync 2, %0;" ::"n"(NEPI) : "memory");  // their fused env step (lower-half threads) is done
-                if (chalf == 1) perm_next = build_a1(it + 1, prefetch(it + 1));
+                if (chalf == 1) perm_next = build_a1(it + 1, prefetch(e_next));
             }
+            e_prev = e_cur; e_cur = e_next;
+            if (it + 2 < n_items) sched_item(sch, pair_id, it + 2, e_next.group, e_next.step, e_next.extra);
             if (timed) c_epi2 += clock64() - t_e2;
             if (threadIdx.x == 64) stamp(it, 19);
         }

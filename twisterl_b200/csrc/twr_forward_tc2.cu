@@ -414,10 +414,10 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
     }
     for (int i = threadIdx.x; i < (MAX_KB1 + (F8 ? A8_TILES : 0)) * TILE_BYTES / 16; i += NTHREADS)   // A8 follows A1
         reinterpret_cast<uint4*>(smem + SM_A1)[i] = make_uint4(0, 0, 0, 0);
+    // head weights as five rows [output][column] (4 actions, value): the heads read four columns of one output per load
     for (int i = threadIdx.x; i < H; i += NTHREADS) {
-        float* w = headw + i * 8;
-        for (int o = 0; o < 4; ++o) w[o] = o < p.A ? p.wa[(size_t)i * p.A + o] : 0.0f;
-        w[4] = p.wv[i]; w[5] = 0.f; w[6] = 0.f; w[7] = 0.f;
+        for (int o = 0; o < 4; ++o) headw[o * H + i] = o < p.A ? p.wa[(size_t)i * p.A + o] : 0.0f;
+        headw[4 * H + i] = p.wv[i];
         b1s[i] = p.b1[i];
     }
     for (int i = threadIdx.x; i < t.E; i += NTHREADS) embb[i] = p.emb_b[i];
@@ -981,15 +981,22 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 tc_ld32(tmem + lane_addr + D2_COL + col0 + 32u, v1);
                 tc_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                    const int col = (int)col0 + j;
-                    float h = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]) + b1s[col];
-                    h = fmaxf(h, 0.f);
-                    const float4 w0 = *reinterpret_cast<const float4*>(headw + col * 8);
-                    const float w4 = headw[col * 8 + 4];
-                    acc[0] = fmaf(h, w0.x, acc[0]); acc[1] = fmaf(h, w0.y, acc[1]);
-                    acc[2] = fmaf(h, w0.z, acc[2]); acc[3] = fmaf(h, w0.w, acc[3]);
-                    acc[4] = fmaf(h, w4, acc[4]);
+                for (int j4 = 0; j4 < 16; ++j4) {
+                    const int col = (int)col0 + 4 * j4;
+                    const float4 bb = *reinterpret_cast<const float4*>(b1s + col);
+                    float h[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j = 4 * j4 + k;
+                        h[k] = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
+                    }
+                    h[0] = fmaxf(h[0] + bb.x, 0.f); h[1] = fmaxf(h[1] + bb.y, 0.f); h[2] = fmaxf(h[2] + bb.z, 0.f); h[3] = fmaxf(h[3] + bb.w, 0.f);
+#pragma unroll
+                    for (int o = 0; o < 5; ++o) {                      // same column order per output as before
+                        const float4 w = *reinterpret_cast<const float4*>(headw + o * H + col);
+                        acc[o] = fmaf(h[0], w.x, acc[o]); acc[o] = fmaf(h[1], w.y, acc[o]);
+                        acc[o] = fmaf(h[2], w.z, acc[o]); acc[o] = fmaf(h[3], w.w, acc[o]);
+                    }
                 }
             }
             tc_fence_before();

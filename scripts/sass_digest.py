@@ -7,7 +7,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 LIB = ROOT / "twisterl_b200" / "lib" / "libtwisterl_b200.so"
 sass = subprocess.run(["cuobjdump", "-sass", str(LIB)], capture_output=True, text=True).stdout
-ops = ["UTCHMMA.2CTA", "UTCHMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "UTCBAR", "SYNCS", "HMMA", "FFMA", "LDG", "STG", "ATOM", "RED"]
+ops = ["UTCHMMA.2CTA", "UTCHMMA", "UTCQMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "UTCBAR", "SYNCS", "HMMA", "FFMA", "LDG", "STG", "ATOM", "RED"]
 counts, total, fn = collections.defaultdict(collections.Counter), collections.Counter(), None
 for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -25,7 +25,8 @@ for line in sass.splitlines():
         if op.startswith("UTCHMMA") and ".2CTA" not in op:
             pass
 out = ["# SASS digest of twisterl_b200/lib/libtwisterl_b200.so (cuobjdump -sass, sm_100a)", "",
-       "`UTCHMMA` = tcgen05.mma (`.2CTA` = cta_group::2; counted in both columns), `LDTM`/`STTM` = tcgen05.ld/st, `UTMALDG` = tensor-map TMA,",
+       "`UTCHMMA` = tcgen05.mma kind::f16 (`.2CTA` = cta_group::2; counted in both columns), `UTCQMMA` = tcgen05.mma kind::f8f6f4 (the fp8 correction products of `f16f8c`),",
+       "`LDTM`/`STTM` = tcgen05.ld/st, `UTMALDG` = tensor-map TMA,",
        "`UBLKCP` = cp.async.bulk, `UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier ops, `HMMA` = legacy mma.sync (must be 0).", "",
        "| kernel | instrs | " + " | ".join(ops) + " |", "|---|---|" + "---|" * len(ops)]
 for fn in sorted(total, key=lambda f: -total[f]):

@@ -935,14 +935,16 @@ static int enqueue_collect(twr_engine* e, const EnvParams& env, const PolicyDev&
     if (fused) {
         // Persistent chunks: one launch covers `chunk` consecutive steps of every tile (envs stay with their
         // CTA pair, finished envs idle), then the live list is re-compacted.  Short episodes use chunk 1.
-        int chunk = T / 8 < 1 ? 1 : (T / 8 > 32 ? 32 : T / 8);
+        // (ceil(T / 8), ceil(T / 2): T = horizon + 1 is odd for even horizons, and a trailing 1-step launch costs 160 us
+        // where a step inside a persistent launch costs 45)
+        int chunk = (T + 7) / 8 > 64 ? 64 : (T + 7) / 8;
         // Adaptive: when the previous collect of this (env, batch) shape kept >= 90 % of its envs alive past half of the
         // horizon, compacting every T/8 steps buys nothing and the launches are made 4x longer (results are identical
         // for any chunking; a policy that starts to finish early flips the hint back after one collect)
         e->hint_key = hint_key_of(env, B);
         {
             auto it = e->survive_half.find(e->hint_key);
-            if (it != e->survive_half.end() && it->second >= 0.9f) chunk = T / 2 < 1 ? 1 : (T / 2 > 128 ? 128 : T / 2);
+            if (it != e->survive_half.end() && it->second >= 0.9f) chunk = (T + 1) / 2 > 256 ? 256 : (T + 1) / 2;
         }
         if (const char* c = getenv("TWISTERL_B200_CHUNK")) { const int v = atoi(c); if (v >= 1) chunk = v; }
         int ci_half = -1;

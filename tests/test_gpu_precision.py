@@ -100,3 +100,33 @@ def test_precision_ladder_on_trained_weights():
     l8e, v8e = forward_batch(e8, pol8, b8)
     assert np.array_equal(l8e, l8) and np.array_equal(v8e, v8)
     pol.release(); pol16.release(); pol8.release(); eng.close(); e16.close(); e8.close()
+
+
+@pytest.mark.parametrize("emb_scale,w_scale", [(8.0, 1.0), (1.0, 8.0), (30.0, 4.0), (200.0, 1.0), (0.05, 1.0)])
+def test_fp8_corrections_track_fp16_corrections_across_weight_scales(emb_scale, w_scale):
+    """The fp8 correction products of `f16f8c` use fixed power-of-two scales (table residue x 2^14 in e4m3, activation
+    residue x 2^6 in e5m2, W x 2^-6 in e5m2, all conversions saturating).  Whatever the magnitude of the weights -- hidden
+    activations from 0.1 to ~200 here -- the result must stay finite and within a few per cent of `f16x2w16`, whose grade is
+    set by the ONE fp16 term of W, not by the corrections (scripts/precision_scale_sweep.py prints the same table)."""
+    import twisterl_b200 as tw
+    from parity import make_policies
+    from twisterl_b200 import _lib
+    from twisterl_b200.env import EnvBatch
+    from twisterl_b200.nn import forward_batch
+    from helpers import synth_state_dict
+    sd = synth_state_dict(3, 256, 512, 256, 4)
+    sd["embeddings.weight"] = (sd["embeddings.weight"] * emb_scale).astype(np.float32)
+    sd["common.0.weight"] = (sd["common.0.weight"] * w_scale).astype(np.float32)
+    st = scramble_states(np.random.default_rng(2), 2048, 4, 4, 200)
+    rl, rv = _f64_reference(sd, obs_from_states(st))
+    spec = _lib.EnvSpec(0, 4, 4, 1, 2, 256)
+    errs = {}
+    for prec in ("f16x2w16", "f16f8c"):
+        eng = tw.Engine(device=0, precision=prec, seed=1)
+        pol, _ = make_policies(sd, 256)
+        b = EnvBatch(spec, len(st), eng); b.set_state(st)
+        l, v = forward_batch(eng, pol, b)
+        assert np.isfinite(l).all() and np.isfinite(v).all()
+        errs[prec] = max(_err(l, rl), _err(v, rv))
+        pol.release(); eng.close()
+    assert errs["f16f8c"] <= 1.15 * errs["f16x2w16"] + 2e-5, errs

@@ -175,7 +175,10 @@ class Policy:
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().orc_policy_free(self._h)
+            try:
+                lib().orc_policy_free(self._h)
+            except Exception:                      # interpreter shutdown: module globals are already gone
+                pass
             self._h = None
 
     def set_embedding(self, vectors, bias, apply_relu=True, obs_shape=None, conv_dim=0):

@@ -367,8 +367,28 @@ static int expand_conv1d(const twr_policy_desc* d, twr_policy_desc* out, std::ve
     return TWR_OK;
 }
 
+// PolicyDev::tc_fold: N when obs_size = N * N and every twist maps each block of N rows onto a block (all blocks hit once)
+static int fold_block(const twr_policy_desc* d) {
+    int N = 1;
+    while ((N + 1) * (N + 1) <= d->obs_size) ++N;
+    if (N * N != d->obs_size || N > TWR_MAX_CELLS) return 0;
+    for (int q = 0; q < d->n_perms; ++q) {
+        const int32_t* pm = d->obs_perms + (size_t)q * d->obs_size;
+        uint64_t seen = 0;
+        for (int c = 0; c < N; ++c) {
+            const int tb = pm[c * N] / N;
+            for (int v = 1; v < N; ++v)
+                if (pm[c * N + v] / N != tb) return 0;
+            if (tb < 0 || tb >= N || ((seen >> tb) & 1ull)) return 0;
+            seen |= 1ull << tb;
+        }
+    }
+    return N;
+}
+
 static int upload_policy(twr_policy* p, const twr_policy_desc* d) {
     twr_engine* e = p->eng;
+    p->dev.tc_fold = p->tc_pack && !p->dev.generic ? fold_block(d) : 0;
     const int E = d->emb_size, A = d->action_net[d->n_action - 1].out;
     const std::vector<const twr_linear_desc*> lins = all_linears(d);
     bool same = d->obs_size == p->dev.obs_size && E == p->dev.E && A == p->dev.A && d->n_perms == p->dev.n_perms &&
@@ -763,6 +783,13 @@ int twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* ob
     if (perm_idx)
         for (int64_t i = 0; i < n; ++i)
             if (perm_idx[i] < -1 || perm_idx[i] >= p->dev.n_perms) return fail(TWR_ERR_INVALID, "perm_idx out of range");
+    // one index per block of tc_fold rows? (then the bias-folded f16f8c image applies to these observations too)
+    bool blocks = p->dev.tc_fold > 0 && n_obs == p->dev.tc_fold;
+    for (int64_t i = 0; blocks && i < n; ++i) {
+        uint64_t seen = 0;
+        for (int a2 = 0; a2 < n_obs; ++a2) seen |= 1ull << (obs[i * n_obs + a2] / p->dev.tc_fold);
+        blocks = seen == (n_obs >= 64 ? ~0ull : (1ull << n_obs) - 1);
+    }
     bool multiset = false;                   // the one-hot GEMM operand cannot express a repeated index: fp32 kernel then
     if (p->dev.tc_pack) {
         for (int64_t i = 0; i < n && !multiset; ++i)
@@ -785,7 +812,7 @@ int twr_policy_forward_obs(twr_engine* e, const twr_policy* p, const int32_t* ob
     ForwardArgs a{};
     a.env.N = n_obs; a.seed = e->seed; a.t = -1;
     a.perm_idx = perm_idx ? d_perm.d : nullptr;
-    a.obs_rows = d_obs.d; a.n = n;
+    a.obs_rows = d_obs.d; a.n = n; a.obs_blocks = blocks ? 1 : 0;
     a.logits = d_logits.d; a.values = d_values.d;
     launch_forward(e, dev, a);
     CU_TRY(cudaGetLastError());

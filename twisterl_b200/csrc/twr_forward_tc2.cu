@@ -162,7 +162,7 @@ __host__ __device__ __forceinline__ uint32_t tile_off8(uint32_t row, uint32_t k)
 // for table row (k / 4) * cN + (k % 4); the other obs_size - 4 * cN rows are unreachable (lib.rs:74-81: cell values 0..3)
 // f8 = 1: the operand image of the fp8-correction variant (it follows the standard image in the same buffer, row0 = its
 // first tensor-map row); NKB8 = k-blocks of 128 of the one-byte one-hot operand
-struct Tc2Params { int NC, NKB1, E, H, cN, f8, NKB8, row0; };
+struct Tc2Params { int NC, NKB1, E, H, cN, f8, NKB8, row0, fold; };
 __host__ __device__ inline size_t slots_g1(const Tc2Params& t) { return t.f8 ? (size_t)(t.NC / 2) * (t.NKB1 + t.NKB8) : (size_t)t.NC * t.NKB1; }
 __host__ __device__ inline size_t slots_g2(const Tc2Params& t) { return t.f8 ? (size_t)t.NC * (t.H == 256 ? 3 : 2) : (size_t)t.NC * (t.H == 256 ? 4 : 2); }
 __host__ __device__ inline size_t slots_per_rank(const Tc2Params& t) { return slots_g1(t) + slots_g2(t); }
@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(256) k_tc2_pack8(PolicyDev p, Tc2Params t, uns
             const int f = last ? (2 * sc + (int)(row >> 6)) * 128 + r * 64 + (int)(row & 63u) : (2 * sc + r) * 128 + (int)row;
             int k = is8 ? kb * 128 + (int)kk : kb * 64 + (int)kk;
             if (t.cN > 0) k = (k >> 2) < t.cN ? (k >> 2) * t.cN + (k & 3) : p.obs_size;
-            const float x = k < p.obs_size ? p.emb[(size_t)k * p.E + f] : 0.0f;
+            // PolicyDev::tc_fold: the embedding bias rides on the rows of block 0 (exactly one of them is in every observation)
+            const float x = k < p.obs_size ? p.emb[(size_t)k * p.E + f] + (k < t.fold ? p.emb_b[f] : 0.0f) : 0.0f;
             const __half hi = __float2half_rn(x);
             if (is8) dst[tile_off8(row, kk)] = (unsigned char)__nv_cvt_float_to_fp8((x - __half2float(hi)) * TABLE8_SCALE, __NV_SATFINITE, __NV_E4M3);
             else *reinterpret_cast<__half*>(dst + tile_off(row, kk)) = hi;
@@ -354,7 +355,7 @@ __device__ __forceinline__ void wait_handoff(const int32_t* flag, int target) {
 // 3 = f16x2w16) or -1 = taken from ForwardArgs::tc_terms at run time (precision ladder / debugging).  Both are template
 // parameters because ONE thread issues every MMA: its loops must unroll to straight-line descriptor arithmetic, or the
 // issue rate, not the tensor pipe, bounds the kernel (measured: runtime trip counts cost 13 % of the whole collect).
-template <int HT, int TERMS>
+template <int HT, int TERMS, bool FOLD = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -867,18 +868,23 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 const float* bias = embb + c * 128 + chalf * 64;
                 uint32_t w[32];
                 if constexpr (F8) {
+                    // accumulator + embedding bias; with the bias folded into the operand image the accumulator is the sum
+                    // (x + 0.0f would not do: the compiler must keep an add that turns -0.0 into +0.0)
+                    auto addb = [&](uint32_t v, const float& b) -> float {
+                        if constexpr (FOLD) return __uint_as_float(v); else return __uint_as_float(v) + b;
+                    };
 #pragma unroll
                     for (int e4 = 0; e4 < 8; ++e4)
-                        split4(__uint_as_float(v0[4 * e4]) + bias[4 * e4], __uint_as_float(v0[4 * e4 + 1]) + bias[4 * e4 + 1],
-                               __uint_as_float(v0[4 * e4 + 2]) + bias[4 * e4 + 2], __uint_as_float(v0[4 * e4 + 3]) + bias[4 * e4 + 3],
+                        split4(addb(v0[4 * e4], bias[4 * e4]), addb(v0[4 * e4 + 1], bias[4 * e4 + 1]),
+                               addb(v0[4 * e4 + 2], bias[4 * e4 + 2]), addb(v0[4 * e4 + 3], bias[4 * e4 + 3]),
                                w[2 * e4], w[2 * e4 + 1], w[16 + e4]);
 #pragma unroll
                     for (int e4 = 24; e4 < 32; ++e4) w[e4] = 0u;
                     tc_st32(taddr, w);
 #pragma unroll
                     for (int e4 = 0; e4 < 8; ++e4)
-                        split4(__uint_as_float(v1[4 * e4]) + bias[32 + 4 * e4], __uint_as_float(v1[4 * e4 + 1]) + bias[32 + 4 * e4 + 1],
-                               __uint_as_float(v1[4 * e4 + 2]) + bias[32 + 4 * e4 + 2], __uint_as_float(v1[4 * e4 + 3]) + bias[32 + 4 * e4 + 3],
+                        split4(addb(v1[4 * e4], bias[32 + 4 * e4]), addb(v1[4 * e4 + 1], bias[32 + 4 * e4 + 1]),
+                               addb(v1[4 * e4 + 2], bias[32 + 4 * e4 + 2]), addb(v1[4 * e4 + 3], bias[32 + 4 * e4 + 3]),
                                w[2 * e4], w[2 * e4 + 1], w[16 + e4]);
                     tc_st32(taddr + 32u, w);
                 } else {
@@ -1074,10 +1080,11 @@ Tc2Params make_params2(const PolicyDev& p, bool f8 = false) {
     t.E = p.E; t.H = p.H; t.NC = p.E / 128; t.cN = p.tc_compact_n;
     t.NKB1 = ((p.tc_compact_n > 0 ? 4 * p.tc_compact_n : p.obs_size) + 63) / 64;
     t.NKB8 = (t.NKB1 + 1) / 2;
-    t.f8 = 0; t.row0 = 0;
-    if (f8) {                                   // the fp8-correction image follows the standard one
+    t.f8 = 0; t.row0 = 0; t.fold = 0;
+    if (f8) {                                   // the fp8-correction image follows the standard one; it carries the folded bias
         t.row0 = (int)((size_t)NCOPIES * 2 * slots_per_rank(t) * (TILE_BYTES / 128));
         t.f8 = 1;
+        t.fold = p.tc_fold;
     }
     return t;
 }
@@ -1160,7 +1167,8 @@ bool forward_tc2_prepare(const PolicyDev& p, const void* pack) {
     if (!get_tmap(*d, pack, forward_tc2_pack_bytes(p), &tmap)) return false;
     if (!d->attr_set) {
         for (auto k : {k_forward_tc2<256, 7>, k_forward_tc2<256, 3>, k_forward_tc2<256, -1>, k_forward_tc2<128, 7>, k_forward_tc2<128, 3>,
-                       k_forward_tc2<128, -1>, k_forward_tc2<256, 19>, k_forward_tc2<128, 19>})
+                       k_forward_tc2<128, -1>, k_forward_tc2<256, 19>, k_forward_tc2<128, 19>, k_forward_tc2<256, 19, true>,
+                       k_forward_tc2<128, 19, true>})
             if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) != cudaSuccess) return false;
         d->attr_set = true;
     }
@@ -1204,10 +1212,16 @@ bool launch_forward_tc2(cudaStream_t st, const PolicyDev& p, const ForwardArgs& 
     ForwardArgs args = a;
     if (a.bal_flags && max_clusters < grid / 2) { args.bal_flags = nullptr; args.bal_delta = 0; }
     const int terms = a.tc_terms ? (a.tc_terms & 7) : 7;
-    const bool f8 = (a.tc_terms & 16) != 0 && terms == 3;                     // fp8 corrections: only defined for the f16x2w16 terms
+    // fp8 corrections: only defined for the f16x2w16 terms.  A policy whose fp8 image carries the folded embedding bias
+    // (tc_fold) serves observations with one index per block -- every env-driven launch, and explicit rows the host has
+    // checked; anything else takes the same terms with fp16 corrections on the standard image.
+    const bool blocks = a.obs_rows ? a.obs_blocks != 0 : p.n_obs == p.tc_fold;
+    const bool f8 = (a.tc_terms & 16) != 0 && terms == 3 && (p.tc_fold == 0 || blocks);
+    const bool fold = f8 && p.tc_fold > 0;
     const Tc2Params t = make_params2(p, f8);
     auto go = [&](auto kern) { kern<<<grid, NTHREADS, SM_TOTAL, st>>>(p, args, t, tmap); };
-    if (p.H == 256) { if (f8) go(k_forward_tc2<256, 19>); else if (terms == 7) go(k_forward_tc2<256, 7>); else if (terms == 3) go(k_forward_tc2<256, 3>); else go(k_forward_tc2<256, -1>); }
+    if (fold) { if (p.H == 256) go(k_forward_tc2<256, 19, true>); else go(k_forward_tc2<128, 19, true>); }
+    else if (p.H == 256) { if (f8) go(k_forward_tc2<256, 19>); else if (terms == 7) go(k_forward_tc2<256, 7>); else if (terms == 3) go(k_forward_tc2<256, 3>); else go(k_forward_tc2<256, -1>); }
     else            { if (f8) go(k_forward_tc2<128, 19>); else if (terms == 7) go(k_forward_tc2<128, 7>); else if (terms == 3) go(k_forward_tc2<128, 3>); else go(k_forward_tc2<128, -1>); }
     g_twr_launches.fetch_add(1, std::memory_order_relaxed);
     return true;

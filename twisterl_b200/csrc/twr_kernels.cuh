@@ -23,6 +23,11 @@ struct PolicyDev {
     // (row (i, v) = i * tc_compact_n + v, v in 0..3; examples/grid_world/src/lib.rs:74-81,161-163); such a policy takes
     // the tensor-core path only for GridWorld envs of that size whose observation comes from the env state
     int tc_compact_n;
+    // > 0: obs_size = tc_fold^2 and every twist maps each block of tc_fold consecutive rows onto another block, so an
+    // observation that holds exactly ONE index per block (what Puzzle / GridWorld envs produce) selects exactly one row of
+    // block 0 before and after a twist: the f16f8c operand image carries the embedding bias on the rows of block 0 and
+    // the kernel's epilogue-1 skips the bias add (k_forward_tc2<.., .., FOLD>)
+    int tc_fold;
     // General layer stacks: any policy that is not "embedding+ReLU -> one common Linear+ReLU ->
     // single-Linear heads" runs k_forward_generic (twr_forward_generic.cu) from this description instead.
     int generic;                              // 1: the fields above (w1..bv, H) are unused
@@ -110,6 +115,7 @@ struct ForwardArgs {
     const int32_t* perm_idx;  // explicit per-position twist (parity API) or NULL -> Philox pick
     const uint4* cells; const int32_t* live; const int32_t* n_live_ptr; int64_t n;
     const int32_t* obs_rows;  // optional [n][n_obs] sparse obs given directly (Policy.forward API); overrides cells
+    int obs_blocks;           // obs_rows only: every row holds exactly one index per block of PolicyDev::tc_fold rows (checked on the host)
     float4* logits; float* values;
     // fused collect step (k_forward_tc2 only): when `fused` != 0 the epilogue does k_collect_step's work
     int fused; StepArgs step; CollectBuffers cb; int32_t* live_next;

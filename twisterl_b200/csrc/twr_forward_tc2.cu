@@ -981,7 +981,12 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             tc_fence_after();
             if (threadIdx.x == 64) stamp(it, 18);
             const long long t_e2 = timed ? clock64() : 0;
-            float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            // packed fp32 (fma.rn.f32x2 / add.f32x2, sm_100): even and odd columns accumulate in the two halves of a register
+            // pair -- the activations of two adjacent accumulator columns and the two weights of an output's row are
+            // adjacent already -- and are added at the end: 10 FFMA2 + 2 FADD2 instead of 20 FFMA + 4 FADD per four columns
+            float2 acc2[5];
+#pragma unroll
+            for (int o = 0; o < 5; ++o) acc2[o] = make_float2(0.f, 0.f);
 #pragma unroll 1
             for (int q = 0; q < H / 128; ++q) {
                 uint32_t v0[32], v1[32];
@@ -993,21 +998,26 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 for (int j4 = 0; j4 < 16; ++j4) {
                     const int col = (int)col0 + 4 * j4;
                     const float4 bb = *reinterpret_cast<const float4*>(b1s + col);
-                    float h[4];
+                    float hv[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int j = 4 * j4 + k;
-                        h[k] = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
+                        hv[k] = __uint_as_float(j < 32 ? v0[j & 31] : v1[j & 31]);
                     }
-                    h[0] = fmaxf(h[0] + bb.x, 0.f); h[1] = fmaxf(h[1] + bb.y, 0.f); h[2] = fmaxf(h[2] + bb.z, 0.f); h[3] = fmaxf(h[3] + bb.w, 0.f);
+                    float2 h01 = __fadd2_rn(make_float2(hv[0], hv[1]), make_float2(bb.x, bb.y));
+                    float2 h23 = __fadd2_rn(make_float2(hv[2], hv[3]), make_float2(bb.z, bb.w));
+                    h01.x = fmaxf(h01.x, 0.f); h01.y = fmaxf(h01.y, 0.f); h23.x = fmaxf(h23.x, 0.f); h23.y = fmaxf(h23.y, 0.f);
 #pragma unroll
-                    for (int o = 0; o < 5; ++o) {                      // same column order per output as before
+                    for (int o = 0; o < 5; ++o) {
                         const float4 w = *reinterpret_cast<const float4*>(headw + o * H + col);
-                        acc[o] = fmaf(h[0], w.x, acc[o]); acc[o] = fmaf(h[1], w.y, acc[o]);
-                        acc[o] = fmaf(h[2], w.z, acc[o]); acc[o] = fmaf(h[3], w.w, acc[o]);
+                        acc2[o] = __ffma2_rn(h01, make_float2(w.x, w.y), acc2[o]);
+                        acc2[o] = __ffma2_rn(h23, make_float2(w.z, w.w), acc2[o]);
                     }
                 }
             }
+            float acc[5];
+#pragma unroll
+            for (int o = 0; o < 5; ++o) acc[o] = acc2[o].x + acc2[o].y;
             tc_fence_before();
             mbar_arrive_cluster(l_d2_empty);
             float* ps = part_s + ((it & 1) * TM + row) * 8;

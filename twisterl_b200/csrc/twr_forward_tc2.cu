@@ -845,9 +845,11 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi01) : "f"(x1), "f"(x0));     // first source -> upper half
             asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi23) : "f"(x3), "f"(x2));
             const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&hi01)), f23 = __half22float2(*reinterpret_cast<const __half2*>(&hi23));
+            const float2 r01 = __fadd2_rn(make_float2(x0, x1), make_float2(-f01.x, -f01.y));     // packed fp32: two residues per instruction
+            const float2 r23 = __fadd2_rn(make_float2(x2, x3), make_float2(-f23.x, -f23.y));
             uint16_t l01, l23;
-            asm("cvt.rn.satfinite.relu.e5m2x2.f32 %0, %1, %2;" : "=h"(l01) : "f"(x1 - f01.y), "f"(x0 - f01.x));
-            asm("cvt.rn.satfinite.relu.e5m2x2.f32 %0, %1, %2;" : "=h"(l23) : "f"(x3 - f23.y), "f"(x2 - f23.x));
+            asm("cvt.rn.satfinite.relu.e5m2x2.f32 %0, %1, %2;" : "=h"(l01) : "f"(r01.y), "f"(r01.x));
+            asm("cvt.rn.satfinite.relu.e5m2x2.f32 %0, %1, %2;" : "=h"(l23) : "f"(r23.y), "f"(r23.x));
             lo = (uint32_t)l01 | ((uint32_t)l23 << 16);
         };
 

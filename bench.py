@@ -325,7 +325,7 @@ def run_ours(args, rank, local_rank, world):
                          "frac": (achieved / pk["bf16"]) if achieved else None,
                          "traffic": TRAFFIC.get((args.precision, args.episodes)),
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the first (129-step) k_forward_tc2 launch of a collect "
-                                         "(ncu --set full, profiles/r2k_tc2_summary.md); the launch writes its records "
+                                         "(ncu --set full, profiles/r2p_tc2_summary.md); the launch writes its records "
                                          "(42 B x envs x steps), operands stay in L2",
                          "peak_source": pk["src"] + " bf16_tflops_sustained",
                          "forward_ms_per_launch": fwd_ms / max(fwd_launches, 1), "forward_share_of_step": fwd_ms / tm.ms,
@@ -360,8 +360,8 @@ def run_ours(args, rank, local_rank, world):
 
 # dram bytes (read + write) of one steady-state forward launch, from the committed ncu capture of the same command
 # dram__bytes_read.sum + dram__bytes_write.sum of the first persistent launch of a 65 536-env collect (ncu --set full, launch 0
-# of profiles/r2k_tc2_summary.md for f16f8c: 129 steps; of profiles/r2_tc2_summary.md for f16x2w16: 128 steps)
-TRAFFIC = {("f16x2w16", 65536): 3_088_896 + 296_557_568, ("f16f8c", 65536): 3_366_144 + 300_231_936}
+# of profiles/r2p_tc2_summary.md for f16f8c: 129 steps; of profiles/r2_tc2_summary.md for f16x2w16: 128 steps)
+TRAFFIC = {("f16x2w16", 65536): 3_088_896 + 296_557_568, ("f16f8c", 65536): 3_399_680 + 297_932_032}
 
 
 # ------------------------------------------------------------- the other BASELINE configs ---

@@ -768,7 +768,9 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
             // bookkeeping of the previous tile's ones), then set one fp16 1.0 per observation index.
             const uint32_t rx = (uint32_t)row & 7u;
             const uint32_t row_base = ((uint32_t)row >> 3) * 1024u + rx * 128u;
-            const bool fast = a.env.kind == 0 && !a.obs_rows && perm < 0 && n_obs <= 16 && t.cN == 0;   // Puzzle, no twist
+            // Puzzle from the env state, at most 16 cells; a twist is one more byte lookup when its table sits in shared memory
+            const bool fast = a.env.kind == 0 && !a.obs_rows && (perm < 0 || operm_smem) && n_obs <= 16 && t.cN == 0;
+            const uint8_t* otab = perm >= 0 ? operm_s + perm * p.obs_size : nullptr;
             if (threadIdx.x == 192) stamp(it, 20);
             mbar_wait_t(bar(B_A1_EMPTY), (it & 1) ^ 1, w_a1e, timed);      // GEMM1 of the previous item is done with A1
             if (threadIdx.x == 192) stamp(it, 21);
@@ -799,7 +801,8 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
                 for (int i = 0; i < 16; ++i) {
                     if (i < n_obs) {
                         const uint32_t v = (uint32_t)(((i < 8) ? s.lo : s.hi) >> (8 * (i & 7))) & 0xFFu;
-                        const uint32_t r = pos < n ? (uint32_t)(i * a.env.N) + v : 0u;
+                        uint32_t r = pos < n ? (uint32_t)(i * a.env.N) + v : 0u;
+                        if (otab && pos < n) r = otab[r];                                          // twist-in, policy.rs:81-83
                         const uint32_t k = r & 63u;
                         *reinterpret_cast<__half*>(smem + SM_A1 + (r >> 6) * TILE_BYTES + row_base + ((((k >> 3) ^ rx) & 7u) << 4) + (k & 7u) * 2u) =
                             __ushort_as_half(0x3C00);

@@ -7,7 +7,7 @@ import bench
 import twisterl_b200 as tw
 from twisterl_b200 import _lib, collector as twc, nn as twn
 sd = bench.synth_weights()
-eng = tw.Engine(device=0, precision="f16x2w16", seed=0x5EED5EED)
+eng = tw.Engine(device=0, precision=os.environ.get("TWISTERL_B200_PRECISION", "f16f8c"), seed=0x5EED5EED)
 pol = bench.synth_policy(twn, sd, 256)
 env = tw.env.Puzzle(4, 4, 128, 2, 256)
 eng.set_timing(True)

@@ -833,10 +833,16 @@ k_forward_tc2(PolicyDev p, ForwardArgs a, Tc2Params t, const __grid_constant__ C
         // relu(x + bias) -> packed fp16 hi pair / lo pair (x = hi + lo to ~22 bits)
         // ReLU rides on the two conversions (see split4 below): hi = fp16(relu(x)) rounded toward zero, so the residue is
         // >= 0 wherever x is, and the relu of the residue's conversion zeroes exactly the lanes with x < 0
-        auto split2 = [](float x0, float x1, uint32_t& hi, uint32_t& lo) {
-            asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));       // first source -> upper half
-            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-            asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+        // (only when the residue is used: a rung of the precision ladder without the h1_lo term rounds hi to nearest)
+        auto split2 = [g2_alo](float x0, float x1, uint32_t& hi, uint32_t& lo) {
+            if (g2_alo) {
+                asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));   // first source -> upper half
+                const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+                asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+            } else {
+                asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+                lo = 0u;
+            }
         };
 
         // fp8 variant: four features -> two fp16 pairs and ONE word of four e5m2 residues (feature k at byte k, the K order
